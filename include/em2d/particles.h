@@ -1,0 +1,89 @@
+/* zpic-b200 :: em2d particle species (reference em2d/particles.h) */
+#ifndef ZPIC_B200_EM2D_PARTICLES_H
+#define ZPIC_B200_EM2D_PARTICLES_H
+
+#include "zpic.h"
+#include "emf.h"
+#include "current.h"
+#include <stdint.h>
+
+#define MAX_SPNAME_LEN 32
+
+/* host AoS record, 28 bytes, observable from Python as a structured dtype
+ * (reference particles.h:29-37). The device keeps tile-binned SoA arrays; this
+ * record only exists in the host mirror. */
+typedef struct Particle {
+	int ix, iy;
+	float x, y;
+	float ux, uy, uz;
+} t_part;
+
+enum density_type { UNIFORM, EMPTY, STEP, SLAB, CUSTOM };
+
+/* injection profile (reference particles.h:55-78) */
+typedef struct Density {
+	float n;
+	enum density_type type;
+	float start, end;
+	float (*custom_x)(float, void*);
+	void *custom_data_x;
+	float (*custom_y)(float, void*);
+	void *custom_data_y;
+	unsigned long custom_x_total_part;
+	double custom_x_total_q;
+} t_density;
+
+/* species container (reference particles.h:85-132) */
+typedef struct Species {
+	char name[MAX_SPNAME_LEN+1];
+	t_part *part;
+	int np;
+	int np_max;
+	float m_q;
+	double energy;
+	float q;
+	int ppc[2];
+	t_density density;
+	float ufl[3];
+	float uth[3];
+	int nx[2];
+	float dx[2];
+	float box[2];
+	float dt;
+	int iter;
+	int moving_window;
+	int n_move;
+	int n_sort;
+} t_species;
+
+void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
+               const float ufl[], const float uth[],
+               const int nx[], float box[], const float dt, t_density* density );
+void spec_delete( t_species* spec );
+void spec_grow_buffer( t_species* spec, const int size );
+/* device: fused interpolate + Boris + split-segment deposit, boundaries, window,
+ * tile re-binning (reference particles.c:1104-1269) */
+void spec_advance( t_species* spec, t_emf* emf, t_current* current );
+void spec_move_window( t_species *spec );
+uint64_t spec_npush( void );
+double spec_time( void );
+double spec_perf( void );
+
+/* diagnostics selectors (reference particles.h:230-246) */
+#define CHARGE      0x1000
+#define PHA         0x2000
+#define PARTICLES   0x3000
+#define X1          0x0001
+#define X2          0x0002
+#define U1          0x0004
+#define U2          0x0005
+#define U3          0x0006
+#define PHASESPACE(a,b) ((a) + (b)*16 + PHA)
+
+void spec_deposit_pha( const t_species *spec, const int rep_type,
+                       const int pha_nx[], const float pha_range[][2], float* buf );
+void spec_report( const t_species *spec, const int rep_type,
+                  const int pha_nx[], const float pha_range[][2] );
+void spec_deposit_charge( const t_species* spec, float* charge );
+
+#endif

@@ -1,0 +1,168 @@
+/* zpic-b200 :: the device seam (C ABI).
+ *
+ * Everything the host C layer (include/em2d, include/em1d) asks of the GPU goes
+ * through the plain-C entry points below: opaque handles, plain pointers and
+ * sizes, no C++ or torch types.  Each entry point names the reference routine it
+ * replaces (paths relative to the reference tree).  The implementations are
+ * hand-written sm_100a CUDA kernels (zpic_b200/csrc/dev); there is no CPU
+ * fallback: if no CUDA device can be initialised zdev_init() returns non-zero
+ * and the host layer aborts.
+ *
+ * Conventions
+ *  - all grids use the reference guard-cell geometry: (nx+3) x (ny+3) float3
+ *    cells, 1 lower / 2 upper guards, row stride nrow = nx+3 (em2d/emf.c:59-89,
+ *    em2d/current.c:33-53).  Host buffers passed in/out are the *_buf arrays
+ *    (guards included).
+ *  - particle records exchanged with the host are the 28-byte AoS t_part
+ *    (em2d/particles.h:29-37); on the device they live as tile-binned SoA.
+ *  - all work is enqueued on one per-process stream; calls returning data to the
+ *    host synchronise that stream, the others do not.
+ *  - errors: CUDA failures print a message to stderr and exit(-1), the
+ *    reference's own convention for fatal errors (em2d/simulation.c:106-110).
+ */
+#ifndef ZPIC_DEV_H
+#define ZPIC_DEV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ runtime */
+
+/* Select the CUDA device (ordinal, or -1 = $ZPIC_DEVICE / $LOCAL_RANK / 0) and
+ * create the stream.  Idempotent.  Returns 0 on success. */
+int  zdev_init( int device );
+/* 1 once zdev_init succeeded */
+int  zdev_ready( void );
+/* block until all enqueued device work finished */
+void zdev_sync( void );
+/* the cudaStream_t used for every launch (so callers can record events on it) */
+void* zdev_stream( void );
+/* number of kernels launched by this library since load (bench "gpu_launches") */
+uint64_t zdev_launch_count( void );
+/* device-side timers: cudaEvent pairs on the library stream */
+void* zdev_event_create( void );
+void  zdev_event_record( void* ev );
+float zdev_event_elapsed_ms( void* start, void* stop );   /* synchronises on stop */
+void  zdev_event_destroy( void* ev );
+/* free / total device memory in bytes */
+void zdev_mem_info( size_t* free_b, size_t* total_b );
+/* write `bytes` of scratch (>= L2 size) to evict the L2 between timed steps */
+void zdev_flush_l2( void );
+
+/* ---------------------------------------------------------- em2d grids (E,B,J) */
+
+typedef struct zdev_grid2d zdev_grid2d;
+
+enum zdev_fld { ZDEV_E = 0, ZDEV_B = 1, ZDEV_J = 2, ZDEV_EPART = 3, ZDEV_BPART = 4 };
+
+/* emf_new / current_new: a grid object holds zeroed E,B and/or J device buffers, each
+ * allocated on first use, so one object can back a t_emf, a t_current or (as sim_new
+ * arranges) both (em2d/emf.c:56-113, current.c:30-79).  Entry points that combine
+ * fields and currents take the field grid `g` and the current grid `g_cur`, which
+ * may be the same object. */
+zdev_grid2d* zdev_grid2d_create( int nx, int ny );
+/* emf_delete + current_delete (em2d/emf.c:123-142, current.c:86-91) */
+void zdev_grid2d_destroy( zdev_grid2d* g );
+/* host mirror -> device / device -> host mirror, whole buffer incl. guards */
+void zdev_grid2d_upload( zdev_grid2d* g, int which, const float* host_buf );
+void zdev_grid2d_download( zdev_grid2d* g, int which, float* host_buf );
+/* raw device pointer of a grid buffer (cell [-1,-1]); for tests / multi-GPU glue */
+float* zdev_grid2d_ptr( zdev_grid2d* g, int which );
+
+/* current_zero (em2d/current.c:98-107) */
+void zdev_current_zero( zdev_grid2d* g );
+/* current_update = current_update_gc + current_smooth, iter++ left to the host
+ * (em2d/current.c:118-183, 297-459).  xtype/ytype: 0 none, 1 binomial, 2 compensated.
+ * Reproduces the reference quirk that the y passes are counted with xlevel
+ * (current.c:449). */
+void zdev_current_update( zdev_grid2d* g, int moving_window,
+                          int xtype, int ytype, int xlevel, int ylevel );
+/* the two halves separately (multi-GPU inserts halo exchanges between them) */
+void zdev_current_update_gc( zdev_grid2d* g, int moving_window );
+void zdev_current_smooth( zdev_grid2d* g, int moving_window,
+                          int xtype, int ytype, int xlevel, int ylevel );
+
+/* uniform external fields: E_part = E + E0 on every cell incl. guards
+ * (em2d/emf.c:838-914, UNIFORM branch).  type 0 disables (E_part aliases E). */
+void zdev_emf_set_ext_uniform( zdev_grid2d* g, int e_on, const float e0[3],
+                               int b_on, const float b0[3] );
+/* custom external fields evaluated once on the host (callbacks are time independent,
+ * SURVEY.md App. D): host_ext is a full (nx+3)x(ny+3) float3 buffer or NULL */
+void zdev_emf_set_ext_grid( zdev_grid2d* g, const float* host_ext_e, const float* host_ext_b );
+
+/* emf_advance minus iter++ (em2d/emf.c:688-716): yee_b(dt/2), yee_e(dt), yee_b(dt/2),
+ * emf_update_gc, emf_update_part_fld, and - when shift_window != 0 -
+ * emf_move_window's left shift + zeroing (emf.c:648-675).  The host decides
+ * shift_window with the reference's float test (emf.c:650). */
+void zdev_emf_advance( zdev_grid2d* g, zdev_grid2d* g_cur, float dt, float dx, float dy,
+                       int moving_window, int shift_window );
+/* pieces, for kernel-level parity tests */
+void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c:500-522 */
+void zdev_yee_e( zdev_grid2d* g, zdev_grid2d* g_cur, float dt_dx, float dt_dy, float dt );  /* emf.c:531-562 */
+void zdev_emf_update_gc( zdev_grid2d* g, int moving_window );           /* emf.c:573-637 */
+void zdev_emf_move_window( zdev_grid2d* g );                            /* emf.c:659-670 */
+/* emf_get_energy: 6 interior sums of squares in double, scaled by 0.5*dx*dy by the
+ * caller (em2d/emf.c:729-750).  Synchronises. */
+void zdev_emf_energy( zdev_grid2d* g, double sums[6] );
+
+/* ---------------------------------------------------------- em2d particles */
+
+typedef struct zdev_spec2d zdev_spec2d;
+
+/* per-step scalars, computed on the host exactly as the reference does
+ * (em2d/particles.c:1111-1117) */
+typedef struct zdev_push2d_params {
+	float tem;      /* (float)(0.5*dt/m_q), double arithmetic on the host */
+	float dt_dx;    /* dt/dx[0] */
+	float dt_dy;    /* dt/dx[1] */
+	float qnx;      /* q*dx[0]/dt */
+	float qny;      /* q*dx[1]/dt */
+	float q;        /* charge per particle */
+	int   moving_window;  /* 1: absorbing x, periodic y (particles.c:1237-1251) */
+	int   shift_window;   /* 1: all ix-- this step (particles.c:619-632) */
+} zdev_push2d_params;
+
+/* Device species for an nx x ny grid.  ppc_hint = expected particles per cell
+ * (sizes the tiles and their capacity), track_ids != 0 carries the injection index
+ * of every particle so the host mirror can be restored in reference order. */
+zdev_spec2d* zdev_spec2d_create( int nx, int ny, int ppc_hint, int track_ids );
+void zdev_spec2d_destroy( zdev_spec2d* s );
+/* host AoS -> device tiles (replaces the whole population) */
+void zdev_spec2d_upload( zdev_spec2d* s, const void* part_aos, int64_t np );
+/* append host AoS particles (moving-window injection, Species.add) */
+void zdev_spec2d_append( zdev_spec2d* s, const void* part_aos, int64_t np );
+/* device tiles -> host AoS; returns the number written (<= max_np).  With
+ * track_ids and a never-absorbed population the order is the injection order. */
+int64_t zdev_spec2d_download( zdev_spec2d* s, void* part_aos, int64_t max_np );
+/* current particle count (synchronises) */
+int64_t zdev_spec2d_np( zdev_spec2d* s );
+/* uniform-density, thermal+fluid initialisation ON the device with a counter-based
+ * generator: same distribution and per-cell mean removal as spec_set_x/spec_set_u
+ * (em2d/particles.c:85-149, 159-354) but NOT the same random stream.  Used for the
+ * throughput configurations whose host mirrors would not fit (hard part 5). */
+void zdev_spec2d_inject_uniform( zdev_spec2d* s, int ppcx, int ppcy,
+                                 const float ufl[3], const float uth[3], uint64_t seed );
+
+/* spec_advance minus the host bookkeeping (em2d/particles.c:1125-1259):
+ * interpolate_fld (:1029-1071) + Boris push (:1146-1207) + dep_current_zamb
+ * (:773-924) into g_cur's J, then boundaries / window shift and tile re-binning.
+ * Kinetic energy sum (double, unscaled) and the new particle count are left on
+ * the device until zdev_spec2d_fetch(). */
+void zdev_spec2d_advance( zdev_spec2d* s, zdev_grid2d* g, zdev_grid2d* g_cur, const zdev_push2d_params* p );
+/* energy sum of the last advance and current particle count (synchronises).
+ * Also raises the fatal tile-capacity error if a tile overflowed. */
+void zdev_spec2d_fetch( zdev_spec2d* s, double* energy_sum, int64_t* np );
+/* spec_deposit_charge on the device (em2d/particles.c:1289-1324): charge is a host
+ * (nx+1)*(ny+1) float array that is ADDED to, like the reference does */
+void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, float* charge );
+/* tile geometry chosen for this species (cells per tile in x,y; number of tiles) */
+void zdev_spec2d_tile_info( zdev_spec2d* s, int* tx, int* ty, int* ntiles, int64_t* capacity );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,404 @@
+// zpic-b200 :: em2d field and current grids on the device.
+//
+// Layout: identical to the reference host buffers - (nx+3) x (ny+3) AoS float3,
+// guards {1 lower, 2 upper}, row stride nrow = nx+3 (reference em2d/emf.c:59-89,
+// em2d/current.c:33-53) - so host mirrors are straight cudaMemcpy's and the
+// reference loop bounds carry over literally.  All kernels are pure HBM-streaming
+// stencils: one thread per cell, x fastest so a warp touches one contiguous
+// 384-byte span per float3 array.  Compiled with --fmad=false: every expression
+// below keeps the reference's operation order so results are bit-identical.
+#include "zdev_common.cuh"
+
+struct zdev_grid2d {
+	int nx, ny, nrow, nrows;
+	size_t ncell;            // (nx+3)*(ny+3)
+	f3 *E, *B, *J;           // point at buffer start, i.e. cell (-1,-1)
+	f3 *tmp;                 // scratch of the same size (smoothing ping-pong, window shift)
+	f3 *Epart, *Bpart;       // fields seen by particles; alias E/B unless external fields are on
+	f3 *Eext, *Bext;         // cached custom external fields (or null)
+	int e_ext, b_ext;        // 0 none, 1 uniform, 2 grid
+	f3 e0, b0;
+	double* d_sums;          // 6 doubles
+};
+
+// cell (i,j), i in [-1,nx+1], j in [-1,ny+1] -> linear index from buffer start
+__device__ __forceinline__ int cidx(int i, int j, int nrow) { return (i + 1) + (j + 1) * nrow; }
+
+extern "C" zdev_grid2d* zdev_grid2d_create(int nx, int ny) {
+	zdev_require_init();
+	zdev_grid2d* g = (zdev_grid2d*) calloc(1, sizeof(zdev_grid2d));
+	g->nx = nx; g->ny = ny; g->nrow = nx + 3; g->nrows = ny + 3;
+	g->ncell = (size_t) g->nrow * g->nrows;
+	ZDEV_CHECK(cudaMalloc(&g->d_sums, 6 * sizeof(double)));
+	return g;
+}
+
+// Buffers are allocated (zeroed) on first use: a grid object that only backs a
+// t_current never pays for E/B and vice versa.
+static f3* grid_alloc_zero(zdev_grid2d* g) {
+	f3* p; size_t bytes = g->ncell * sizeof(f3);
+	ZDEV_CHECK(cudaMalloc(&p, bytes));
+	ZDEV_CHECK(cudaMemsetAsync(p, 0, bytes, zdev_strm));
+	return p;
+}
+static void need_EB(zdev_grid2d* g) {
+	if (g->E) return;
+	g->E = grid_alloc_zero(g); g->B = grid_alloc_zero(g);
+	g->Epart = g->E; g->Bpart = g->B;
+}
+static void need_J(zdev_grid2d* g) { if (!g->J) g->J = grid_alloc_zero(g); }
+static void need_tmp(zdev_grid2d* g) { if (!g->tmp) g->tmp = grid_alloc_zero(g); }
+
+extern "C" void zdev_grid2d_destroy(zdev_grid2d* g) {
+	if (!g) return;
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	if (g->e_ext) cudaFree(g->Epart);
+	if (g->b_ext) cudaFree(g->Bpart);
+	cudaFree(g->Eext); cudaFree(g->Bext);
+	cudaFree(g->E); cudaFree(g->B); cudaFree(g->J); cudaFree(g->tmp); cudaFree(g->d_sums);
+	free(g);
+}
+
+static f3* grid_sel(zdev_grid2d* g, int which) {
+	if (which == ZDEV_J) need_J(g); else need_EB(g);
+	switch (which) {
+	case ZDEV_E: return g->E;
+	case ZDEV_B: return g->B;
+	case ZDEV_J: return g->J;
+	case ZDEV_EPART: return g->Epart;
+	case ZDEV_BPART: return g->Bpart;
+	}
+	fprintf(stderr, "(*error*) zdev_grid2d: invalid grid selector %d\n", which); exit(-1);
+}
+
+extern "C" void zdev_grid2d_upload(zdev_grid2d* g, int which, const float* host_buf) {
+	ZDEV_CHECK(cudaMemcpyAsync(grid_sel(g, which), host_buf, g->ncell * sizeof(f3), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+}
+extern "C" void zdev_grid2d_download(zdev_grid2d* g, int which, float* host_buf) {
+	ZDEV_CHECK(cudaMemcpyAsync(host_buf, grid_sel(g, which), g->ncell * sizeof(f3), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+}
+extern "C" float* zdev_grid2d_ptr(zdev_grid2d* g, int which) { return (float*) grid_sel(g, which); }
+
+extern "C" void zdev_current_zero(zdev_grid2d* g) {
+	need_J(g);
+	ZDEV_CHECK(cudaMemsetAsync(g->J, 0, g->ncell * sizeof(f3), zdev_strm));
+}
+
+// ------------------------------------------------------------------ Yee solver
+
+// reference em2d/emf.c:500-522 : i in [-1,nx], j in [-1,ny]
+__global__ void k_yee_b(f3* __restrict__ B, const f3* __restrict__ E, int nx, int ny, int nrow,
+                        float dt_dx, float dt_dy) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+	int j = blockIdx.y * blockDim.y + threadIdx.y - 1;
+	if (i > nx || j > ny) return;
+	int c = cidx(i, j, nrow);
+	f3 e = E[c], ex = E[c + 1], ey = E[c + nrow], b = B[c];
+	b.x += ( - dt_dy * ( ey.z - e.z ) );
+	b.y += (   dt_dx * ( ex.z - e.z ) );
+	b.z += ( - dt_dx * ( ex.y - e.y ) + dt_dy * ( ey.x - e.x ) );
+	B[c] = b;
+}
+
+// reference em2d/emf.c:531-562 : i in [0,nx+1], j in [0,ny+1]
+__global__ void k_yee_e(f3* __restrict__ E, const f3* __restrict__ B, const f3* __restrict__ J,
+                        int nx, int ny, int nrow, float dt_dx, float dt_dy, float dt) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int j = blockIdx.y * blockDim.y + threadIdx.y;
+	if (i > nx + 1 || j > ny + 1) return;
+	int c = cidx(i, j, nrow);
+	f3 b = B[c], bx = B[c - 1], by = B[c - nrow], jc = J[c], e = E[c];
+	e.x += ( + dt_dy * ( b.z - by.z ) ) - dt * jc.x;
+	e.y += ( - dt_dx * ( b.z - bx.z ) ) - dt * jc.y;
+	e.z += ( + dt_dx * ( b.y - bx.y ) - dt_dy * ( b.x - by.x ) ) - dt * jc.z;
+	E[c] = e;
+}
+
+extern "C" void zdev_yee_b(zdev_grid2d* g, float dt_dx, float dt_dy) {
+	need_EB(g);
+	dim3 blk(64, 4), grd(zdev_div_up(g->nx + 2, 64), zdev_div_up(g->ny + 2, 4));
+	ZDEV_LAUNCH(k_yee_b, grd, blk, 0, g->B, g->E, g->nx, g->ny, g->nrow, dt_dx, dt_dy);
+}
+static void check_same_shape(zdev_grid2d* a, zdev_grid2d* b) {
+	if (a->nx != b->nx || a->ny != b->ny) { fprintf(stderr, "(*error*) zpic-b200: field / current grid size mismatch\n"); exit(-1); }
+}
+extern "C" void zdev_yee_e(zdev_grid2d* g, zdev_grid2d* gj, float dt_dx, float dt_dy, float dt) {
+	need_EB(g); need_J(gj); check_same_shape(g, gj);
+	dim3 blk(64, 4), grd(zdev_div_up(g->nx + 2, 64), zdev_div_up(g->ny + 2, 4));
+	ZDEV_LAUNCH(k_yee_e, grd, blk, 0, g->E, g->B, gj->J, g->nx, g->ny, g->nrow, dt_dx, dt_dy, dt);
+}
+
+// ------------------------------------------------------------------ guard cells
+
+// periodic x copies for every row (reference em2d/emf.c:583-607): one thread per row
+__global__ void k_gc_x_copy(f3* __restrict__ A, f3* __restrict__ Bf, int nx, int nrows, int nrow) {
+	int r = blockIdx.x * blockDim.x + threadIdx.x;   // buffer row 0..nrows-1
+	if (r >= nrows) return;
+	f3* a = A + (size_t) r * nrow + 1;                // cell (0, r-1)
+	a[-1] = a[nx - 1]; a[nx] = a[0]; a[nx + 1] = a[1];
+	if (Bf) { f3* b = Bf + (size_t) r * nrow + 1; b[-1] = b[nx - 1]; b[nx] = b[0]; b[nx + 1] = b[1]; }
+}
+// periodic y copies for every column incl. x guards (reference em2d/emf.c:611-635)
+__global__ void k_gc_y_copy(f3* __restrict__ A, f3* __restrict__ Bf, int ny, int nrow) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;   // buffer column 0..nrow-1
+	if (c >= nrow) return;
+	size_t s = nrow;
+	f3* a = A + c + s;                                // cell (c-1, 0)
+	a[-(long) s] = a[(size_t)(ny - 1) * s]; a[(size_t) ny * s] = a[0]; a[(size_t)(ny + 1) * s] = a[s];
+	if (Bf) { f3* b = Bf + c + s;
+		b[-(long) s] = b[(size_t)(ny - 1) * s]; b[(size_t) ny * s] = b[0]; b[(size_t)(ny + 1) * s] = b[s]; }
+}
+
+extern "C" void zdev_emf_update_gc(zdev_grid2d* g, int moving_window) {
+	need_EB(g);
+	if (!moving_window)
+		ZDEV_LAUNCH(k_gc_x_copy, zdev_div_up(g->nrows, 128), 128, 0, g->E, g->B, g->nx, g->nrows, g->nrow);
+	ZDEV_LAUNCH(k_gc_y_copy, zdev_div_up(g->nrow, 128), 128, 0, g->E, g->B, g->ny, g->nrow);
+}
+
+// J fold: lower += upper, then upper = lower (reference em2d/current.c:124-157)
+__global__ void k_fold_x(f3* __restrict__ J, int nx, int nrows, int nrow) {
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrows) return;
+	f3* a = J + (size_t) r * nrow + 1;
+	#pragma unroll
+	for (int i = -1; i < 2; i++) {
+		f3 lo = a[i], up = a[nx + i];
+		lo.x += up.x; lo.y += up.y; lo.z += up.z;
+		a[i] = lo; a[nx + i] = lo;
+	}
+}
+__global__ void k_fold_y(f3* __restrict__ J, int ny, int nrow) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nrow) return;
+	size_t s = nrow;
+	f3* a = J + c + s;
+	#pragma unroll
+	for (int j = -1; j < 2; j++) {
+		f3 lo = a[(long) j * (long) s], up = a[(size_t)(ny + j) * s];
+		lo.x += up.x; lo.y += up.y; lo.z += up.z;
+		a[(long) j * (long) s] = lo; a[(size_t)(ny + j) * s] = lo;
+	}
+}
+
+extern "C" void zdev_current_update_gc(zdev_grid2d* g, int moving_window) {
+	need_J(g);
+	if (!moving_window)
+		ZDEV_LAUNCH(k_fold_x, zdev_div_up(g->nrows, 128), 128, 0, g->J, g->nx, g->nrows, g->nrow);
+	ZDEV_LAUNCH(k_fold_y, zdev_div_up(g->nrow, 128), 128, 0, g->J, g->ny, g->nrow);
+}
+
+// ------------------------------------------------------------------ smoothing
+
+__device__ __forceinline__ f3 stencil3(f3 fl, f3 f0, f3 fu, float sa, float sb) {
+	f3 fs;   // reference em2d/current.c:334-336, left-to-right
+	fs.x = sa * fl.x + sb * f0.x + sa * fu.x;
+	fs.y = sa * fl.y + sb * f0.y + sa * fu.y;
+	fs.z = sa * fl.z + sb * f0.z + sa * fu.z;
+	return fs;
+}
+
+// One [sa,sb,sa] pass along x, out of place (reference kernel_x, current.c:316-354).
+// Only rows 0..ny-1 are filtered; x guards of those rows are refreshed from the
+// filtered interior unless the window moves; other rows pass through unchanged.
+__global__ void k_smooth_x(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int ny, int nrow,
+                           float sa, float sb, int moving_window) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+	int j = blockIdx.y * blockDim.y + threadIdx.y - 1;
+	if (i > nx + 1 || j > ny + 1) return;
+	int c = cidx(i, j, nrow);
+	if (j < 0 || j >= ny) { dst[c] = src[c]; return; }
+	int iw = i;
+	if (i < 0 || i >= nx) {
+		if (moving_window) { dst[c] = src[c]; return; }
+		iw = (i < 0) ? i + nx : i - nx;
+	}
+	int cw = cidx(iw, j, nrow);
+	dst[c] = stencil3(src[cw - 1], src[cw], src[cw + 1], sa, sb);
+}
+
+// One pass along y (reference kernel_y, current.c:366-413): columns 0..nx-1 filtered,
+// then y guards of ALL columns copied from the (new) interior rows.
+__global__ void k_smooth_y(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int ny, int nrow,
+                           float sa, float sb) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x - 1;
+	int j = blockIdx.y * blockDim.y + threadIdx.y - 1;
+	if (i > nx + 1 || j > ny + 1) return;
+	int jw = (j < 0) ? j + ny : ((j >= ny) ? j - ny : j);
+	int cw = cidx(i, jw, nrow);
+	int c = cidx(i, j, nrow);
+	if (i < 0 || i >= nx) { dst[c] = src[cw]; return; }
+	dst[c] = stencil3(src[cw - nrow], src[cw], src[cw + nrow], sa, sb);
+}
+
+// reference get_smooth_comp, em2d/current.c:297-304 (double -> float on b)
+static void smooth_comp(int n, float* sa, float* sb) {
+	float a = -1;
+	float b = (float) ((4.0 + 2.0 * n) / n);
+	float total = 2 * a + b;
+	*sa = a / total; *sb = b / total;
+}
+
+static void smooth_pass(zdev_grid2d* g, int dir, float sa, float sb, int moving_window) {
+	need_J(g); need_tmp(g);
+	dim3 blk(64, 4), grd(zdev_div_up(g->nx + 3, 64), zdev_div_up(g->ny + 3, 4));
+	if (dir == 0) ZDEV_LAUNCH(k_smooth_x, grd, blk, 0, g->tmp, g->J, g->nx, g->ny, g->nrow, sa, sb, moving_window);
+	else          ZDEV_LAUNCH(k_smooth_y, grd, blk, 0, g->tmp, g->J, g->nx, g->ny, g->nrow, sa, sb);
+	f3* t = g->J; g->J = g->tmp; g->tmp = t;
+}
+
+extern "C" void zdev_current_smooth(zdev_grid2d* g, int moving_window, int xtype, int ytype, int xlevel, int ylevel) {
+	float sa, sb;
+	if (xtype != 0) {
+		for (int i = 0; i < xlevel; i++) smooth_pass(g, 0, 0.25f, 0.5f, moving_window);
+		if (xtype == 2) { smooth_comp(xlevel, &sa, &sb); smooth_pass(g, 0, sa, sb, moving_window); }
+	}
+	if (ytype != 0) {
+		// sic: the reference counts the y passes with xlevel (em2d/current.c:449)
+		for (int i = 0; i < xlevel; i++) smooth_pass(g, 1, 0.25f, 0.5f, moving_window);
+		if (ytype == 2) { smooth_comp(ylevel, &sa, &sb); smooth_pass(g, 1, sa, sb, moving_window); }
+	}
+}
+
+extern "C" void zdev_current_update(zdev_grid2d* g, int moving_window, int xtype, int ytype, int xlevel, int ylevel) {
+	zdev_current_update_gc(g, moving_window);
+	zdev_current_smooth(g, moving_window, xtype, ytype, xlevel, ylevel);
+}
+
+// ------------------------------------------------------------------ moving window
+
+// new[i] = old[i+1] for i in [-1,nx-2]; columns nx-1..nx+1 zeroed (reference emf.c:659-670)
+__global__ void k_shift_left(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int nrows, int nrow) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;   // buffer column
+	int r = blockIdx.y * blockDim.y + threadIdx.y;   // buffer row
+	if (c >= nrow || r >= nrows) return;
+	size_t k = (size_t) r * nrow + c;
+	f3 z = {0.f, 0.f, 0.f};
+	dst[k] = (c < nx) ? src[k + 1] : z;            // buffer column c = cell c-1
+}
+
+extern "C" void zdev_emf_move_window(zdev_grid2d* g) {
+	need_EB(g); need_tmp(g);
+	dim3 blk(64, 4), grd(zdev_div_up(g->nrow, 64), zdev_div_up(g->nrows, 4));
+	int alias_e = (g->Epart == g->E), alias_b = (g->Bpart == g->B);
+	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->E, g->nx, g->nrows, g->nrow);
+	{ f3* t = g->E; g->E = g->tmp; g->tmp = t; }
+	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->B, g->nx, g->nrows, g->nrow);
+	{ f3* t = g->B; g->B = g->tmp; g->tmp = t; }
+	if (alias_e) g->Epart = g->E;
+	if (alias_b) g->Bpart = g->B;
+}
+
+// ------------------------------------------------------------------ external fields
+
+__global__ void k_add_uniform(f3* __restrict__ dst, const f3* __restrict__ src, size_t n, f3 v) {
+	size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	f3 e = src[k]; e.x += v.x; e.y += v.y; e.z += v.z; dst[k] = e;
+}
+__global__ void k_add_grid(f3* __restrict__ dst, const f3* __restrict__ src, const f3* __restrict__ ext, size_t n) {
+	size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	f3 e = src[k], v = ext[k]; e.x += v.x; e.y += v.y; e.z += v.z; dst[k] = e;
+}
+
+// reference emf_update_part_fld, em2d/emf.c:838-914
+static void update_part_fld(zdev_grid2d* g) {
+	int grd = zdev_div_up(g->ncell, 256);
+	if (g->e_ext == 1) ZDEV_LAUNCH(k_add_uniform, grd, 256, 0, g->Epart, g->E, g->ncell, g->e0);
+	else if (g->e_ext == 2) ZDEV_LAUNCH(k_add_grid, grd, 256, 0, g->Epart, g->E, g->Eext, g->ncell);
+	if (g->b_ext == 1) ZDEV_LAUNCH(k_add_uniform, grd, 256, 0, g->Bpart, g->B, g->ncell, g->b0);
+	else if (g->b_ext == 2) ZDEV_LAUNCH(k_add_grid, grd, 256, 0, g->Bpart, g->B, g->Bext, g->ncell);
+}
+
+static void set_ext(zdev_grid2d* g, int is_b, int mode, const float v[3], const float* host_grid) {
+	need_EB(g);
+	f3** part = is_b ? &g->Bpart : &g->Epart;
+	f3*  self = is_b ? g->B : g->E;
+	int* flag = is_b ? &g->b_ext : &g->e_ext;
+	f3** ext  = is_b ? &g->Bext : &g->Eext;
+	if (*flag && !mode) { cudaFree(*part); *part = self; }
+	if (!*flag && mode) ZDEV_CHECK(cudaMalloc(part, g->ncell * sizeof(f3)));
+	if (!mode) *part = self;
+	*flag = mode;
+	if (mode == 1) { f3 t = {v[0], v[1], v[2]}; if (is_b) g->b0 = t; else g->e0 = t; }
+	if (mode == 2) {
+		if (!*ext) ZDEV_CHECK(cudaMalloc(ext, g->ncell * sizeof(f3)));
+		ZDEV_CHECK(cudaMemcpyAsync(*ext, host_grid, g->ncell * sizeof(f3), cudaMemcpyHostToDevice, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	}
+}
+
+extern "C" void zdev_emf_set_ext_uniform(zdev_grid2d* g, int e_on, const float e0[3], int b_on, const float b0[3]) {
+	set_ext(g, 0, e_on ? 1 : 0, e0, nullptr);
+	set_ext(g, 1, b_on ? 1 : 0, b0, nullptr);
+	update_part_fld(g);
+}
+extern "C" void zdev_emf_set_ext_grid(zdev_grid2d* g, const float* he, const float* hb) {
+	if (he) set_ext(g, 0, 2, nullptr, he);
+	if (hb) set_ext(g, 1, 2, nullptr, hb);
+	update_part_fld(g);
+}
+
+// ------------------------------------------------------------------ field advance
+
+extern "C" void zdev_emf_advance(zdev_grid2d* g, zdev_grid2d* gj, float dt, float dx, float dy, int moving_window, int shift_window) {
+	// reference em2d/emf.c:694-698, scalars formed exactly as in yee_b/yee_e (:509-510, :537-538)
+	float dtb = dt / 2.0f;
+	zdev_yee_b(g, dtb / dx, dtb / dy);
+	zdev_yee_e(g, gj, dt / dx, dt / dy, dt);
+	zdev_yee_b(g, dtb / dx, dtb / dy);
+	zdev_emf_update_gc(g, moving_window);
+	update_part_fld(g);
+	if (shift_window) {
+		zdev_emf_move_window(g);
+		// E_part/B_part buffers are refreshed by the next emf_advance, as in the reference
+	}
+}
+
+// ------------------------------------------------------------------ energy
+
+__global__ void k_energy(const f3* __restrict__ E, const f3* __restrict__ B, int nx, int ny, int nrow, double* out) {
+	double s[6] = {0, 0, 0, 0, 0, 0};
+	long n = (long) nx * ny;
+	for (long k = (long) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long) gridDim.x * blockDim.x) {
+		int j = (int) (k / nx), i = (int) (k - (long) j * nx);
+		f3 e = E[cidx(i, j, nrow)], b = B[cidx(i, j, nrow)];
+		// float products widened to double, as in reference em2d/emf.c:739-744
+		s[0] += e.x * e.x; s[1] += e.y * e.y; s[2] += e.z * e.z;
+		s[3] += b.x * b.x; s[4] += b.y * b.y; s[5] += b.z * b.z;
+	}
+	__shared__ double red[6][8];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	#pragma unroll
+	for (int q = 0; q < 6; q++) {
+		double v = s[q];
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+		if (lane == 0) red[q][w] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		double v = 0;
+		for (int k = 0; k < (int) (blockDim.x >> 5); k++) v += red[threadIdx.x][k];
+		atomicAdd(&out[threadIdx.x], v);
+	}
+}
+
+extern "C" void zdev_emf_energy(zdev_grid2d* g, double sums[6]) {
+	need_EB(g);
+	ZDEV_CHECK(cudaMemsetAsync(g->d_sums, 0, 6 * sizeof(double), zdev_strm));
+	int grd = zdev_div_up((long) g->nx * g->ny, 256);
+	if (grd > 4 * zdev_num_sm) grd = 4 * zdev_num_sm;
+	ZDEV_LAUNCH(k_energy, grd, 256, 0, g->E, g->B, g->nx, g->ny, g->nrow, g->d_sums);
+	ZDEV_CHECK(cudaMemcpyAsync(sums, g->d_sums, 6 * sizeof(double), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+}
+
+// accessors used by the particle kernels (zdev_spec2d.cu)
+f3* zdev_grid2d_Epart(zdev_grid2d* g) { need_EB(g); return g->Epart; }
+f3* zdev_grid2d_Bpart(zdev_grid2d* g) { need_EB(g); return g->Bpart; }
+f3* zdev_grid2d_J(zdev_grid2d* g) { need_J(g); return g->J; }
+int zdev_grid2d_nx(zdev_grid2d* g) { return g->nx; }
+int zdev_grid2d_ny(zdev_grid2d* g) { return g->ny; }

@@ -1,0 +1,521 @@
+/* zpic-b200 :: em2d particle species, host side of the API (reference em2d/particles.c).
+ *
+ * Host: species construction and the particle injector (sequential, drawing from the
+ * single global random stream so that initial conditions and every moving-window
+ * column are bit-identical to the reference), diagnostics output.
+ * Device: spec_advance - field interpolation, Boris push, current deposit,
+ * boundaries, window shift, tile binning (csrc/dev/zdev_spec2d.cu) - and the charge
+ * deposit.  spec->part is a mirror that is refreshed only when somebody reads it.
+ */
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "zb_state.h"
+#include "random.h"
+#include "timer.h"
+#include "zdf.h"
+
+static double   push_seconds = 0.0;
+static uint64_t push_count = 0;
+
+double   spec_time( void )  { return push_seconds; }
+uint64_t spec_npush( void ) { return push_count; }
+double   spec_perf( void )  { return (push_count > 0) ? push_seconds / push_count : -1.0; }
+
+/* ------------------------------------------------------------------ injection (host) */
+
+static float density_one( float x, void* data ) { (void) x; (void) data; return 1.0; }
+
+static void grow( t_part** buf, int* np_max, int size )
+{
+	if (size > *np_max) {
+		*np_max = ( size/1024 + 1 ) * 1024;       /* 1024-particle chunks (reference particles.c:463) */
+		*buf = realloc(*buf, (size_t) *np_max * sizeof(t_part));
+		if (!*buf) { fprintf(stderr, "(*error*) species buffer: out of memory\n"); exit(-1); }
+	}
+}
+
+void spec_grow_buffer( t_species* spec, const int size )
+{
+	grow(&spec->part, &spec->np_max, size);
+}
+
+/* upper bound of the number of particles the profile puts in `range`
+ * (reference spec_np_inj, particles.c:367-449, incl. the dx[1] slip in SLAB) */
+static int count_upper_bound( t_species* spec, const int range[][2] )
+{
+	const int ncx = range[0][1] - range[0][0] + 1, ncy = range[1][1] - range[1][0] + 1;
+	switch (spec->density.type) {
+	case STEP: {
+		int i0 = spec->density.start / spec->dx[0] - spec->n_move;
+		int n;
+		if (i0 > range[0][1]) n = 0;
+		else { if (i0 < range[0][0]) i0 = range[0][0]; n = ( range[0][1] - i0 + 1 ) * spec->ppc[0]; }
+		return n * ncy * spec->ppc[1];
+	}
+	case SLAB: {
+		int i0 = spec->density.start / spec->dx[0] - spec->n_move;
+		int i1 = spec->density.end / spec->dx[1] - spec->n_move;
+		int n;
+		if (i0 > range[0][1] || i1 < range[0][0]) n = 0;
+		else {
+			if (i0 < range[0][0]) i0 = range[0][0];
+			if (i1 > range[0][1]) i1 = range[0][1];
+			n = ( i1 - i0 + 1 ) * spec->ppc[0];
+		}
+		return n * ncy * spec->ppc[1];
+	}
+	case CUSTOM: {
+		/* trapezoidal integrals of the two profile factors */
+		double x = (range[0][0] + spec->n_move) * spec->dx[0];
+		double qx = spec->density.custom_x(x, spec->density.custom_data_x);
+		x = (range[0][1] + 1 + spec->n_move) * spec->dx[0];
+		qx += spec->density.custom_x(x, spec->density.custom_data_x);
+		qx *= 0.5;
+		for (int i = range[0][0] + 1; i <= range[0][1]; i++) {
+			x = (i + spec->n_move) * spec->dx[0];
+			qx += spec->density.custom_x(x, spec->density.custom_data_x);
+		}
+		double y = range[1][0] * spec->dx[1];
+		double qy = spec->density.custom_y(y, spec->density.custom_data_y);
+		y = (range[1][1] + 1) * spec->dx[1];
+		qy += spec->density.custom_y(y, spec->density.custom_data_y);
+		qy *= 0.5;
+		for (int j = range[1][0] + 1; j <= range[1][1]; j++) {
+			y = j * spec->dx[1];
+			qy += spec->density.custom_y(y, spec->density.custom_data_y);
+		}
+		return ceil(qx * spec->ppc[0]) * ceil(qy * spec->ppc[1]);
+	}
+	case EMPTY:
+		return 0;
+	default:
+		return ncx * spec->ppc[0] * ncy * spec->ppc[1];
+	}
+}
+
+/* place particles in `range` following the density profile; returns the new count
+ * (reference spec_set_x, particles.c:159-354) */
+static int place_particles( t_species* spec, const int range[][2], t_part* part, int ip )
+{
+	const int npc = spec->ppc[0] * spec->ppc[1];
+	const float dpcx = 1.0f / spec->ppc[0], dpcy = 1.0f / spec->ppc[1];
+
+	/* positions inside a cell, x fastest */
+	float* cx = malloc(npc * sizeof(float)); float* cy = malloc(npc * sizeof(float));
+	for (int j = 0, k = 0; j < spec->ppc[1]; j++)
+		for (int i = 0; i < spec->ppc[0]; i++, k++) {
+			cx[k] = dpcx * ( i + 0.5 );
+			cy[k] = dpcy * ( j + 0.5 );
+		}
+
+	const enum density_type type = spec->density.type;
+	if (type == CUSTOM) {
+		/* inverse-CDF placement on a piecewise linear density, x then y, with the running
+		   x integral carried across calls so window columns continue the sequence */
+		const double dx = spec->dx[0], dy = spec->dx[1];
+		const double cppx = 1.0 / spec->ppc[0], cppy = 1.0 / spec->ppc[1];
+		const double thresh = 4 * cppx * cppy;
+		const int n_movex = spec->n_move;
+		const int ix0 = range[0][0], iy0 = range[1][0];
+
+		unsigned long kx = spec->density.custom_x_total_part;
+		double d0x, d1x = spec->density.custom_x_total_q;
+		double n0x, n1x = spec->density.custom_x((ix0 + n_movex) * dx, spec->density.custom_data_x);
+		const double n0y0 = spec->density.custom_y(iy0 * dy, spec->density.custom_data_y);
+
+		for (int ix = ix0; ix <= range[0][1]; ix++) {
+			n0x = n1x;
+			n1x = spec->density.custom_x((ix + 1 + n_movex) * dx, spec->density.custom_data_x);
+			d0x = d1x;
+			d1x += 0.5 * (n0x + n1x);
+			double Rsx;
+			while ( (Rsx = (kx + 0.5) * cppx) < d1x ) {
+				double x = 2 * (Rsx - d0x) / ( sqrt( n0x*n0x + 2 * (n1x - n0x) * (Rsx - d0x) ) + n0x );
+				double nx = (0.5 - x) * n0x + (0.5 + x) * n1x;
+				int ky = 0;
+				double n0y, n1y = n0y0, d0y, d1y = 0;
+				for (int iy = iy0; iy <= range[1][1]; iy++) {
+					n0y = n1y;
+					n1y = spec->density.custom_y((iy + 1) * dy, spec->density.custom_data_y);
+					d0y = d1y;
+					d1y += 0.5 * (n0y + n1y);
+					double Rsy;
+					while ( (Rsy = (ky + 0.5) * cppy) < d1y ) {
+						double y = 2 * (Rsy - d0y) / ( sqrt( n0y*n0y + 2 * (n1y - n0y) * (Rsy - d0y) ) + n0y );
+						double ny = (0.5 - y) * n0y + (0.5 + y) * n1y;
+						if (nx * ny > thresh) {
+							part[ip].ix = ix; part[ip].iy = iy;
+							part[ip].x = x;   part[ip].y = y;
+							ip++;
+						}
+						ky++;
+					}
+				}
+				kx++;
+			}
+		}
+		spec->density.custom_x_total_q = d1x;
+		spec->density.custom_x_total_part = kx;
+	} else if (type != EMPTY) {
+		/* UNIFORM / STEP / SLAB: regular lattice, optionally clipped in x */
+		float lo = 0, hi = 0;
+		if (type == STEP || type == SLAB) lo = spec->density.start / spec->dx[0] - spec->n_move;
+		if (type == SLAB) hi = spec->density.end / spec->dx[0] - spec->n_move;
+		for (int j = range[1][0]; j <= range[1][1]; j++)
+			for (int i = range[0][0]; i <= range[0][1]; i++)
+				for (int k = 0; k < npc; k++) {
+					if (type == STEP && !( i + cx[k] > lo )) continue;
+					if (type == SLAB && !( i + cx[k] > lo && i + cx[k] < hi )) continue;
+					part[ip].ix = i; part[ip].iy = j;
+					part[ip].x = cx[k]; part[ip].y = cy[k];
+					ip++;
+				}
+	}
+	free(cx); free(cy);
+	return ip;
+}
+
+/* thermal momenta for part[first..last], cell-mean removed, fluid momentum added
+ * (reference spec_set_u, particles.c:96-146; the cell index uses nx[1] as stride,
+ * App. B item 5 - kept, it decides which particles share a mean) */
+static void draw_momenta( t_species* spec, t_part* part, int first, int last )
+{
+	for (int i = first; i <= last; i++) {
+		part[i].ux = spec->uth[0] * rand_norm();
+		part[i].uy = spec->uth[1] * rand_norm();
+		part[i].uz = spec->uth[2] * rand_norm();
+	}
+
+	const int size = spec->nx[0] * spec->nx[1];
+	const int stride = spec->nx[1];
+	float3* mean = calloc(size, sizeof(float3));
+	int* count = calloc(size, sizeof(int));
+	for (int i = first; i <= last; i++) {
+		const int c = part[i].ix + stride * part[i].iy;
+		mean[c].x += part[i].ux; mean[c].y += part[i].uy; mean[c].z += part[i].uz;
+		count[c] += 1;
+	}
+	for (int c = 0; c < size; c++) {
+		const float norm = (count[c] > 0) ? 1.0f / count[c] : 0;
+		mean[c].x *= norm; mean[c].y *= norm; mean[c].z *= norm;
+	}
+	for (int i = first; i <= last; i++) {
+		const int c = part[i].ix + stride * part[i].iy;
+		part[i].ux += spec->ufl[0] - mean[c].x;
+		part[i].uy += spec->ufl[1] - mean[c].y;
+		part[i].uz += spec->ufl[2] - mean[c].z;
+	}
+	free(count); free(mean);
+}
+
+/* inject into an arbitrary AoS buffer (the species mirror at start-up, a scratch
+ * column buffer when the window moves) - reference spec_inject_particles :476-492 */
+void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max )
+{
+	const int first = *np;
+	grow(buf, np_max, *np + count_upper_bound(spec, range));
+	*np = place_particles(spec, range, *buf, *np);
+	draw_momenta(spec, *buf, first, *np - 1);
+}
+
+void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
+               const float *ufl, const float *uth,
+               const int nx[], float box[], const float dt, t_density* density )
+{
+	zb_spec_drop(spec);
+
+	strncpy(spec->name, name, MAX_SPNAME_LEN);
+	spec->name[MAX_SPNAME_LEN] = 0;
+
+	int npc = 1;
+	for (int i = 0; i < 2; i++) {
+		spec->nx[i] = nx[i];
+		spec->ppc[i] = ppc[i];
+		npc *= ppc[i];
+		spec->box[i] = box[i];
+		spec->dx[i] = box[i] / nx[i];
+	}
+	spec->m_q = m_q;
+	spec->q = copysign( 1.0f, m_q ) / npc;
+	spec->dt = dt;
+	spec->energy = 0;
+
+	spec->np_max = 0;
+	spec->part = NULL;
+
+	if (density) spec->density = *density;
+	else spec->density = (t_density) { .type = UNIFORM, .n = 1.0 };
+	if (spec->density.n == 0.) spec->density.n = 1.0;
+	if (spec->density.type == CUSTOM) {
+		if (!spec->density.custom_x) spec->density.custom_x = &density_one;
+		if (!spec->density.custom_y) spec->density.custom_y = &density_one;
+		spec->density.custom_x_total_part = 0;
+		spec->density.custom_x_total_q = 0;
+	}
+	spec->q *= fabsf( spec->density.n );
+
+	for (int i = 0; i < 3; i++) {
+		spec->ufl[i] = ufl ? ufl[i] : 0;
+		spec->uth[i] = uth ? uth[i] : 0;
+	}
+
+	spec->iter = 0;
+	spec->moving_window = 0;
+	spec->n_move = 0;
+
+	spec->np = 0;
+	const int range[][2] = { {0, nx[0]-1}, {0, nx[1]-1} };
+	spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
+
+	spec->n_sort = 16;    /* kept for API compatibility; device tiles are re-binned every step */
+}
+
+void spec_delete( t_species* spec )
+{
+	zb_spec_drop(spec);
+	free(spec->part);
+	spec->part = NULL;
+	spec->np = -1;
+}
+
+/* Stand-alone window move on the host mirror (reference particles.c:619-640).  The
+ * device path does not come through here: spec_advance folds the shift into the push
+ * kernel and uploads the injected column. */
+void spec_move_window( t_species *spec )
+{
+	if ( (spec->iter * spec->dt) > (spec->dx[0] * (spec->n_move + 1)) ) {
+		zb_spec_to_host(spec);
+		for (int i = 0; i < spec->np; i++) spec->part[i].ix--;
+		spec->n_move++;
+		const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
+		spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
+		zb_spec* e = zb_spec_of(spec, 1);
+		e->dev_stale = 1;
+	}
+}
+
+/* ------------------------------------------------------------------ advance (device) */
+
+void spec_advance( t_species* spec, t_emf* emf, t_current* current )
+{
+	uint64_t t0 = timer_ticks();
+
+	zb_spec_to_device(spec);
+	zb_emf_to_device(emf);
+	zb_spec* s = zb_spec_of(spec, 1);
+	zb_grid* gf = zb_grid_of_emf(emf, 1);
+	zb_grid* gc = zb_grid_of_cur(current, 1);
+
+	/* per-step scalars exactly as the reference forms them (particles.c:1111-1117) */
+	zdev_push2d_params prm;
+	prm.tem   = 0.5 * spec->dt / spec->m_q;
+	prm.dt_dx = spec->dt / spec->dx[0];
+	prm.dt_dy = spec->dt / spec->dx[1];
+	prm.qnx   = spec->q * spec->dx[0] / spec->dt;
+	prm.qny   = spec->q * spec->dx[1] / spec->dt;
+	prm.q     = spec->q;
+	prm.moving_window = spec->moving_window;
+	/* the window test uses the already incremented iteration (particles.c:1234-1240, :621) */
+	prm.shift_window = spec->moving_window &&
+		( ((spec->iter + 1) * spec->dt) > (spec->dx[0] * (spec->n_move + 1)) );
+
+	zdev_spec2d_advance(s->d, zb_dev(gf), zb_dev(gc), &prm);
+	s->host_stale = 1;
+	gc->j_host_stale = 1;
+	spec->iter += 1;
+
+	int n_injected = 0;
+	if (prm.shift_window) {
+		/* new plasma enters through the right edge: host injector (global random stream),
+		   then the column is appended to the device tiles */
+		spec->n_move++;
+		const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
+		t_part* col = NULL; int ncol = 0, ncol_max = 0;
+		spec_inject_into(spec, range, &col, &ncol, &ncol_max);
+		zdev_spec2d_append(s->d, col, ncol);
+		free(col);
+		n_injected = ncol;
+	}
+
+	if (!zb_opt_lazy()) {
+		double esum; int64_t np;
+		zdev_spec2d_fetch(s->d, &esum, &np);
+		spec->energy = spec->q * spec->m_q * esum * spec->dx[0] * spec->dx[1];
+		spec->np = (int) (np + n_injected);
+		s->np_seen = spec->np;
+		spec_grow_buffer(spec, spec->np);
+		s->part_seen = spec->part;
+		push_count += spec->np;
+	} else {
+		push_count += spec->np;      /* population estimate; exact after the next sync */
+	}
+	push_seconds += timer_interval_seconds(t0, timer_ticks());
+}
+
+/* ------------------------------------------------------------------ charge density */
+
+void spec_deposit_charge( const t_species* spec, float* charge )
+{
+	zb_spec_to_device((t_species*) spec);
+	zb_spec* s = zb_spec_of(spec, 1);
+	zdev_spec2d_deposit_charge(s->d, spec->q, spec->moving_window, charge);
+}
+
+/* ------------------------------------------------------------------ reports (host, ZDF) */
+
+static void report_particles( const t_species *spec )
+{
+	static const char* quants[]  = { "x", "y", "ux", "uy", "uz" };
+	static const char* qlabels[] = { "x", "y", "u_x", "u_y", "u_z" };
+	static const char* qunits[]  = { "c/\\omega_p", "c/\\omega_p", "c", "c", "c" };
+
+	t_zdf_iteration iter = { .name = "ITERATION", .n = spec->iter,
+	                         .t = spec->iter * spec->dt, .time_units = "1/\\omega_p" };
+	t_zdf_part_info info = { .name = (char*) spec->name, .label = (char*) spec->name, .nquants = 5,
+	                         .quants = (char**) quants, .qlabels = (char**) qlabels,
+	                         .qunits = (char**) qunits, .np = spec->np };
+	char path[1024];
+	snprintf(path, 1024, "PARTICLES/%s", spec->name);
+	t_zdf_file file;
+	zdf_open_part_file(&file, &info, &iter, path);
+
+	const int np = spec->np;
+	const t_part* p = spec->part;
+	float* data = malloc((size_t) (np > 0 ? np : 1) * sizeof(float));
+	for (int i = 0; i < np; i++) data[i] = ( spec->n_move + p[i].ix + p[i].x ) * spec->dx[0];
+	zdf_add_quant_part_file(&file, quants[0], data, np);
+	for (int i = 0; i < np; i++) data[i] = ( p[i].iy + p[i].y ) * spec->dx[1];
+	zdf_add_quant_part_file(&file, quants[1], data, np);
+	for (int i = 0; i < np; i++) data[i] = p[i].ux;
+	zdf_add_quant_part_file(&file, quants[2], data, np);
+	for (int i = 0; i < np; i++) data[i] = p[i].uy;
+	zdf_add_quant_part_file(&file, quants[3], data, np);
+	for (int i = 0; i < np; i++) data[i] = p[i].uz;
+	zdf_add_quant_part_file(&file, quants[4], data, np);
+	free(data);
+	zdf_close_file(&file);
+}
+
+static void report_charge( const t_species *spec )
+{
+	const int nx = spec->nx[0], ny = spec->nx[1];
+	float* rho = calloc((size_t) (nx + 1) * (ny + 1), sizeof(float));
+	spec_deposit_charge(spec, rho);
+	float* buf = malloc((size_t) nx * ny * sizeof(float));
+	for (int j = 0; j < ny; j++)
+		memcpy(buf + (size_t) j * nx, rho + (size_t) j * (nx + 1), nx * sizeof(float));
+	free(rho);
+
+	t_zdf_grid_axis axis[2] = {
+		{ .min = spec->n_move * spec->dx[0], .max = spec->box[0] + spec->n_move * spec->dx[0],
+		  .name = "x", .label = "x", .units = "c/\\omega_p" },
+		{ .min = 0.0, .max = spec->box[1], .name = "y", .label = "y", .units = "c/\\omega_p" }
+	};
+	char name[128], label[128];
+	snprintf(name, 128, "%s-charge", spec->name);
+	snprintf(label, 128, "%s \\rho", spec->name);
+	t_zdf_grid_info info = { .ndims = 2, .name = name, .label = label, .units = "n_e", .axis = axis };
+	info.count[0] = nx; info.count[1] = ny;
+	t_zdf_iteration iter = { .name = "ITERATION", .n = spec->iter,
+	                         .t = spec->iter * spec->dt, .time_units = "1/\\omega_p" };
+	char path[1024];
+	snprintf(path, 1024, "CHARGE/%s", spec->name);
+	zdf_save_grid(buf, zdf_float32, &info, &iter, path);
+	free(buf);
+}
+
+/* value of one phasespace axis quantity for particle p (reference spec_pha_axis :1512-1538) */
+static inline float pha_value( const t_species* spec, const t_part* p, int quant )
+{
+	switch (quant) {
+	case X1: return ( p->x + p->ix ) * spec->dx[0];
+	case X2: return ( p->y + p->iy ) * spec->dx[1];
+	case U1: return p->ux;
+	case U2: return p->uy;
+	case U3: return p->uz;
+	}
+	return 0;
+}
+
+/* linear deposit on a 2D phasespace grid (reference :1569-1632) */
+void spec_deposit_pha( const t_species *spec, const int rep_type,
+                       const int pha_nx[], const float pha_range[][2], float* buf )
+{
+	zb_spec_to_host(spec);
+
+	const int nrow = pha_nx[0];
+	const int quant1 = rep_type & 0x000F;
+	const int quant2 = (rep_type & 0x00F0) >> 4;
+	const float x1min = pha_range[0][0], x2min = pha_range[1][0];
+	const float rdx1 = pha_nx[0] / ( pha_range[0][1] - pha_range[0][0] );
+	const float rdx2 = pha_nx[1] / ( pha_range[1][1] - pha_range[1][0] );
+
+	for (int k = 0; k < spec->np; k++) {
+		const t_part* p = &spec->part[k];
+		float nx1 = ( pha_value(spec, p, quant1) - x1min ) * rdx1;
+		float nx2 = ( pha_value(spec, p, quant2) - x2min ) * rdx2;
+		int i1 = (int) (nx1 + 0.5f), i2 = (int) (nx2 + 0.5f);
+		float w1 = nx1 - i1 + 0.5f, w2 = nx2 - i2 + 0.5f;
+		int idx = i1 + nrow * i2;
+		const int in1a = (i1 >= 0 && i1 < pha_nx[0]), in1b = (i1 + 1 >= 0 && i1 + 1 < pha_nx[0]);
+		if (i2 >= 0 && i2 < pha_nx[1]) {
+			if (in1a) buf[idx]     += (1.0f - w1) * (1.0f - w2) * spec->q;
+			if (in1b) buf[idx + 1] += w1 * (1.0f - w2) * spec->q;
+		}
+		idx += nrow;
+		if (i2 + 1 >= 0 && i2 + 1 < pha_nx[1]) {
+			if (in1a) buf[idx]     += (1.0f - w1) * w2 * spec->q;
+			if (in1b) buf[idx + 1] += w1 * w2 * spec->q;
+		}
+	}
+}
+
+static void report_pha( const t_species *spec, const int rep_type,
+                        const int pha_nx[], const float pha_range[][2] )
+{
+	float* buf = calloc((size_t) pha_nx[0] * pha_nx[1], sizeof(float));
+	spec_deposit_pha(spec, rep_type, pha_nx, pha_range, buf);
+
+	const int q1 = rep_type & 0x000F, q2 = (rep_type & 0x00F0) >> 4;
+	static const char* ax_name[]  = { "x1", "x2", "x3", "u1", "u2", "u3" };
+	static const char* ax_label[] = { "x", "y", "z", "u_x", "u_y", "u_z" };
+	const char* u1 = (q1 <= X2) ? "c/\\omega_p" : "m_e c";
+	const char* u2 = (q2 <= X2) ? "c/\\omega_p" : "m_e c";
+
+	t_zdf_grid_axis axis[2] = {
+		{ .min = pha_range[0][0], .max = pha_range[0][1], .name = (char*) ax_name[q1-1],
+		  .label = (char*) ax_label[q1-1], .units = (char*) u1 },
+		{ .min = pha_range[1][0], .max = pha_range[1][1], .name = (char*) ax_name[q2-1],
+		  .label = (char*) ax_label[q2-1], .units = (char*) u2 }
+	};
+	char name[64], label[64];
+	snprintf(name, 64, "%s-%s%s", spec->name, ax_name[q1-1], ax_name[q2-1]);
+	snprintf(label, 64, "%s %s-%s", spec->name, ax_label[q1-1], ax_label[q2-1]);
+	t_zdf_grid_info info = { .ndims = 2, .name = name, .label = label, .units = "a.u.", .axis = axis };
+	info.count[0] = pha_nx[0]; info.count[1] = pha_nx[1];
+	t_zdf_iteration iter = { .name = "ITERATION", .n = spec->iter,
+	                         .t = spec->iter * spec->dt, .time_units = "1/\\omega_p" };
+	char path[1024];
+	snprintf(path, 1024, "PHASESPACE/%s", spec->name);
+	zdf_save_grid(buf, zdf_float32, &info, &iter, path);
+	free(buf);
+}
+
+void spec_report( const t_species *spec, const int rep_type,
+                  const int pha_nx[], const float pha_range[][2] )
+{
+	switch (rep_type & 0xF000) {
+	case CHARGE:
+		report_charge(spec);
+		break;
+	case PHA:
+		report_pha(spec, rep_type, pha_nx, pha_range);
+		break;
+	case PARTICLES:
+		zb_spec_to_host(spec);
+		report_particles(spec);
+		break;
+	}
+}

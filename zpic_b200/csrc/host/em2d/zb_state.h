@@ -1,0 +1,62 @@
+/* zpic-b200 :: host <-> device bookkeeping for the em2d API layer (internal).
+ *
+ * The public structs (include/em2d) carry no device members; the device twin of
+ * every t_emf / t_current / t_species is found through a small registry keyed by
+ * the host object's address.  Each entry also tracks which side holds the current
+ * data so mirrors are only copied when somebody needs them (SURVEY.md 8b,
+ * "coherence contract").
+ */
+#ifndef ZB_STATE_H
+#define ZB_STATE_H
+
+#include "zpic_dev.h"
+#include "simulation.h"
+
+/* E/B/J device grids shared by one t_emf and (after sim_new) one t_current */
+typedef struct zb_grid {
+	const t_emf* emf;          /* owner keys, either may be NULL */
+	const t_current* cur;
+	zdev_grid2d* g;            /* NULL until first device use: see zb_dev() */
+	int nx, ny;
+	int eb_dev_stale;          /* host E_buf/B_buf were modified after the last upload */
+	int eb_host_stale;         /* device advanced E/B after the last download */
+	int j_host_stale;          /* device J newer than host J_buf */
+	int part_host_stale;       /* device E_part/B_part newer than the host *_part_buf */
+} zb_grid;
+
+typedef struct zb_spec {
+	const t_species* spec;
+	zdev_spec2d* d;
+	int dev_stale;             /* host part[] newer than the device copy (or never uploaded) */
+	int host_stale;            /* device newer than host part[] */
+	const t_part* part_seen;   /* host buffer address / count at the last transfer: a change */
+	int np_seen;               /*   means host code touched the buffer (Species.add, realloc) */
+} zb_spec;
+
+zb_grid* zb_grid_of_emf( const t_emf* emf, int create );
+zb_grid* zb_grid_of_cur( const t_current* cur, int create );
+/* device grid object of an entry, created on demand */
+zdev_grid2d* zb_dev( zb_grid* e );
+/* make emf and current share one device grid object (done by sim_new) */
+void zb_grid_pair( const t_emf* emf, const t_current* cur );
+void zb_grid_drop_emf( const t_emf* emf );
+void zb_grid_drop_cur( const t_current* cur );
+
+zb_spec* zb_spec_of( const t_species* spec, int create );
+void zb_spec_drop( const t_species* spec );
+
+/* bring one side up to date */
+void zb_emf_to_device( t_emf* emf );       /* upload E/B if the host copy is newer */
+void zb_emf_to_host( const t_emf* emf );   /* download E/B (and *_part_buf) if the device copy is newer */
+void zb_cur_to_host( const t_current* cur );
+void zb_spec_to_device( t_species* spec );
+void zb_spec_to_host( const t_species* spec );
+
+/* options (environment: ZPIC_LAZY, ZPIC_TRACK_IDS, ZPIC_COHERENT) */
+int zb_opt_lazy( void );        /* 1: do not fetch energy / np after every spec_advance */
+int zb_opt_track_ids( void );   /* 1: keep injection order recoverable in the host mirror */
+int zb_opt_coherent( void );    /* 1: host mirrors are refreshed before and after every sim_iter */
+
+void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max );
+
+#endif
