@@ -1,0 +1,227 @@
+"""GPU parity tests: the product (CUDA) against the unmodified reference (strict build,
+oracle/_ref) on the same decks and seeds, through the same C API calls.
+
+Bars (BASELINE.json north_star): integer state bit-exact after one step; E/B/J and
+momenta rel-L2 <= 1e-5 after 1 and 100 steps; energies within 1e-6 relative.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from zpic_b200 import abi_em2d as A
+
+pytestmark = pytest.mark.gpu
+
+TOL_FIELD = 1e-5      # relative L2 on E, B, J (north_star)
+TOL_ENERGY = 1e-6     # relative, energy diagnostics
+
+
+@pytest.fixture(autouse=True)
+def _ids(ours):
+    # keep injection order recoverable so particles compare one to one
+    ours.zpic_b200_set_option(b"track_ids", 1)
+    ours.zpic_b200_set_option(b"lazy", 0)
+    ours.zpic_b200_set_option(b"coherent", 0)
+    assert ours.zdev_init(-1) == 0, "no CUDA device: GPU tests cannot run"
+
+
+def _fill_random(deck, rng, amp=1.0):
+    for g in (deck.E(), deck.B(), deck.J()):
+        g[...] = 0
+    shape = deck.E().shape
+    vals = [(amp * rng.standard_normal(shape)).astype(np.float32) for _ in range(3)]
+    return vals
+
+
+def test_field_solver_bit_exact(ours, ref):
+    """yee_b/yee_e/yee_b + guard refresh on random E, B, J: every cell, guards included"""
+    rng = np.random.default_rng(1)
+    a = H.Deck(ours, (70, 45), (7.0, 9.0), 0.05)
+    b = H.Deck(ref, (70, 45), (7.0, 9.0), 0.05)
+    e, bb, j = _fill_random(a, rng)
+    for d in (a, b):
+        d.E()[...] = e
+        d.B()[...] = bb
+        d.J()[...] = j
+    a.touch()
+    # J lives on the device only during a step: upload it explicitly for this kernel-level test
+    from zpic_b200 import load
+    lib = load("em2d")
+    g = lib.zdev_grid2d_create(70, 45)
+    lib.zdev_grid2d_upload(g, 0, e.ctypes.data)
+    lib.zdev_grid2d_upload(g, 1, bb.ctypes.data)
+    lib.zdev_grid2d_upload(g, 2, j.ctypes.data)
+    for it in range(3):
+        lib.zdev_emf_advance(g, g, 0.05, float(np.float32(7.0) / np.float32(70)), float(np.float32(9.0) / np.float32(45)), 0, 0)
+        ref.emf_advance(C.byref(b.sim.emf), C.byref(b.sim.current))
+    eo = np.empty_like(e)
+    bo = np.empty_like(e)
+    lib.zdev_grid2d_download(g, 0, eo.ctypes.data)
+    lib.zdev_grid2d_download(g, 1, bo.ctypes.data)
+    lib.zdev_grid2d_destroy(g)
+    assert np.array_equal(eo.view(np.uint32), b.E().view(np.uint32))
+    assert np.array_equal(bo.view(np.uint32), b.B().view(np.uint32))
+
+
+@pytest.mark.parametrize("mw", [0, 1])
+@pytest.mark.parametrize("smooth", [(0, 0, 0, 0), (1, 0, 2, 0), (2, 0, 4, 0), (1, 1, 1, 1), (2, 2, 3, 2), (0, 2, 0, 2)])
+def test_current_update_bit_exact(ours, ref, smooth, mw):
+    """guard fold + binomial / compensated smoothing (incl. the xlevel-for-y quirk)"""
+    rng = np.random.default_rng(2)
+    nx, ny = 53, 38
+    b = H.Deck(ref, (nx, ny), (5.3, 3.8), 0.05)
+    j = rng.standard_normal(b.J().shape).astype(np.float32)
+    b.J()[...] = j
+    b.sim.current.moving_window = mw
+    b.sim.current.smooth = A.Smooth(*[smooth[0], smooth[1], smooth[2], smooth[3]])
+    ref.current_update(C.byref(b.sim.current))
+    g = ours.zdev_grid2d_create(nx, ny)
+    ours.zdev_grid2d_upload(g, 2, j.ctypes.data)
+    ours.zdev_current_update(g, mw, smooth[0], smooth[1], smooth[2], smooth[3])
+    jo = np.empty_like(j)
+    ours.zdev_grid2d_download(g, 2, jo.ctypes.data)
+    ours.zdev_grid2d_destroy(g)
+    assert np.array_equal(jo.view(np.uint32), b.J().view(np.uint32))
+
+
+def test_window_shift_bit_exact(ours, ref):
+    rng = np.random.default_rng(3)
+    nx, ny = 40, 21
+    e = rng.standard_normal((ny + 3, nx + 3, 3)).astype(np.float32)
+    g = ours.zdev_grid2d_create(nx, ny)
+    ours.zdev_grid2d_upload(g, 0, e.ctypes.data)
+    ours.zdev_grid2d_upload(g, 1, e.ctypes.data)
+    ours.zdev_emf_move_window(g)
+    out = np.empty_like(e)
+    ours.zdev_grid2d_download(g, 0, out.ctypes.data)
+    ours.zdev_grid2d_destroy(g)
+    want = np.zeros_like(e)
+    want[:, 0:nx, :] = e[:, 1:nx + 1, :]     # buffer col c = cell c-1: cells -1..nx-2 <- cells 0..nx-1
+    assert np.array_equal(out, want)
+
+
+def _compare_weibel(ours, ref, n, ppc, steps, checkpoints):
+    a = H.weibel(ours, n=n, ppc=ppc, n_sort=0)
+    b = H.weibel(ref, n=n, ppc=ppc, n_sort=0)
+    done = 0
+    res = {}
+    for cp in checkpoints:
+        a.iter(cp - done)
+        b.iter(cp - done)
+        done = cp
+        sa, sb = a.snapshot(), b.snapshot()
+        ea, eb = a.emf_energy(), b.emf_energy()
+        res[cp] = (sa, sb, ea, eb)
+    a.delete()
+    b.delete()
+    return res
+
+
+def test_weibel_one_step_integer_state_bit_exact(ours, ref):
+    """ppc 8x8 puts particles 1/16 cell from the faces so a fraction changes cell at step 1"""
+    res = _compare_weibel(ours, ref, 64, (8, 8), 1, [1])
+    sa, sb, ea, eb = res[1]
+    crossed = 0
+    for k in range(2):
+        pa, pb = sa["parts"][k], sb["parts"][k]
+        assert sa["np"][k] == sb["np"][k]
+        assert np.array_equal(pa["ix"], pb["ix"]) and np.array_equal(pa["iy"], pb["iy"])
+        for q in ("x", "y", "ux", "uy", "uz"):
+            assert np.array_equal(pa[q].view(np.uint32), pb[q].view(np.uint32)), q
+    # the step-1 fields are zero for Weibel; J only differs by summation order
+    assert H.rel_l2(sa["J"], sb["J"]) < 1e-6
+    assert H.rel_l2(sa["E"], sb["E"]) < 1e-6
+    for k in range(2):
+        assert abs(sa["energy"][k] - sb["energy"][k]) <= TOL_ENERGY * abs(sb["energy"][k])
+
+
+def test_weibel_cells_cross_after_a_few_steps(ours, ref):
+    """after 12 steps thousands of particles changed cell and wrapped around the box"""
+    res = _compare_weibel(ours, ref, 64, (2, 2), 12, [12])
+    sa, sb, ea, eb = res[12]
+    moved = 0
+    for k in range(2):
+        pa, pb = sa["parts"][k], sb["parts"][k]
+        assert sa["np"][k] == sb["np"][k]
+        same = (pa["ix"] == pb["ix"]) & (pa["iy"] == pb["iy"])
+        # a particle within rounding distance of a cell face may legitimately land on the other
+        # side once J (hence E, B) differs in the last bits: allow a handful, no more
+        assert (~same).sum() <= 3, (~same).sum()
+        assert H.rel_l2(pa["ux"], pb["ux"]) < TOL_FIELD
+        assert H.rel_l2(pa["uz"], pb["uz"]) < TOL_FIELD
+    for q in ("E", "B", "J"):
+        assert H.rel_l2(sa[q], sb[q]) < TOL_FIELD, q
+
+
+def test_weibel_100_steps_within_tolerance(ours, ref):
+    """config 1: em2d/input/weibel.c as shipped, 1 and 100 steps"""
+    res = _compare_weibel(ours, ref, 128, (2, 2), 100, [1, 100])
+    for cp, (sa, sb, ea, eb) in res.items():
+        for q in ("E", "B", "J"):
+            err = H.rel_l2(sa[q], sb[q])
+            assert err < TOL_FIELD, (cp, q, err)
+        for k in range(2):
+            assert sa["np"][k] == sb["np"][k] == 65536
+            for q in ("ux", "uy", "uz"):
+                err = H.rel_l2(sa["parts"][k][q], sb["parts"][k][q])
+                assert err < TOL_FIELD, (cp, k, q, err)
+            assert abs(sa["energy"][k] - sb["energy"][k]) <= TOL_ENERGY * abs(sb["energy"][k])
+        tot_a, tot_b = ea.sum(), eb.sum()
+        if tot_b > 0:
+            assert abs(tot_a - tot_b) <= 1e-5 * tot_b, (cp, tot_a, tot_b)
+
+
+def test_charge_deposit(ours, ref):
+    a = H.weibel(ours, n=32, ppc=(2, 2), n_sort=0)
+    b = H.weibel(ref, n=32, ppc=(2, 2), n_sort=0)
+    a.iter(3)
+    b.iter(3)
+    for k in range(2):
+        ra, rb = a.charge(k), b.charge(k)
+        assert H.rel_l2(ra, rb) < 1e-6
+    a.delete()
+    b.delete()
+
+
+def test_lwfa_moving_window(ours, ref):
+    """laser + moving window + absorbing x + compensated smoothing + window injection"""
+    kw = dict(nx=(256, 64), box=(5.12, 12.8), dt=0.014, ppc=(2, 2), start=4.0, laser_start=3.5, a0=1.0, n_sort=0)
+    a = H.lwfa(ours, **kw)
+    b = H.lwfa(ref, **kw)
+    done = 0
+    for cp in (1, 40, 120):
+        a.iter(cp - done)
+        b.iter(cp - done)
+        done = cp
+        sa, sb = a.snapshot(), b.snapshot()
+        assert a.sim.emf.n_move == b.sim.emf.n_move
+        assert a.species[0].n_move == b.species[0].n_move
+        assert sa["np"][0] == sb["np"][0], (cp, sa["np"], sb["np"])
+        for q in ("E", "B", "J"):
+            err = H.rel_l2(sa[q], sb[q])
+            assert err < TOL_FIELD, (cp, q, err)
+        pa, pb = H.canon(sa["parts"][0]), H.canon(sb["parts"][0])
+        assert np.array_equal(pa["ix"], pb["ix"]) and np.array_equal(pa["iy"], pb["iy"]), cp
+    assert b.sim.emf.n_move > 0 and sb["np"][0] > 0
+    a.delete()
+    b.delete()
+
+
+def test_external_uniform_fields(ours, ref):
+    sp = [dict(name="e", m_q=-1.0, ppc=(2, 2), uth=(0.01, 0.01, 0.01), ufl=(0.2, 0, 0), n_sort=0)]
+    a = H.Deck(ours, (32, 32), (3.2, 3.2), 0.05, sp)
+    b = H.Deck(ref, (32, 32), (3.2, 3.2), 0.05, sp)
+    for d in (a, b):
+        d.set_ext_uniform(E0=(0.0, 0.01, 0.0), B0=(0.0, 0.0, 1.0))
+    a.iter(20)
+    b.iter(20)
+    sa, sb = a.snapshot(), b.snapshot()
+    for q in ("ux", "uy", "uz"):
+        assert H.rel_l2(sa["parts"][0][q], sb["parts"][0][q]) < TOL_FIELD
+    for q in ("E", "B", "J"):
+        assert H.rel_l2(sa[q], sb[q]) < TOL_FIELD
+    a.delete()
+    b.delete()
