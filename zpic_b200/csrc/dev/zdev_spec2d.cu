@@ -1,18 +1,33 @@
 // zpic-b200 :: em2d particle species on the device.
 //
-// Data layout in HBM.  The grid is cut into tiles of TX x TY cells; every tile owns
-// a fixed-capacity segment [tile_off[t], tile_off[t+1]) of seven SoA arrays
-// (ix, iy, x, y, ux, uy, uz; optional injection tag) of which the first tile_np[t]
-// slots are live.  One CTA advances one tile: it stages the (TX+2)x(TY+2) E/B
-// neighbourhood in shared memory once, streams the tile's particles through
-// registers with fully coalesced SoA loads, and writes survivors back compacted in
-// place.  Particles that leave the tile go through a small global "migrants" list
-// that a second kernel appends to the destination tiles; per step a particle is
-// therefore read once and written once (56 B), plus the few percent that migrate.
+// Data layout in HBM.  The grid is cut into tiles of TX x TY cells; every tile owns a
+// fixed-capacity segment [tile_off[t], tile_off[t+1]) of six SoA arrays
+//     cell (lx | ly<<16, tile-local cell; -1 = empty slot), x, y, ux, uy, uz
+// (24 B per particle; an optional 7th array carries the injection tag), of which the
+// first tile_np[t] slots are in use.  There are two such buffers, A and B, and every
+// step streams A -> B.
+//
+// One CTA advances one tile (k_push2d):
+//   phase A  an index-only counting sort of the tile's particles by cell, done in shared
+//            memory with native integer atomics: perm[] lists the live slots in cell
+//            order (empty slots drop out here, so compaction is free);
+//   phase B  warps walk perm[] in order with no block barriers: gather the particle from
+//            A, interpolate E/B from the shared-memory field tile, Boris push, move.
+//            Because the lanes of a warp now sit in the same one or two cells, the eight
+//            current contributions of the (non-crossing) particles are combined with a
+//            segmented warp scan and only the last lane of each run issues the 8 L2
+//            reductions.  The few particles that cross a cell face go to a warp-private
+//            queue and are split/deposited 32 at a time, so the rare path costs no
+//            divergence.  Survivors are written to B at their sorted position
+//            (coalesced); particles that left the tile go to a global migrants list and
+//            leave an empty slot behind.
+// k_migrate2d then appends the migrants to their destination tiles in B.
+// Per step a particle is read once and written once (48 B; 56 B with the reference's
+// 28-byte record), plus the few percent that migrate.
 //
 // Replaces reference em2d/particles.c:1104-1269 (spec_advance incl. boundaries and
-// spec_move_window's index shift) and :942-1007 (spec_sort: binning by tile is kept
-// current every step instead of a counting sort every n_sort steps).
+// spec_move_window's index shift) and :942-1007 (spec_sort - here the cell order is
+// rebuilt every step instead of every n_sort steps).
 #include "zdev_common.cuh"
 #include "pic2d_core.cuh"
 #include <vector>
@@ -30,7 +45,8 @@ struct part_aos { int ix, iy; float x, y, ux, uy, uz; };
 
 // SoA view handed to kernels by value
 struct soa2d {
-	int *ix, *iy;
+	int *cell;           // tile buffers: lx | ly<<16 (or -1); migrants list: global ix
+	int *iy;             // migrants list only: global iy
 	float *x, *y, *ux, *uy, *uz;
 	int *tag;            // null unless ids are tracked
 };
@@ -48,10 +64,12 @@ struct zdev_spec2d {
 	int TX, TY, ntx, nty, ntiles;
 	int ppc_hint, track_ids;
 	double slack;
-	int64_t cap_total;               // total SoA slots
-	soa2d p;                         // tile-binned particles
+	int64_t cap_total;               // total SoA slots per buffer
+	int max_cap;                     // largest tile capacity (sizes perm[] in shared memory)
+	soa2d p, q;                      // current (A) and next (B) tile-binned buffers
 	int64_t* tile_off;               // device, ntiles+1
-	int* tile_np;                    // device, ntiles
+	int* tile_np;                    // device, ntiles: slots in use in p
+	int* tile_np_q;                  // device, ntiles: slots in use in q
 	soa2d mig;                       // migrants list (global cell indices)
 	unsigned int mig_cap;
 	ctl2d* ctl;                      // device
@@ -61,21 +79,29 @@ struct zdev_spec2d {
 };
 
 static const int PUSH_THREADS = 256;
-static const int MAX_TILE = 16;      // cells per tile edge (shared-memory E/B tile is (MAX_TILE+2)^2)
+static const int PUSH_WARPS = PUSH_THREADS / 32;
+static const int XQ_CAP = 64;        // warp-private queue of cell-crossing particles
 
-static void soa_alloc(soa2d& a, int64_t n, int with_tag) {
+static void soa_alloc(soa2d& a, int64_t n, int with_tag, int with_iy) {
 	size_t nn = (size_t) (n > 0 ? n : 1);
-	ZDEV_CHECK(cudaMalloc(&a.ix, nn * 4)); ZDEV_CHECK(cudaMalloc(&a.iy, nn * 4));
+	memset(&a, 0, sizeof(a));
+	ZDEV_CHECK(cudaMalloc(&a.cell, nn * 4));
+	if (with_iy) ZDEV_CHECK(cudaMalloc(&a.iy, nn * 4));
 	ZDEV_CHECK(cudaMalloc(&a.x, nn * 4));  ZDEV_CHECK(cudaMalloc(&a.y, nn * 4));
 	ZDEV_CHECK(cudaMalloc(&a.ux, nn * 4)); ZDEV_CHECK(cudaMalloc(&a.uy, nn * 4));
 	ZDEV_CHECK(cudaMalloc(&a.uz, nn * 4));
-	a.tag = nullptr;
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&a.tag, nn * 4));
 }
 static void soa_free(soa2d& a) {
-	cudaFree(a.ix); cudaFree(a.iy); cudaFree(a.x); cudaFree(a.y);
+	cudaFree(a.cell); cudaFree(a.iy); cudaFree(a.x); cudaFree(a.y);
 	cudaFree(a.ux); cudaFree(a.uy); cudaFree(a.uz); cudaFree(a.tag);
 	memset(&a, 0, sizeof(a));
+}
+
+// supported tile shapes (kernel template instantiations)
+static bool tile_supported(int tx, int ty) {
+	return (tx == 16 && ty == 16) || (tx == 16 && ty == 8) || (tx == 8 && ty == 8) ||
+	       (tx == 8 && ty == 4) || (tx == 4 && ty == 4);
 }
 
 extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int track_ids) {
@@ -85,16 +111,20 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 	s->nx = nx; s->ny = ny;
 	s->ppc_hint = ppc_hint > 0 ? ppc_hint : 1;
 	s->track_ids = track_ids;
-	// tile size: aim at ~4096 particles per tile (amortises the E/B staging and the J
-	// traffic, keeps migration to a few percent); overridable for experiments
+	// tile shape: aim at ~4096 particles per tile (amortises the field staging, keeps the
+	// per-step migration to a few percent, bounds the shared-memory index buffer)
 	int cells = 4096 / s->ppc_hint;
-	int tx = MAX_TILE, ty = MAX_TILE;
-	while (tx * ty > cells && tx * ty > 16) { if (ty >= tx) ty >>= 1; else tx >>= 1; }
+	int tx = 16, ty = 16;
+	if (cells < 256) { tx = 16; ty = 8; }
+	if (cells < 128) { tx = 8; ty = 8; }
+	if (cells < 64)  { tx = 8; ty = 4; }
+	if (cells < 32)  { tx = 4; ty = 4; }
 	if (const char* e = getenv("ZPIC_TILE_X")) tx = atoi(e);
 	if (const char* e = getenv("ZPIC_TILE_Y")) ty = atoi(e);
-	if (tx < 1) tx = 1; if (ty < 1) ty = 1;
-	if (tx > MAX_TILE) tx = MAX_TILE; if (ty > MAX_TILE) ty = MAX_TILE;
-	if (tx > nx) tx = nx; if (ty > ny) ty = ny;
+	if (!tile_supported(tx, ty)) {
+		fprintf(stderr, "(*error*) zpic-b200: unsupported tile shape %dx%d (use 16x16, 16x8, 8x8, 8x4 or 4x4)\n", tx, ty);
+		exit(-1);
+	}
 	s->TX = tx; s->TY = ty;
 	s->ntx = (nx + tx - 1) / tx; s->nty = (ny + ty - 1) / ty;
 	s->ntiles = s->ntx * s->nty;
@@ -102,7 +132,9 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 	if (const char* e = getenv("ZPIC_TILE_SLACK")) s->slack = atof(e);
 	ZDEV_CHECK(cudaMalloc(&s->tile_off, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
 	ZDEV_CHECK(cudaMalloc(&s->tile_np, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&s->tile_np_q, (size_t) s->ntiles * sizeof(int)));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+	ZDEV_CHECK(cudaMemsetAsync(s->tile_np_q, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaMalloc(&s->ctl, sizeof(ctl2d)));
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	s->h_off = new std::vector<int64_t>();
@@ -110,7 +142,7 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 }
 
 static void spec_free_particles(zdev_spec2d* s) {
-	if (s->cap_total) { soa_free(s->p); soa_free(s->mig); }
+	if (s->cap_total) { soa_free(s->p); soa_free(s->q); soa_free(s->mig); }
 	s->cap_total = 0; s->mig_cap = 0;
 }
 
@@ -118,7 +150,7 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	if (!s) return;
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
-	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->ctl);
+	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl);
 	delete s->h_off;
 	delete s;
 }
@@ -128,12 +160,13 @@ extern "C" void zdev_spec2d_tile_info(zdev_spec2d* s, int* tx, int* ty, int* nti
 }
 
 // Lay out tile segments for the given per-tile populations and (re)allocate the SoA
-// arrays.  Capacity per tile = slack * max(population, nominal fill) rounded to 32.
+// buffers.  Capacity per tile = slack * max(population, nominal fill), rounded to 32.
 static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np) {
 	double slack = s->slack;
 	if (slack <= 0.0) slack = (np > (int64_t) 200000000) ? 1.25 : 2.0;
 	std::vector<int64_t>& off = *s->h_off;
 	off.assign(s->ntiles + 1, 0);
+	int64_t max_cap = 0;
 	for (int ty = 0; ty < s->nty; ty++) for (int tx = 0; tx < s->ntx; tx++) {
 		int t = tx + ty * s->ntx;
 		int cx = (tx + 1) * s->TX <= s->nx ? s->TX : s->nx - tx * s->TX;
@@ -143,15 +176,23 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 		int64_t cap = (int64_t) (want * slack) + 64;
 		cap = (cap + 31) & ~(int64_t) 31;
 		off[t + 1] = off[t] + cap;
+		if (cap > max_cap) max_cap = cap;
+	}
+	if (max_cap * 4 > 160 * 1024) {
+		fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed the shared-memory index "
+		        "buffer; use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) max_cap, s->TX, s->TY);
+		exit(-1);
 	}
 	int64_t total = off[s->ntiles];
 	spec_free_particles(s);
-	soa_alloc(s->p, total, s->track_ids);
+	soa_alloc(s->p, total, s->track_ids, 0);
+	soa_alloc(s->q, total, s->track_ids, 0);
 	s->cap_total = total;
-	int64_t mc = total / 4 + 65536;
+	s->max_cap = (int) max_cap;
+	int64_t mc = total / 6 + 65536;
 	if (mc > 0x7fffffff) mc = 0x7fffffff;
 	s->mig_cap = (unsigned int) mc;
-	soa_alloc(s->mig, s->mig_cap, s->track_ids);
+	soa_alloc(s->mig, s->mig_cap, s->track_ids, 1);
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t),
 	                           cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
@@ -172,11 +213,12 @@ __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int 
 	int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= np) return;
 	part_aos r = a[k];
-	int t = r.ix / TX + (r.iy / TY) * ntx;
+	int tx = r.ix / TX, ty = r.iy / TY, t = tx + ty * ntx;
 	int slot = atomicAdd(&tile_np[t], 1);
 	int64_t d = off[t] + slot;
 	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
-	p.ix[d] = r.ix; p.iy[d] = r.iy; p.x[d] = r.x; p.y[d] = r.y; p.ux[d] = r.ux; p.uy[d] = r.uy; p.uz[d] = r.uz;
+	p.cell[d] = (r.ix - tx * TX) | ((r.iy - ty * TY) << 16);
+	p.x[d] = r.x; p.y[d] = r.y; p.ux[d] = r.ux; p.uy[d] = r.uy; p.uz[d] = r.uz;
 	if (p.tag) p.tag[d] = tag0 + (int) k;
 }
 
@@ -235,29 +277,69 @@ extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np)
 	s->np_host += np;
 }
 
+// per tile: number of live slots (slots whose cell is not -1)
+__global__ void k_count_live(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np, int* live) {
+	int t = blockIdx.x;
+	int n = tile_np[t], c = 0;
+	int64_t b = off[t];
+	for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.cell[b + k] >= 0);
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	__shared__ int w[8];
+	if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) { int s = 0; for (int k = 0; k < (int) (blockDim.x >> 5); k++) s += w[k]; live[t] = s; }
+}
+
 // tiles -> AoS.  prefix[t] = first output slot of tile t (ignored when scattering by tag)
 __global__ void k_gather_aos(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np,
-                             const int64_t* __restrict__ prefix, part_aos* __restrict__ out, int by_tag) {
+                             const int64_t* __restrict__ prefix, part_aos* __restrict__ out, int by_tag,
+                             int TX, int TY, int ntx) {
 	int t = blockIdx.x;
 	int n = tile_np[t];
+	int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
 	int64_t b = off[t], o = prefix[t];
-	for (int k = threadIdx.x; k < n; k += blockDim.x) {
-		part_aos r;
-		r.ix = p.ix[b + k]; r.iy = p.iy[b + k]; r.x = p.x[b + k]; r.y = p.y[b + k];
-		r.ux = p.ux[b + k]; r.uy = p.uy[b + k]; r.uz = p.uz[b + k];
-		int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + k;
-		out[d] = r;
+	__shared__ int s_run;
+	if (threadIdx.x == 0) s_run = 0;
+	__syncthreads();
+	for (int k0 = 0; k0 < n; k0 += blockDim.x) {
+		int k = k0 + threadIdx.x;
+		int c = (k < n) ? p.cell[b + k] : -1;
+		bool live = c >= 0;
+		unsigned m = __ballot_sync(0xffffffffu, live);
+		int wbase = 0;
+		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
+		wbase = __shfl_sync(0xffffffffu, wbase, 0);
+		if (live) {
+			part_aos r;
+			r.ix = x0 + (c & 0xffff); r.iy = y0 + (c >> 16);
+			r.x = p.x[b + k]; r.y = p.y[b + k];
+			r.ux = p.ux[b + k]; r.uy = p.uy[b + k]; r.uz = p.uz[b + k];
+			int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
+			out[d] = r;
+		}
 	}
+}
+
+// live particles per tile -> host vector; returns the total
+static int64_t spec_live_counts(zdev_spec2d* s, std::vector<int>& cnt) {
+	int* d_live; ZDEV_CHECK(cudaMalloc(&d_live, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_LAUNCH(k_count_live, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_live);
+	cnt.resize(s->ntiles);
+	ZDEV_CHECK(cudaMemcpyAsync(cnt.data(), d_live, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	cudaFree(d_live);
+	int64_t np = 0;
+	for (int t = 0; t < s->ntiles; t++) np += cnt[t];
+	return np;
 }
 
 extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_np) {
 	if (!s->cap_total) return 0;
-	std::vector<int> cnt(s->ntiles);
-	ZDEV_CHECK(cudaMemcpyAsync(cnt.data(), s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
-	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	std::vector<int> cnt;
+	int64_t np = spec_live_counts(s, cnt);
 	std::vector<int64_t> prefix(s->ntiles);
-	int64_t np = 0;
-	for (int t = 0; t < s->ntiles; t++) { prefix[t] = np; np += cnt[t]; }
+	int64_t acc = 0;
+	for (int t = 0; t < s->ntiles; t++) { prefix[t] = acc; acc += cnt[t]; }
 	s->np_host = np;
 	if (np == 0) return 0;
 	if (np > max_np) {
@@ -269,7 +351,7 @@ extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_
 	ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part_aos)));
 	ZDEV_CHECK(cudaMemcpyAsync(d_prefix, prefix.data(), (size_t) s->ntiles * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_LAUNCH(k_gather_aos, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_prefix, d_aos,
-	            (s->track_ids && s->ids_valid) ? 1 : 0);
+	            (s->track_ids && s->ids_valid) ? 1 : 0, s->TX, s->TY, s->ntx);
 	ZDEV_CHECK(cudaMemcpyAsync(part, d_aos, (size_t) np * sizeof(part_aos), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_prefix); cudaFree(d_aos);
@@ -278,13 +360,9 @@ extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_
 
 extern "C" int64_t zdev_spec2d_np(zdev_spec2d* s) {
 	if (!s->cap_total) return 0;
-	std::vector<int> cnt(s->ntiles);
-	ZDEV_CHECK(cudaMemcpyAsync(cnt.data(), s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
-	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-	int64_t np = 0;
-	for (int t = 0; t < s->ntiles; t++) np += cnt[t];
-	s->np_host = np;
-	return np;
+	std::vector<int> cnt;
+	s->np_host = spec_live_counts(s, cnt);
+	return s->np_host;
 }
 
 // ------------------------------------------------------------------ device-side uniform injection
@@ -337,7 +415,7 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		float a, b, c; normal3(seed, gid0 + k, a, b, c);
 		int kx = k % ppcx, ky = k / ppcx;
 		int64_t d = base + k;
-		p.ix[d] = ix; p.iy[d] = iy;
+		p.cell[d] = lx | (ly << 16);
 		p.x[d] = (float) (dpcx * (kx + 0.5)); p.y[d] = (float) (dpcy * (ky + 0.5));
 		p.ux[d] = uth.x * a + (ufl.x - sx);
 		p.uy[d] = uth.y * b + (ufl.y - sy);
@@ -372,14 +450,11 @@ extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, c
 
 struct push_geom {
 	int nx, ny, nrow;        // grid
-	int TX, TY, ntx;         // tiling
+	int ntx;                 // tiles per row
 };
 
 // scatter one segment's 8 contributions into the global J grid (L2 reductions)
-__device__ __forceinline__ void deposit_seg_global(f3* __restrict__ J, int nrow, const seg2d& s, float qnx, float qny) {
-	float w[8];
-	seg_weights(s, qnx, qny, w);
-	f3* c = J + (s.ix + 1) + (s.iy + 1) * nrow;
+__device__ __forceinline__ void red_weights(f3* __restrict__ c, int nrow, const float w[8]) {
 	atomicAdd(&c[0].x, w[0]);
 	atomicAdd(&c[nrow].x, w[1]);
 	atomicAdd(&c[0].y, w[2]);
@@ -389,56 +464,115 @@ __device__ __forceinline__ void deposit_seg_global(f3* __restrict__ J, int nrow,
 	atomicAdd(&c[nrow].z, w[6]);
 	atomicAdd(&c[nrow + 1].z, w[7]);
 }
+__device__ __forceinline__ void deposit_seg_global(f3* __restrict__ J, int nrow, const seg2d& s, float qnx, float qny) {
+	float w[8];
+	seg_weights(s, qnx, qny, w);
+	red_weights(J + (s.ix + 1) + (s.iy + 1) * nrow, nrow, w);
+}
 
-// One CTA per tile.  Dynamic shared memory: E and B neighbourhoods, (TX+2)*(TY+2) f3 each.
+// one queued cell-crossing move (warp-private shared-memory queue)
+struct xq_entry { int ix, iy, dij; float x0, y0, dx, dy, qvz; };
+
+// split + deposit up to 32 queued moves, one per lane
+__device__ __forceinline__ void drain_crossers(const xq_entry* q, int n, int lane, f3* __restrict__ J, int nrow,
+                                               float qnx, float qny) {
+	if (lane < n) {
+		xq_entry e = q[lane];
+		seg2d vp[3];
+		int vnp = split_trajectory(e.ix, e.iy, (e.dij & 3) - 1, ((e.dij >> 2) & 3) - 1, e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
+		deposit_seg_global(J, nrow, vp[0], qnx, qny);
+		deposit_seg_global(J, nrow, vp[1], qnx, qny);
+		if (vnp > 2) deposit_seg_global(J, nrow, vp[2], qnx, qny);
+	}
+}
+
+// One CTA per tile.  Dynamic shared memory: perm[max_cap] ints.
+template <int TX, int TY>
 __global__ void __launch_bounds__(PUSH_THREADS)
-k_push2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, soa2d mig, unsigned int mig_cap,
+k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
+         int* __restrict__ tile_np_out, soa2d mig, unsigned int mig_cap,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
          push_geom g, zdev_push2d_params prm) {
-	extern __shared__ f3 s_fld[];
-	__shared__ int s_wcnt[2][PUSH_THREADS / 32];
-	__shared__ double s_en[PUSH_THREADS / 32];
+	constexpr int SROW = TX + 2;
+	constexpr int PLANE = SROW * (TY + 2);
+	constexpr int NC = TX * TY;
+	extern __shared__ int s_perm[];
+	__shared__ float s_fld[6 * PLANE];
+	__shared__ int s_cnt[NC];
+	__shared__ int s_wsum[PUSH_WARPS];
+	__shared__ double s_en[PUSH_WARPS];
+	__shared__ xq_entry s_xq[PUSH_WARPS][XQ_CAP];
 
 	const int t = blockIdx.x;
 	const int tx = t % g.ntx, ty = t / g.ntx;
-	const int x0 = tx * g.TX, y0 = ty * g.TY;
-	const int cx = min(g.TX, g.nx - x0), cy = min(g.TY, g.ny - y0);
-	const int srow = g.TX + 2;
-	f3* sE = s_fld;
-	f3* sB = s_fld + srow * (g.TY + 2);
-
-	// stage the field neighbourhood: cells [x0-1, x0+cx] x [y0-1, y0+cy]
-	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += blockDim.x) {
-		int r = k / (cx + 2), c = k - r * (cx + 2);
-		int gi = (x0 + c) + (y0 + r) * g.nrow;        // buffer index of cell (x0-1+c, y0-1+r)
-		sE[c + r * srow] = E[gi];
-		sB[c + r * srow] = B[gi];
-	}
-	__syncthreads();
-	// cell (i,j) of the grid -> sE[(i-x0+1) + (j-y0+1)*srow]
-	const f3* sE0 = sE + 1 + srow;
-	const f3* sB0 = sB + 1 + srow;
-
+	const int x0 = tx * TX, y0 = ty * TY;
+	const int cx = min(TX, g.nx - x0), cy = min(TY, g.ny - y0);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int run_out = 0;
-	double energy = 0.0;
 
-	for (int c0 = 0, it = 0; c0 < n; c0 += PUSH_THREADS, it ^= 1) {
-		const int i = c0 + threadIdx.x;
-		const bool active = i < n;
-		int ix = 0, iy = 0, tag = 0;
+	// ---- stage the field neighbourhood as planes: cells [x0-1, x0+cx] x [y0-1, y0+cy]
+	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += PUSH_THREADS) {
+		int r = k / (cx + 2), c = k - r * (cx + 2);
+		int gi = (x0 + c) + (y0 + r) * g.nrow;        // buffer index of cell (x0-1+c, y0-1+r)
+		f3 e = E[gi], b = B[gi];
+		int o = c + r * SROW;
+		s_fld[o] = e.x; s_fld[o + PLANE] = e.y; s_fld[o + 2 * PLANE] = e.z;
+		s_fld[o + 3 * PLANE] = b.x; s_fld[o + 4 * PLANE] = b.y; s_fld[o + 5 * PLANE] = b.z;
+	}
+	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
+	__syncthreads();
+
+	// ---- phase A: counting sort of slot indices by cell
+	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
+		int c = A.cell[base + i];
+		if (c >= 0) atomicAdd(&s_cnt[(c & 0xffff) + (c >> 16) * TX], 1);
+	}
+	__syncthreads();
+	int nlive;
+	{	// exclusive scan of s_cnt (NC <= 256 == PUSH_THREADS): s_cnt becomes the write cursor
+		int v = (threadIdx.x < NC) ? s_cnt[threadIdx.x] : 0;
+		int incl = v;
+		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+		if (lane == 31) s_wsum[warp] = incl;
+		__syncthreads();
+		int woff = 0, tot = 0;
+		#pragma unroll
+		for (int w = 0; w < PUSH_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
+		if (threadIdx.x < NC) s_cnt[threadIdx.x] = woff + incl - v;
+		nlive = tot;
+		__syncthreads();
+	}
+	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
+		int c = A.cell[base + i];
+		if (c >= 0) s_perm[atomicAdd(&s_cnt[(c & 0xffff) + (c >> 16) * TX], 1)] = i;
+	}
+	__syncthreads();
+
+	// ---- phase B: warps stream the sorted particles, no block barriers from here on
+	xq_entry* xq = s_xq[warp];
+	int nxq = 0;
+	double energy = 0.0;
+	f3* const J0 = J + (x0 + 1) + (y0 + 1) * g.nrow;          // cell (x0,y0)
+
+	for (int p0 = warp * 32; p0 < nlive; p0 += PUSH_THREADS) {
+		const int p = p0 + lane;
+		const bool active = p < nlive;
+		float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+		int key = 0x7fffffff, lx = 0, ly = 0, fate = 0, tag = 0, ncell = -1, gix = 0, giy = 0;
 		float x = 0, y = 0, ux = 0, uy = 0, uz = 0;
-		int fate = 0;                                 // 0 drop / inactive, 1 stay, 2 migrate
+		bool crosses = false;
+		xq_entry xe;
 		if (active) {
-			const int64_t k = base + i;
-			ix = p.ix[k]; iy = p.iy[k]; x = p.x[k]; y = p.y[k];
-			ux = p.ux[k]; uy = p.uy[k]; uz = p.uz[k];
-			if (p.tag) tag = p.tag[k];
+			const int64_t k = base + s_perm[p];
+			const int c = A.cell[k];
+			lx = c & 0xffff; ly = c >> 16;
+			key = lx + ly * TX;
+			x = A.x[k]; y = A.y[k]; ux = A.ux[k]; uy = A.uy[k]; uz = A.uz[k];
+			if (A.tag) tag = A.tag[k];
 
 			f3 Ep, Bp;
-			interp_EB(sE0, sB0, srow, ix - x0, iy - y0, x, y, Ep, Bp);
+			interp_EB_planes<SROW, PLANE>(s_fld, lx, ly, x, y, Ep, Bp);
 			energy += boris(Ep, Bp, prm.tem, ux, uy, uz);
 
 			float rg = 1.0f / sqrtf(1.0f + ux * ux + uy * uy + uz * uz);
@@ -449,14 +583,19 @@ k_push2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_n
 			x1 -= di; y1 -= dj;
 			float qvz = prm.q * uz * rg;
 
-			seg2d vp[3];
-			int vnp = split_trajectory(ix, iy, di, dj, x, y, dx, dy, qvz, vp);
-			deposit_seg_global(J, g.nrow, vp[0], prm.qnx, prm.qny);
-			if (vnp > 1) deposit_seg_global(J, g.nrow, vp[1], prm.qnx, prm.qny);
-			if (vnp > 2) deposit_seg_global(J, g.nrow, vp[2], prm.qnx, prm.qny);
+			crosses = (di | dj) != 0;
+			if (crosses) {
+				xe.ix = x0 + lx; xe.iy = y0 + ly; xe.dij = (di + 1) | ((dj + 1) << 2);
+				xe.x0 = x; xe.y0 = y; xe.dx = dx; xe.dy = dy; xe.qvz = qvz;
+			} else {
+				seg2d s0;
+				s0.x0 = x; s0.y0 = y; s0.dx = dx; s0.dy = dy; s0.x1 = x + dx; s0.y1 = y + dy;
+				s0.qvz = qvz * 0.5f; s0.ix = 0; s0.iy = 0;
+				seg_weights(s0, prm.qnx, prm.qny, w);
+			}
 
 			x = x1; y = y1;
-			ix += di - prm.shift_window; iy += dj;
+			int ix = x0 + lx + di - prm.shift_window, iy = y0 + ly + dj;
 			// boundaries (reference particles.c:1237-1259)
 			fate = 1;
 			if (prm.moving_window) {
@@ -465,27 +604,56 @@ k_push2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_n
 				ix += ((ix < 0) ? g.nx : 0) - ((ix >= g.nx) ? g.nx : 0);
 			}
 			iy += ((iy < 0) ? g.ny : 0) - ((iy >= g.ny) ? g.ny : 0);
-			if (fate && (ix < x0 || ix >= x0 + cx || iy < y0 || iy >= y0 + cy)) fate = 2;
+			const int nlx = ix - x0, nly = iy - y0;
+			if (fate) {
+				if (nlx < 0 || nlx >= cx || nly < 0 || nly >= cy) { fate = 2; gix = ix; giy = iy; }
+				else ncell = nlx | (nly << 16);
+			}
 		}
 
-		// in-place compaction of the survivors of this chunk
-		const unsigned stay_m = __ballot_sync(0xffffffffu, fate == 1);
+		// --- current of the non-crossing particles: segmented warp scan over runs of equal cell
+		{
+			const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+			const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const bool take = (lane - d) >= start;
+				#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					float u = __shfl_up_sync(0xffffffffu, w[q], d);
+					if (take) w[q] += u;
+				}
+			}
+			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+			if (tail && active) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
+		}
+
+		// --- cell crossers: queue, drain 32 at a time
+		{
+			const unsigned xm = __ballot_sync(0xffffffffu, crosses);
+			if (xm) {
+				if (crosses) xq[nxq + __popc(xm & ((1u << lane) - 1))] = xe;
+				nxq += __popc(xm);
+				__syncwarp();
+				if (nxq >= 32) {
+					drain_crossers(xq + nxq - 32, 32, lane, J, g.nrow, prm.qnx, prm.qny);
+					nxq -= 32;
+					__syncwarp();
+				}
+			}
+		}
+
+		// --- write the survivors to their sorted slot in B, route the leavers
+		if (active) {
+			const int64_t d = base + p;
+			Bo.cell[d] = ncell;
+			if (fate == 1) {
+				Bo.x[d] = x; Bo.y[d] = y; Bo.ux[d] = ux; Bo.uy[d] = uy; Bo.uz[d] = uz;
+				if (Bo.tag) Bo.tag[d] = tag;
+			}
+		}
 		const unsigned mig_m = __ballot_sync(0xffffffffu, fate == 2);
-		if (lane == 0) s_wcnt[it][warp] = __popc(stay_m);
-		__syncthreads();      // every load of this chunk precedes every store
-		int woff = 0, total = 0;
-		#pragma unroll
-		for (int w = 0; w < PUSH_THREADS / 32; w++) {
-			int c = s_wcnt[it][w];
-			woff += (w < warp) ? c : 0;
-			total += c;
-		}
-		if (fate == 1) {
-			const int64_t d = base + run_out + woff + __popc(stay_m & ((1u << lane) - 1));
-			p.ix[d] = ix; p.iy[d] = iy; p.x[d] = x; p.y[d] = y; p.ux[d] = ux; p.uy[d] = uy; p.uz[d] = uz;
-			if (p.tag) p.tag[d] = tag;
-		}
-		run_out += total;
 		if (mig_m) {
 			unsigned int mbase = 0;
 			if (lane == 0) mbase = atomicAdd(&ctl->n_mig, (unsigned int) __popc(mig_m));
@@ -493,46 +661,67 @@ k_push2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_n
 			if (fate == 2) {
 				unsigned int d = mbase + __popc(mig_m & ((1u << lane) - 1));
 				if (d < mig_cap) {
-					mig.ix[d] = ix; mig.iy[d] = iy; mig.x[d] = x; mig.y[d] = y;
+					mig.cell[d] = gix; mig.iy[d] = giy; mig.x[d] = x; mig.y[d] = y;
 					mig.ux[d] = ux; mig.uy[d] = uy; mig.uz[d] = uz;
 					if (mig.tag) mig.tag[d] = tag;
 				} else atomicOr(&ctl->flags, 2u);
 			}
 		}
 	}
+	if (nxq) drain_crossers(xq, nxq, lane, J, g.nrow, prm.qnx, prm.qny);
 
-	// tile epilogue: population, energy
+	// ---- tile epilogue: slots in use, live count, energy
 	for (int o = 16; o > 0; o >>= 1) energy += __shfl_down_sync(0xffffffffu, energy, o);
 	if (lane == 0) s_en[warp] = energy;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		double e = 0;
-		for (int w = 0; w < PUSH_THREADS / 32; w++) e += s_en[w];
-		if (n > 0) atomicAdd(&ctl->energy, e);
-		tile_np[t] = run_out;
-		if (run_out) atomicAdd(&ctl->np, (unsigned long long) run_out);
+		for (int w = 0; w < PUSH_WARPS; w++) e += s_en[w];
+		if (nlive > 0) atomicAdd(&ctl->energy, e);
+		tile_np_out[t] = nlive;
 	}
 }
 
-// append the migrants to their destination tiles
+// append the migrants to their destination tiles and count the population
 __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, soa2d mig,
-                            unsigned int mig_cap, ctl2d* __restrict__ ctl, push_geom g) {
+                            unsigned int mig_cap, ctl2d* __restrict__ ctl, int TX, int TY, int ntx) {
 	unsigned int n = ctl->n_mig;
 	if (n > mig_cap) n = mig_cap;
-	unsigned int accepted = 0;
 	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-		int ix = mig.ix[k], iy = mig.iy[k];
-		int t = ix / g.TX + (iy / g.TY) * g.ntx;
+		int ix = mig.cell[k], iy = mig.iy[k];
+		int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 		int slot = atomicAdd(&tile_np[t], 1);
 		int64_t d = tile_off[t] + slot;
 		if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
-		p.ix[d] = ix; p.iy[d] = iy; p.x[d] = mig.x[k]; p.y[d] = mig.y[k];
+		p.cell[d] = (ix - tx * TX) | ((iy - ty * TY) << 16);
+		p.x[d] = mig.x[k]; p.y[d] = mig.y[k];
 		p.ux[d] = mig.ux[k]; p.uy[d] = mig.uy[k]; p.uz[d] = mig.uz[k];
 		if (p.tag) p.tag[d] = mig.tag[k];
-		accepted++;
 	}
-	for (int o = 16; o > 0; o >>= 1) accepted += __shfl_down_sync(0xffffffffu, accepted, o);
-	if ((threadIdx.x & 31) == 0 && accepted) atomicAdd(&ctl->np, (unsigned long long) accepted);
+}
+
+// total live particles (slots with cell >= 0) -> ctl->np
+__global__ void k_count_total(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np, int ntiles, ctl2d* ctl) {
+	unsigned long long c = 0;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		int n = tile_np[t];
+		int64_t b = off[t];
+		for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.cell[b + k] >= 0);
+	}
+	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->np, c);
+}
+
+template <int TX, int TY>
+static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const push_geom& g, const zdev_push2d_params& prm) {
+	size_t smem = (size_t) s->max_cap * sizeof(int);
+	static size_t configured = 0;
+	if (smem > configured) {
+		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		configured = smem;
+	}
+	ZDEV_LAUNCH((k_push2d<TX, TY>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+	            s->mig, s->mig_cap, s->ctl, E, B, J, g, prm);
 }
 
 extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid2d* gcur, const zdev_push2d_params* prm) {
@@ -542,35 +731,51 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	}
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
-	push_geom g = { s->nx, s->ny, s->nx + 3, s->TX, s->TY, s->ntx };
-	size_t smem = (size_t) 2 * (s->TX + 2) * (s->TY + 2) * sizeof(f3);
-	ZDEV_LAUNCH(k_push2d, s->ntiles, PUSH_THREADS, smem, s->p, s->tile_off, s->tile_np, s->mig, s->mig_cap, s->ctl,
-	            zdev_grid2d_Epart(grid), zdev_grid2d_Bpart(grid), zdev_grid2d_J(gcur), g, *prm);
-	int mg = 2 * zdev_num_sm;
-	ZDEV_LAUNCH(k_migrate2d, mg, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->mig_cap, s->ctl, g);
+	push_geom g = { s->nx, s->ny, s->nx + 3, s->ntx };
+	const f3* E = zdev_grid2d_Epart(grid); const f3* B = zdev_grid2d_Bpart(grid); f3* J = zdev_grid2d_J(gcur);
+	if      (s->TX == 16 && s->TY == 16) launch_push<16, 16>(s, E, B, J, g, *prm);
+	else if (s->TX == 16 && s->TY == 8)  launch_push<16, 8>(s, E, B, J, g, *prm);
+	else if (s->TX == 8  && s->TY == 8)  launch_push<8, 8>(s, E, B, J, g, *prm);
+	else if (s->TX == 8  && s->TY == 4)  launch_push<8, 4>(s, E, B, J, g, *prm);
+	else                                 launch_push<4, 4>(s, E, B, J, g, *prm);
+	// B becomes the current buffer
+	{ soa2d t = s->p; s->p = s->q; s->q = t; }
+	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
+	ZDEV_LAUNCH(k_migrate2d, 2 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->mig_cap, s->ctl,
+	            s->TX, s->TY, s->ntx);
 	if (prm->moving_window) s->ids_valid = 0;
 }
 
 extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* np) {
 	ctl2d h;
+	memset(&h, 0, sizeof h);
+	if (s->cap_total && np)
+		ZDEV_LAUNCH(k_count_total, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->ntiles, s->ctl);
 	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof(h), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	check_flags(s, h.flags);
-	s->np_host = (int64_t) h.np;
+	if (np) {
+		// the count is accumulated into ctl->np by k_count_total: reset so a second fetch does not double it
+		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->np, 0, sizeof(unsigned long long), zdev_strm));
+		s->np_host = (int64_t) h.np;
+		*np = (int64_t) h.np;
+	}
 	if (energy_sum) *energy_sum = h.energy;
-	if (np) *np = (int64_t) h.np;
 }
 
 // ------------------------------------------------------------------ charge deposit
 
 // reference spec_deposit_charge, em2d/particles.c:1289-1324 (node centred, linear)
 __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np,
-                                 float* __restrict__ rho, int nrow, float q) {
+                                 float* __restrict__ rho, int nrow, float q, int TX, int TY, int ntx) {
 	int t = blockIdx.x;
 	int n = tile_np[t];
+	int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
 	int64_t b = off[t];
 	for (int k = threadIdx.x; k < n; k += blockDim.x) {
-		int idx = p.ix[b + k] + nrow * p.iy[b + k];
+		int c = p.cell[b + k];
+		if (c < 0) continue;
+		int idx = (x0 + (c & 0xffff)) + nrow * (y0 + (c >> 16));
 		float w1 = p.x[b + k], w2 = p.y[b + k];
 		atomicAdd(&rho[idx], (1.0f - w1) * (1.0f - w2) * q);
 		atomicAdd(&rho[idx + 1], (w1) * (1.0f - w2) * q);
@@ -578,21 +783,22 @@ __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const
 		atomicAdd(&rho[idx + 1 + nrow], (w1) * (w2) * q);
 	}
 }
-__global__ void k_charge_fold(float* __restrict__ rho, int nx, int ny, int moving_window) {
+__global__ void k_charge_fold(float* __restrict__ rho, int nx, int ny, int mode) {
 	int nrow = nx + 1;
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	// x fold first (all rows), then y fold: done by two launches of this kernel
-	if (moving_window >= 0) { if (!moving_window && k <= ny) rho[(size_t) k * nrow] += rho[nx + (size_t) k * nrow]; }
-	else { if (k <= nx) rho[k] += rho[k + (size_t) ny * nrow]; }
+	if (mode == 0) { if (k <= ny) rho[(size_t) k * nrow] += rho[nx + (size_t) k * nrow]; }   // x fold
+	else           { if (k <= nx) rho[k] += rho[k + (size_t) ny * nrow]; }                   // y fold
 }
 
 extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_window, float* charge) {
 	size_t n = (size_t) (s->nx + 1) * (s->ny + 1);
 	float* d_rho; ZDEV_CHECK(cudaMalloc(&d_rho, n * sizeof(float)));
 	ZDEV_CHECK(cudaMemcpyAsync(d_rho, charge, n * sizeof(float), cudaMemcpyHostToDevice, zdev_strm));
-	if (s->cap_total) ZDEV_LAUNCH(k_deposit_charge, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_rho, s->nx + 1, q);
-	ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->ny + 1, 128), 128, 0, d_rho, s->nx, s->ny, moving_window ? 1 : 0);
-	ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->nx + 1, 128), 128, 0, d_rho, s->nx, s->ny, -1);
+	if (s->cap_total)
+		ZDEV_LAUNCH(k_deposit_charge, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_rho, s->nx + 1, q,
+		            s->TX, s->TY, s->ntx);
+	if (!moving_window) ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->ny + 1, 128), 128, 0, d_rho, s->nx, s->ny, 0);
+	ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->nx + 1, 128), 128, 0, d_rho, s->nx, s->ny, 1);
 	ZDEV_CHECK(cudaMemcpyAsync(charge, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_rho);
