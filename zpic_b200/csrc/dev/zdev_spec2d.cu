@@ -1,11 +1,14 @@
 // zpic-b200 :: em2d particle species on the device.
 //
 // Data layout in HBM.  The grid is cut into tiles of TX x TY cells; every tile owns a
-// fixed-capacity segment [tile_off[t], tile_off[t+1]) of six SoA arrays
-//     cell (lx | ly<<16, tile-local cell; -1 = empty slot), x, y, ux, uy, uz
-// (24 B per particle; an optional 7th array carries the injection tag), of which the
-// first tile_np[t] slots are in use.  There are two such buffers, A and B, and every
-// step streams A -> B.
+// fixed-capacity segment [tile_off[t], tile_off[t+1]) of
+//     rec[]  24-byte records {x, y, ux, uy, uz, cell}, cell = lx | ly<<16 (tile local),
+//            moved with three 64-bit accesses off one address register;
+//     key[]  16-bit cell number lx + ly*TX (0xffff = empty slot), the only thing the
+//            index sort has to read;
+//     tag[]  optional injection index (parity runs),
+// of which the first tile_np[t] slots are in use.  There are two such buffers, A and B,
+// and every step streams A -> B.
 //
 // One CTA advances one tile (k_push2d):
 //   phase A  an index-only counting sort of the tile's particles by cell, done in shared
@@ -22,7 +25,7 @@
 //            (coalesced); particles that left the tile go to a global migrants list and
 //            leave an empty slot behind.
 // k_migrate2d then appends the migrants to their destination tiles in B.
-// Per step a particle is read once and written once (48 B; 56 B with the reference's
+// Per step a particle is read once and written once (2 x 26 B; 56 B with the reference's
 // 28-byte record), plus the few percent that migrate.
 //
 // Replaces reference em2d/particles.c:1104-1269 (spec_advance incl. boundaries and
@@ -43,13 +46,29 @@ int zdev_grid2d_ny(zdev_grid2d* g);
 // host AoS record (include/em2d/particles.h t_part)
 struct part_aos { int ix, iy; float x, y, ux, uy, uz; };
 
-// SoA view handed to kernels by value
+// device particle record, 24 bytes, 8-byte aligned
+struct rec24 { float x, y, ux, uy, uz; int cell; };
+static_assert(sizeof(rec24) == 24, "rec24 must be 24 bytes");
+#define KEY_EMPTY 0xffffu
+
+// buffer view handed to kernels by value
 struct soa2d {
-	int *cell;           // tile buffers: lx | ly<<16 (or -1); migrants list: global ix
+	rec24* rec;          // tile buffers: cell = lx | ly<<16; migrants list: cell = global ix
+	unsigned short* key; // tile buffers only
 	int *iy;             // migrants list only: global iy
-	float *x, *y, *ux, *uy, *uz;
 	int *tag;            // null unless ids are tracked
 };
+
+__device__ __forceinline__ rec24 rec_load(const rec24* p) {
+	const float2* q = reinterpret_cast<const float2*>(p);
+	float2 a = q[0], b = q[1], c = q[2];
+	rec24 r; r.x = a.x; r.y = a.y; r.ux = b.x; r.uy = b.y; r.uz = c.x; r.cell = __float_as_int(c.y);
+	return r;
+}
+__device__ __forceinline__ void rec_store(rec24* p, float x, float y, float ux, float uy, float uz, int cell) {
+	float2* q = reinterpret_cast<float2*>(p);
+	q[0] = make_float2(x, y); q[1] = make_float2(ux, uy); q[2] = make_float2(uz, __int_as_float(cell));
+}
 
 // control block in device memory, zeroed at the start of every advance
 struct ctl2d {
@@ -82,19 +101,16 @@ static const int PUSH_THREADS = 256;
 static const int PUSH_WARPS = PUSH_THREADS / 32;
 static const int XQ_CAP = 64;        // warp-private queue of cell-crossing particles
 
-static void soa_alloc(soa2d& a, int64_t n, int with_tag, int with_iy) {
+static void soa_alloc(soa2d& a, int64_t n, int with_tag, int is_mig) {
 	size_t nn = (size_t) (n > 0 ? n : 1);
 	memset(&a, 0, sizeof(a));
-	ZDEV_CHECK(cudaMalloc(&a.cell, nn * 4));
-	if (with_iy) ZDEV_CHECK(cudaMalloc(&a.iy, nn * 4));
-	ZDEV_CHECK(cudaMalloc(&a.x, nn * 4));  ZDEV_CHECK(cudaMalloc(&a.y, nn * 4));
-	ZDEV_CHECK(cudaMalloc(&a.ux, nn * 4)); ZDEV_CHECK(cudaMalloc(&a.uy, nn * 4));
-	ZDEV_CHECK(cudaMalloc(&a.uz, nn * 4));
+	ZDEV_CHECK(cudaMalloc(&a.rec, nn * sizeof(rec24)));
+	if (is_mig) ZDEV_CHECK(cudaMalloc(&a.iy, nn * 4));
+	else ZDEV_CHECK(cudaMalloc(&a.key, nn * 2));
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&a.tag, nn * 4));
 }
 static void soa_free(soa2d& a) {
-	cudaFree(a.cell); cudaFree(a.iy); cudaFree(a.x); cudaFree(a.y);
-	cudaFree(a.ux); cudaFree(a.uy); cudaFree(a.uz); cudaFree(a.tag);
+	cudaFree(a.rec); cudaFree(a.key); cudaFree(a.iy); cudaFree(a.tag);
 	memset(&a, 0, sizeof(a));
 }
 
@@ -189,7 +205,7 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	soa_alloc(s->q, total, s->track_ids, 0);
 	s->cap_total = total;
 	s->max_cap = (int) max_cap;
-	int64_t mc = total / 6 + 65536;
+	int64_t mc = total / 8 + 65536;
 	if (mc > 0x7fffffff) mc = 0x7fffffff;
 	s->mig_cap = (unsigned int) mc;
 	soa_alloc(s->mig, s->mig_cap, s->track_ids, 1);
@@ -217,8 +233,9 @@ __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int 
 	int slot = atomicAdd(&tile_np[t], 1);
 	int64_t d = off[t] + slot;
 	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
-	p.cell[d] = (r.ix - tx * TX) | ((r.iy - ty * TY) << 16);
-	p.x[d] = r.x; p.y[d] = r.y; p.ux[d] = r.ux; p.uy[d] = r.uy; p.uz[d] = r.uz;
+	const int lx = r.ix - tx * TX, ly = r.iy - ty * TY;
+	rec_store(p.rec + d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
+	p.key[d] = (unsigned short) (lx + ly * TX);
 	if (p.tag) p.tag[d] = tag0 + (int) k;
 }
 
@@ -282,7 +299,7 @@ __global__ void k_count_live(soa2d p, const int64_t* __restrict__ off, const int
 	int t = blockIdx.x;
 	int n = tile_np[t], c = 0;
 	int64_t b = off[t];
-	for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.cell[b + k] >= 0);
+	for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.key[b + k] != KEY_EMPTY);
 	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
 	__shared__ int w[8];
 	if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = c;
@@ -303,17 +320,16 @@ __global__ void k_gather_aos(soa2d p, const int64_t* __restrict__ off, const int
 	__syncthreads();
 	for (int k0 = 0; k0 < n; k0 += blockDim.x) {
 		int k = k0 + threadIdx.x;
-		int c = (k < n) ? p.cell[b + k] : -1;
-		bool live = c >= 0;
+		bool live = (k < n) && p.key[b + k] != KEY_EMPTY;
 		unsigned m = __ballot_sync(0xffffffffu, live);
 		int wbase = 0;
 		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
 		wbase = __shfl_sync(0xffffffffu, wbase, 0);
 		if (live) {
+			rec24 v = rec_load(p.rec + b + k);
 			part_aos r;
-			r.ix = x0 + (c & 0xffff); r.iy = y0 + (c >> 16);
-			r.x = p.x[b + k]; r.y = p.y[b + k];
-			r.ux = p.ux[b + k]; r.uy = p.uy[b + k]; r.uz = p.uz[b + k];
+			r.ix = x0 + (v.cell & 0xffff); r.iy = y0 + (v.cell >> 16);
+			r.x = v.x; r.y = v.y; r.ux = v.ux; r.uy = v.uy; r.uz = v.uz;
 			int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
 			out[d] = r;
 		}
@@ -415,11 +431,9 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		float a, b, c; normal3(seed, gid0 + k, a, b, c);
 		int kx = k % ppcx, ky = k / ppcx;
 		int64_t d = base + k;
-		p.cell[d] = lx | (ly << 16);
-		p.x[d] = (float) (dpcx * (kx + 0.5)); p.y[d] = (float) (dpcy * (ky + 0.5));
-		p.ux[d] = uth.x * a + (ufl.x - sx);
-		p.uy[d] = uth.y * b + (ufl.y - sy);
-		p.uz[d] = uth.z * c + (ufl.z - sz);
+		rec_store(p.rec + d, (float) (dpcx * (kx + 0.5)), (float) (dpcy * (ky + 0.5)),
+		          uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz), lx | (ly << 16));
+		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = (int) (gid0 + k);
 	}
 	if (lx == 0 && ly == 0) {
@@ -525,8 +539,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 
 	// ---- phase A: counting sort of slot indices by cell
 	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
-		int c = A.cell[base + i];
-		if (c >= 0) atomicAdd(&s_cnt[(c & 0xffff) + (c >> 16) * TX], 1);
+		unsigned c = A.key[base + i];
+		if (c != KEY_EMPTY) atomicAdd(&s_cnt[c], 1);
 	}
 	__syncthreads();
 	int nlive;
@@ -544,8 +558,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		__syncthreads();
 	}
 	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
-		int c = A.cell[base + i];
-		if (c >= 0) s_perm[atomicAdd(&s_cnt[(c & 0xffff) + (c >> 16) * TX], 1)] = i;
+		unsigned c = A.key[base + i];
+		if (c != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c], 1)] = i;
 	}
 	__syncthreads();
 
@@ -565,17 +579,17 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		xq_entry xe;
 		if (active) {
 			const int64_t k = base + s_perm[p];
-			const int c = A.cell[k];
-			lx = c & 0xffff; ly = c >> 16;
+			const rec24 v = rec_load(A.rec + k);
+			lx = v.cell & 0xffff; ly = v.cell >> 16;
 			key = lx + ly * TX;
-			x = A.x[k]; y = A.y[k]; ux = A.ux[k]; uy = A.uy[k]; uz = A.uz[k];
+			x = v.x; y = v.y; ux = v.ux; uy = v.uy; uz = v.uz;
 			if (A.tag) tag = A.tag[k];
 
 			f3 Ep, Bp;
 			interp_EB_planes<SROW, PLANE>(s_fld, lx, ly, x, y, Ep, Bp);
 			energy += boris(Ep, Bp, prm.tem, ux, uy, uz);
 
-			float rg = 1.0f / sqrtf(1.0f + ux * ux + uy * uy + uz * uz);
+			float rg = div_exact(1.0f, sqrt_exact(1.0f + ux * ux + uy * uy + uz * uz));
 			float dx = prm.dt_dx * rg * ux;
 			float dy = prm.dt_dy * rg * uy;
 			float x1 = x + dx, y1 = y + dy;
@@ -611,22 +625,54 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			}
 		}
 
-		// --- current of the non-crossing particles: segmented warp scan over runs of equal cell
+		// --- current of the non-crossing particles, combined per run of equal cell
 		{
 			const int prev = __shfl_up_sync(0xffffffffu, key, 1);
 			const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const bool take = (lane - d) >= start;
+			if (heads == 1u) {
+				// all 32 lanes in one cell: transposed butterfly, 9 shuffles for the 8 sums, after
+				// which lane 4*k holds the total of contribution k and issues its single reduction
+				float v4[4], v2[2], v1;
+				const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
 				#pragma unroll
-				for (int q = 0; q < 8; q++) {
-					float u = __shfl_up_sync(0xffffffffu, w[q], d);
-					if (take) w[q] += u;
+				for (int q = 0; q < 4; q++) {
+					float send = b16 ? w[q] : w[q + 4], keep = b16 ? w[q + 4] : w[q];
+					v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
 				}
+				#pragma unroll
+				for (int q = 0; q < 2; q++) {
+					float send = b8 ? v4[q] : v4[q + 2], keep = b8 ? v4[q + 2] : v4[q];
+					v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+				}
+				{
+					float send = b4 ? v2[0] : v2[1], keep = b4 ? v2[1] : v2[0];
+					v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+				}
+				v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+				v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+				if ((lane & 3) == 0) {
+					const int k = lane >> 2;                       // contribution index, see seg_weights()
+					const int comp = (k < 2) ? 0 : ((k < 4) ? 1 : 2);
+					const int right = (k == 3) | (k == 5) | (k == 7);
+					const int up = (k == 1) | (k == 6) | (k == 7);
+					float* a = reinterpret_cast<float*>(J0 + lx + right + (ly + up) * g.nrow) + comp;
+					atomicAdd(a, v1);
+				}
+			} else {
+				// general case: segmented inclusive scan, the last lane of each run holds its totals
+				const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+				#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const bool take = (lane - d) >= start;
+					#pragma unroll
+					for (int q = 0; q < 8; q++) {
+						float u = __shfl_up_sync(0xffffffffu, w[q], d);
+						if (take) w[q] += u;
+					}
+				}
+				const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+				if (tail && active) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
 			}
-			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-			if (tail && active) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
 		}
 
 		// --- cell crossers: queue, drain 32 at a time
@@ -647,9 +693,9 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		// --- write the survivors to their sorted slot in B, route the leavers
 		if (active) {
 			const int64_t d = base + p;
-			Bo.cell[d] = ncell;
+			Bo.key[d] = (fate == 1) ? (unsigned short) ((ncell & 0xffff) + (ncell >> 16) * TX) : (unsigned short) KEY_EMPTY;
 			if (fate == 1) {
-				Bo.x[d] = x; Bo.y[d] = y; Bo.ux[d] = ux; Bo.uy[d] = uy; Bo.uz[d] = uz;
+				rec_store(Bo.rec + d, x, y, ux, uy, uz, ncell);
 				if (Bo.tag) Bo.tag[d] = tag;
 			}
 		}
@@ -661,8 +707,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			if (fate == 2) {
 				unsigned int d = mbase + __popc(mig_m & ((1u << lane) - 1));
 				if (d < mig_cap) {
-					mig.cell[d] = gix; mig.iy[d] = giy; mig.x[d] = x; mig.y[d] = y;
-					mig.ux[d] = ux; mig.uy[d] = uy; mig.uz[d] = uz;
+					rec_store(mig.rec + d, x, y, ux, uy, uz, gix);
+					mig.iy[d] = giy;
 					if (mig.tag) mig.tag[d] = tag;
 				} else atomicOr(&ctl->flags, 2u);
 			}
@@ -688,14 +734,15 @@ __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* 
 	unsigned int n = ctl->n_mig;
 	if (n > mig_cap) n = mig_cap;
 	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-		int ix = mig.cell[k], iy = mig.iy[k];
+		rec24 v = rec_load(mig.rec + k);
+		int ix = v.cell, iy = mig.iy[k];
 		int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 		int slot = atomicAdd(&tile_np[t], 1);
 		int64_t d = tile_off[t] + slot;
 		if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
-		p.cell[d] = (ix - tx * TX) | ((iy - ty * TY) << 16);
-		p.x[d] = mig.x[k]; p.y[d] = mig.y[k];
-		p.ux[d] = mig.ux[k]; p.uy[d] = mig.uy[k]; p.uz[d] = mig.uz[k];
+		const int lx = ix - tx * TX, ly = iy - ty * TY;
+		rec_store(p.rec + d, v.x, v.y, v.ux, v.uy, v.uz, lx | (ly << 16));
+		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = mig.tag[k];
 	}
 }
@@ -706,7 +753,7 @@ __global__ void k_count_total(soa2d p, const int64_t* __restrict__ off, const in
 	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
 		int n = tile_np[t];
 		int64_t b = off[t];
-		for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.cell[b + k] >= 0);
+		for (int k = threadIdx.x; k < n; k += blockDim.x) c += (p.key[b + k] != KEY_EMPTY);
 	}
 	for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
 	if ((threadIdx.x & 31) == 0 && c) atomicAdd(&ctl->np, c);
@@ -773,10 +820,10 @@ __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const
 	int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
 	int64_t b = off[t];
 	for (int k = threadIdx.x; k < n; k += blockDim.x) {
-		int c = p.cell[b + k];
-		if (c < 0) continue;
-		int idx = (x0 + (c & 0xffff)) + nrow * (y0 + (c >> 16));
-		float w1 = p.x[b + k], w2 = p.y[b + k];
+		if (p.key[b + k] == KEY_EMPTY) continue;
+		rec24 v = rec_load(p.rec + b + k);
+		int idx = (x0 + (v.cell & 0xffff)) + nrow * (y0 + (v.cell >> 16));
+		float w1 = v.x, w2 = v.y;
 		atomicAdd(&rho[idx], (1.0f - w1) * (1.0f - w2) * q);
 		atomicAdd(&rho[idx + 1], (w1) * (1.0f - w2) * q);
 		atomicAdd(&rho[idx + nrow], (1.0f - w1) * (w2) * q);
