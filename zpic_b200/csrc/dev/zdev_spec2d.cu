@@ -569,25 +569,44 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	double energy = 0.0;
 	f3* const J0 = J + (x0 + 1) + (y0 + 1) * g.nrow;          // cell (x0,y0)
 
+	// software pipeline: the record of the next iteration is requested before the current one
+	// is processed, so its HBM/L2 latency hides behind ~600 instructions of arithmetic
+	rec24 nv; int ntag = 0;
+	{
+		const int pn = warp * 32 + lane;
+		const int64_t k = base + ((pn < nlive) ? s_perm[pn] : 0);
+		nv = rec_load(A.rec + k);
+		if (A.tag) ntag = A.tag[k];
+	}
+
 	for (int p0 = warp * 32; p0 < nlive; p0 += PUSH_THREADS) {
 		const int p = p0 + lane;
 		const bool active = p < nlive;
-		float w[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-		int key = 0x7fffffff, lx = 0, ly = 0, fate = 0, tag = 0, ncell = -1, gix = 0, giy = 0;
-		float x = 0, y = 0, ux = 0, uy = 0, uz = 0;
-		bool crosses = false;
-		xq_entry xe;
-		if (active) {
-			const int64_t k = base + s_perm[p];
-			const rec24 v = rec_load(A.rec + k);
-			lx = v.cell & 0xffff; ly = v.cell >> 16;
-			key = lx + ly * TX;
-			x = v.x; y = v.y; ux = v.ux; uy = v.uy; uz = v.uz;
-			if (A.tag) tag = A.tag[k];
+		const rec24 v = nv;
+		const int tag = ntag;
+		{
+			const int pn = p + PUSH_THREADS;
+			const int64_t k = base + ((pn < nlive) ? s_perm[pn] : 0);
+			nv = rec_load(A.rec + k);
+			if (A.tag) ntag = A.tag[k];
+		}
 
+		// Lanes past the end of the tile (last iteration only) run the arithmetic on whatever
+		// record slot 0 holds - a valid particle of this tile or stale finite data clamped to a
+		// valid cell - and are masked out of every side effect below.
+		float w[8];
+		int lx = v.cell & 0xffff, ly = (v.cell >> 16) & 0xffff;
+		if (!active) { lx = 0; ly = 0; }
+		const int key = active ? lx + ly * TX : 0x7fffffff;
+		float x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
+		int fate, ncell = -1, gix = 0, giy = 0;
+		bool crosses;
+		xq_entry xe;
+		{
 			f3 Ep, Bp;
 			interp_EB_planes<SROW, PLANE>(s_fld, lx, ly, x, y, Ep, Bp);
-			energy += boris(Ep, Bp, prm.tem, ux, uy, uz);
+			const float en = boris(Ep, Bp, prm.tem, ux, uy, uz);
+			energy += active ? (double) en : 0.0;
 
 			float rg = div_exact(1.0f, sqrt_exact(1.0f + ux * ux + uy * uy + uz * uz));
 			float dx = prm.dt_dx * rg * ux;
@@ -597,21 +616,23 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			x1 -= di; y1 -= dj;
 			float qvz = prm.q * uz * rg;
 
-			crosses = (di | dj) != 0;
-			if (crosses) {
-				xe.ix = x0 + lx; xe.iy = y0 + ly; xe.dij = (di + 1) | ((dj + 1) << 2);
-				xe.x0 = x; xe.y0 = y; xe.dx = dx; xe.dy = dy; xe.qvz = qvz;
-			} else {
+			crosses = active && ((di | dj) != 0);
+			xe.ix = x0 + lx; xe.iy = y0 + ly; xe.dij = (di + 1) | ((dj + 1) << 2);
+			xe.x0 = x; xe.y0 = y; xe.dx = dx; xe.dy = dy; xe.qvz = qvz;
+			{
 				seg2d s0;
 				s0.x0 = x; s0.y0 = y; s0.dx = dx; s0.dy = dy; s0.x1 = x + dx; s0.y1 = y + dy;
 				s0.qvz = qvz * 0.5f; s0.ix = 0; s0.iy = 0;
 				seg_weights(s0, prm.qnx, prm.qny, w);
+				const bool zero = crosses || !active;      // crossers deposit through the queue
+				#pragma unroll
+				for (int q = 0; q < 8; q++) w[q] = zero ? 0.0f : w[q];
 			}
 
 			x = x1; y = y1;
 			int ix = x0 + lx + di - prm.shift_window, iy = y0 + ly + dj;
 			// boundaries (reference particles.c:1237-1259)
-			fate = 1;
+			fate = active ? 1 : 0;
 			if (prm.moving_window) {
 				if (ix < 0 || ix >= g.nx) fate = 0;
 			} else {
