@@ -8,7 +8,8 @@ _cache = {}
 
 
 def lib_path(code="em2d"):
-    return os.path.join(_HERE, "lib", "libzpic_b200_%s.so" % code)
+    # ZPIC_LIB_SUFFIX selects an experimental build variant (see zpic_b200/build.py)
+    return os.path.join(_HERE, "lib", "libzpic_b200_%s%s.so" % (code, os.environ.get("ZPIC_LIB_SUFFIX", "")))
 
 
 def load(code="em2d"):

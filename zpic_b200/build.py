@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
     "-std=c++17", "-Xcompiler", "-fPIC",
     "-I" + os.path.join(REPO, "include"), "-I" + os.path.join(CSRC, "dev"),
-]
+] + os.environ.get("ZPIC_NVCC_EXTRA", "").split()
 # host C: strict IEEE, no contraction (same flags as the strict oracle build)
 CC_FLAGS = ["-O2", "-std=gnu99", "-ffp-contract=off", "-fPIC", "-Wall", "-Wno-unused-result",
             "-I" + os.path.join(REPO, "include")]
@@ -66,7 +66,7 @@ def _headers():
 
 
 def lib_path(code="em2d"):
-    return os.path.join(LIBDIR, "libzpic_b200_%s.so" % code)
+    return os.path.join(LIBDIR, "libzpic_b200_%s%s.so" % (code, os.environ.get("ZPIC_LIB_SUFFIX", "")))
 
 
 def build(code="em2d", force=False, verbose=False):

@@ -99,6 +99,9 @@ struct zdev_spec2d {
 
 static const int PUSH_THREADS = 256;
 static const int PUSH_WARPS = PUSH_THREADS / 32;
+#ifndef PUSH_MIN_BLOCKS
+#define PUSH_MIN_BLOCKS 2           // CTAs per SM the register allocation is sized for
+#endif
 static const int XQ_CAP = 64;        // warp-private queue of cell-crossing particles
 
 static void soa_alloc(soa2d& a, int64_t n, int with_tag, int is_mig) {
@@ -502,7 +505,7 @@ __device__ __forceinline__ void drain_crossers(const xq_entry* q, int n, int lan
 
 // One CTA per tile.  Dynamic shared memory: perm[max_cap] ints.
 template <int TX, int TY>
-__global__ void __launch_bounds__(PUSH_THREADS)
+__global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, soa2d mig, unsigned int mig_cap,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
@@ -572,9 +575,10 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	// software pipeline: the record of the next iteration is requested before the current one
 	// is processed, so its HBM/L2 latency hides behind ~600 instructions of arithmetic
 	rec24 nv; int ntag = 0;
+	const int first = (nlive > 0) ? s_perm[0] : 0;
 	{
 		const int pn = warp * 32 + lane;
-		const int64_t k = base + ((pn < nlive) ? s_perm[pn] : 0);
+		const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
 		nv = rec_load(A.rec + k);
 		if (A.tag) ntag = A.tag[k];
 	}
@@ -586,17 +590,15 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		const int tag = ntag;
 		{
 			const int pn = p + PUSH_THREADS;
-			const int64_t k = base + ((pn < nlive) ? s_perm[pn] : 0);
+			const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
 			nv = rec_load(A.rec + k);
 			if (A.tag) ntag = A.tag[k];
 		}
 
-		// Lanes past the end of the tile (last iteration only) run the arithmetic on whatever
-		// record slot 0 holds - a valid particle of this tile or stale finite data clamped to a
-		// valid cell - and are masked out of every side effect below.
+		// Lanes past the end of the tile (last iteration only) run the arithmetic on a copy of
+		// the tile's first particle and are masked out of every side effect below.
 		float w[8];
-		int lx = v.cell & 0xffff, ly = (v.cell >> 16) & 0xffff;
-		if (!active) { lx = 0; ly = 0; }
+		const int lx = v.cell & 0xffff, ly = v.cell >> 16;
 		const int key = active ? lx + ly * TX : 0x7fffffff;
 		float x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
 		int fate, ncell = -1, gix = 0, giy = 0;
