@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py - particle-pushes/s of the em2d time step on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA implementation
+    python bench.py --impl reference --gpus N --steps K ...  # the reference C code on the host cores
+
+A "step" is one full sim_iter of the reference API (em2d/simulation.c:45-56): current_zero,
+spec_advance for every species (interpolate + Boris push + current deposit + boundaries +
+re-binning), current_update, emf_advance.  `value` = particle pushes per second of the whole
+job, counted like the reference counts them (np per species per step, em2d/particles.c:1267),
+with the state resident in HBM.  Workload at N=1: configs[1] of BASELINE.json - the Weibel deck
+scaled to 4096 x 4096 cells, 2 species x 64 particles per cell (2^31 particles), periodic,
+re-binned every step; per-GPU work is kept fixed for N>1 (weak scaling: the box grows along x).
+
+Extra keys (see the task contract): `roofline` for the dominant kernel (k_push2d) from CUDA
+events recorded around its launches on the library stream; `cpu_baseline` = the unmodified
+reference (oracle/_ref, -Ofast as shipped) timed on one host core over a bounded sample;
+`e2e` = the same metric through the public C API (sim_new / sim_iter) with HOST buffers, i.e.
+host->device upload of particles+fields and device->host download inside every timed step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+METRIC = "particle-pushes/sec (push+deposit)"
+UNIT = "pushes/s"
+BYTES_PER_PUSH = 56.0          # algorithmic: 28 B read + 28 B write per particle
+CELL = 0.1                     # dx of the shipped Weibel deck (em2d/input/weibel.c:17-18)
+DT = 0.07
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu = gpu
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([t.strip() for t in line.split(",")])
+                if self.stop_flag:
+                    break
+        except OSError:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # samples under load only: the upper half (idle samples before/after the region are low)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# decks through the C API (the same calls for our library and for the reference build)
+
+def build_weibel(lib, A, nx, ny, ppc, seed=(12345, 67890)):
+    """reference em2d/input/weibel.c:13-40 with adjustable size / ppc"""
+    libc = C.CDLL(None)
+    libc.calloc.restype = C.c_void_p
+    libc.calloc.argtypes = [C.c_size_t, C.c_size_t]
+    lib.set_rand_seed(*seed)
+    cnx = (C.c_int * 2)(nx, ny)
+    box = (C.c_float * 2)(nx * CELL, ny * CELL)
+    species = C.cast(libc.calloc(2, C.sizeof(A.Species)), C.POINTER(A.Species))
+    cppc = (C.c_int * 2)(*ppc)
+    uth = (C.c_float * 3)(0.1, 0.1, 0.1)
+    for k, (name, m_q, uz) in enumerate(((b"electrons", -1.0, 0.6), (b"positrons", 1.0, -0.6))):
+        ufl = (C.c_float * 3)(0.0, 0.0, uz)
+        lib.spec_new(C.byref(species[k]), name, m_q, cppc, ufl, uth, cnx, box, DT, None)
+    sim = A.Simulation()
+    lib.sim_new(C.byref(sim), cnx, box, DT, 35.0, 10, species, 2)
+    return sim, species, (cnx, box)
+
+
+def fit_grid(lib, n, ppc_total):
+    """shrink the square grid until two species fit in free device memory (keeps ppc)"""
+    free_b, total_b = C.c_size_t(), C.c_size_t()
+    lib.zdev_mem_info(C.byref(free_b), C.byref(total_b))
+    while n > 256:
+        need = 2 * (n * n * ppc_total) * (2 * 26 * 1.25 + 28 / 8.0) + 5 * (n + 3) ** 2 * 12
+        if need < 0.92 * free_b.value:
+            break
+        n //= 2
+    return n, free_b.value
+
+
+def run_ours(args):
+    from zpic_b200 import abi_em2d as A
+    from zpic_b200 import load
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+    lib = load("em2d")
+    if lib.zdev_init(local) != 0:
+        raise SystemExit("bench.py: no CUDA device - the CUDA path is the only path")
+    K, W = args.steps, max(args.warmup, 0)
+    ppc = (args.ppc, args.ppc)
+    n, free_b = fit_grid(lib, args.n, args.ppc * args.ppc)
+
+    # ---- leg 1: state resident in HBM (device-side initialisation), fully asynchronous stepping
+    os.environ.setdefault("ZPIC_TILE_SLACK", "1.25")
+    lib.zpic_b200_set_option(b"device_init", 1)
+    lib.zpic_b200_set_option(b"lazy", 1)
+    lib.zpic_b200_set_option(b"coherent", 0)
+    lib.zdev_set_push_timing(1)
+    sim, species, _ = build_weibel(lib, A, n, n, ppc)
+    np_total = 2 * n * n * args.ppc * args.ppc
+
+    def barrier():
+        lib.zdev_sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    for _ in range(max(W, 1)):
+        lib.sim_iter(C.byref(sim))
+    barrier()
+    # reset per-kernel timers after warm-up
+    from zpic_b200._lib import spec_handle
+    handles = [spec_handle(lib, C.byref(species[k])) for k in range(2)]
+    for h in handles:
+        lib.zdev_spec2d_push_timing(h, None, None, 1)
+    launches0 = lib.zdev_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
+    barrier()
+    lib.zdev_event_record(e0)
+    for _ in range(K):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_event_record(e1)
+    ms = lib.zdev_event_elapsed_ms(e0, e1)
+    barrier()
+    clocks = sampler.finish() if rank == 0 else None
+    launches = lib.zdev_launch_count() - launches0
+    push_ms, push_n = 0.0, 0
+    for h in handles:
+        t, c = C.c_double(), C.c_int64()
+        lib.zdev_spec2d_push_timing(h, C.byref(t), C.byref(c), 1)
+        push_ms += t.value
+        push_n += c.value
+    lib.zdev_set_push_timing(0)
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    # sanity: the population did not leak (periodic box)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    en, cnt = C.c_double(), C.c_int64()
+    lib.zdev_spec2d_fetch(handles[0], C.byref(en), C.byref(cnt))
+    assert cnt.value == n * n * args.ppc * args.ppc, "particles were lost: %d" % cnt.value
+    value = world * np_total * K / (ms * 1e-3)
+    lib.sim_delete(C.byref(sim))
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        per_launch = np_total / 2.0                       # particles per k_push2d launch (one species)
+        avg_ms = push_ms / max(push_n, 1)
+        achieved = BYTES_PER_PUSH * per_launch / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "push_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_per_particle", 0) * per_launch or None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "em2d Weibel %dx%d cells, 2 species x %d ppc, periodic (BASELINE configs[1]%s)"
+                                   % (n, n, args.ppc * args.ppc, "" if n == 4096 else ", grid reduced to fit memory"),
+                       "particles_per_gpu": np_total, "dt": DT, "dx": CELL,
+                       "init": "device-side counter-based thermal+fluid distribution (seeded from the host stream)",
+                       "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (np_total * 52 / 1e9),
+                       "decomposition": "independent periodic replica per GPU" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "kernel": "k_push2d", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle": BYTES_PER_PUSH, "particles_per_launch": per_launch,
+                         "avg_launch_ms": avg_ms, "launches_timed": push_n,
+                         "kernel_share_of_step": push_ms / ms},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        # ---- leg 2: end to end through the public API with HOST buffers
+        out["e2e"] = run_e2e(lib, A, args, n)
+        # ---- leg 3: the reference on one host core, bounded sample
+        out["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds, threads=1)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def run_e2e(lib, A, args, n_full):
+    """sim_iter with host buffers: 'coherent' mode uploads every particle / field buffer from the
+    host mirrors before the step and downloads them after it (what a caller that inspects or edits
+    raw buffers between all iterations gets).  Host-side initialisation with the reference random
+    stream; bounded to a grid whose host injection takes seconds."""
+    n = min(n_full, args.e2e_n)
+    ppc = (args.ppc, args.ppc)
+    lib.zpic_b200_set_option(b"device_init", 0)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    lib.zpic_b200_set_option(b"coherent", 1)
+    sim, species, _ = build_weibel(lib, A, n, n, ppc)
+    np_total = 2 * n * n * args.ppc * args.ppc
+    lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    dt = time.perf_counter() - t0
+    grid_b = (n + 3) * (n + 3) * 12
+    h2d = np_total * 28 + 2 * grid_b
+    d2h = np_total * 28 + 3 * grid_b
+    lib.zpic_b200_set_option(b"coherent", 0)
+    # the same public API with the state left on the device (default mode): host scalars in,
+    # energies / particle counts out every step
+    lib.zpic_b200_set_option(b"coherent", 0)
+    lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    dt_res = time.perf_counter() - t0
+    lib.sim_delete(C.byref(sim))
+    return {"value": np_total * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "mode": "coherent: every sim_iter uploads all particles + E,B from the host mirrors and downloads "
+                    "particles + E,B,J back (pageable host memory)",
+            "workload": "em2d Weibel %dx%d, 2 x %d ppc, host-initialised with the reference random stream" % (n, n, args.ppc ** 2),
+            "steps": steps,
+            "api_resident": {"value": np_total * steps / dt_res, "unit": UNIT,
+                             "note": "same API calls, state left in HBM between sim_iter calls; per step only the "
+                                     "push scalars go in and energy + particle count (24 B per species) come out"}}
+
+
+# ------------------------------------------------------------------------------------------
+# the reference on the host
+
+def ref_run(n, ppc, steps, fast=True):
+    """one process, one core: the unmodified reference on a Weibel box of n x n cells"""
+    from zpic_b200 import abi_em2d as A
+    path = os.path.join(REPO, "oracle", "_ref", "libzpic_ref_em2d%s.so" % ("_fast" if fast else ""))
+    if not os.path.exists(path):
+        return None
+    lib = A.declare(C.CDLL(path))
+    sim, species, _ = build_weibel(lib, A, n, n, (ppc, ppc))
+    lib.sim_iter(C.byref(sim))          # warm caches / first-touch
+    p0, t0 = lib.spec_npush(), lib.spec_time()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        lib.sim_iter(C.byref(sim))
+    wall = time.perf_counter() - w0
+    pushes = lib.spec_npush() - p0
+    return {"pushes": int(pushes), "wall_s": wall, "spec_time_s": lib.spec_time() - t0}
+
+
+def cpu_baseline(seconds=15.0, threads=1):
+    """bounded sample of the same workload on `threads` host cores (independent replicas: the
+    reference has no threads, em2d/Makefile:1-4)"""
+    n, ppc = 256, 8                                   # 2 x 4.2 M particles, ~1 s per step per core
+    per_step = 2 * n * n * ppc * ppc
+    steps = max(2, int(seconds * 8.5e6 / per_step))
+    code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+            "print(json.dumps(bench.ref_run(%d, %d, %d)))" % (REPO, n, ppc, steps))
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, text=True) for _ in range(threads)]
+    results = []
+    for p in procs:
+        out = p.communicate()[0].strip().splitlines()
+        results.append(json.loads(out[-1]) if out else None)
+    if not results or any(r is None for r in results):
+        return {"value": None, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": "oracle/_ref not built on this box"}
+    wall = max(r["wall_s"] for r in results)
+    pushes = sum(r["pushes"] for r in results)
+    return {"value": pushes / wall, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "unmodified reference (-Ofast, as shipped) em2d Weibel %dx%d, 2 x %d ppc, %d steps%s; "
+                      "whole sim_iter wall time" % (n, n, ppc * ppc, steps,
+                                                    " x %d independent replicas" % threads if threads > 1 else ""),
+            "reference_spec_advance_only": sum(r["pushes"] for r in results) / max(r["spec_time_s"] for r in results)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    K = args.steps
+    # each "step" = a bounded sample: every core advances its own 256^2 x 2 x 64 ppc replica once
+    n, ppc = 256, 8
+    steps_run = K + max(args.warmup - 1, 0)
+    code = ("import sys, json; sys.path.insert(0, %r); import bench; "
+            "print(json.dumps(bench.ref_run(%d, %d, %d)))" % (REPO, n, ppc, steps_run))
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, text=True) for _ in range(threads)]
+    results = []
+    for p in procs:
+        o = p.communicate()[0].strip().splitlines()
+        results.append(json.loads(o[-1]) if o else None)
+    if any(r is None for r in results):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libzpic_ref_em2d_fast.so not present"}))
+        return
+    wall = max(r["wall_s"] for r in results)
+    pushes = sum(r["pushes"] for r in results)
+    value = pushes / wall
+    sample = ("unmodified reference (-Ofast) em2d Weibel %dx%d, 2 x %d ppc per replica, %d independent replicas "
+              "(one per host core; the reference is single threaded)" % (n, n, ppc * ppc, threads))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": args.warmup, "ms_per_step": wall / steps_run * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "em2d Weibel, 2 species x 64 ppc, periodic (BASELINE configs[1] physics)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096, help="grid cells per side per GPU")
+    ap.add_argument("--ppc", type=int, default=8, help="particles per cell per direction (8 -> 64 ppc)")
+    ap.add_argument("--e2e-n", type=int, default=1024, dest="e2e_n")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

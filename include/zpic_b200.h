@@ -33,6 +33,10 @@ void zpic_b200_touch_emf( struct EMF* emf );
  * every step).  Also settable through ZPIC_LAZY / ZPIC_TRACK_IDS / ZPIC_COHERENT. */
 void zpic_b200_set_option( const char* name, int value );
 
+/* opaque device handles (zdev_spec2d* / zdev_grid2d* of include/zpic_dev.h) behind a host object */
+void* zpic_b200_species_handle( struct Species* spec );
+void* zpic_b200_grid_handle( struct EMF* emf );
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,6 +159,12 @@ void zdev_spec2d_fetch( zdev_spec2d* s, double* energy_sum, int64_t* np );
 /* spec_deposit_charge on the device (em2d/particles.c:1289-1324): charge is a host
  * (nx+1)*(ny+1) float array that is ADDED to, like the reference does */
 void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, float* charge );
+/* Device timing of the push kernel alone (k_push2d, not the migration pass): when enabled
+ * every launch is bracketed by CUDA events on the library stream; the accumulated time and
+ * launch count are read back (and optionally reset) per species.  Used by bench.py for
+ * the roofline figure. */
+void zdev_set_push_timing( int on );
+void zdev_spec2d_push_timing( zdev_spec2d* s, double* total_ms, int64_t* launches, int reset );
 /* tile geometry chosen for this species (cells per tile in x,y; number of tiles) */
 void zdev_spec2d_tile_info( zdev_spec2d* s, int* tx, int* ty, int* ntiles, int64_t* capacity );
 

@@ -84,6 +84,20 @@ def _declare_dev(lib):
         if hasattr(lib, name):
             getattr(lib, name).restype = None
             getattr(lib, name).argtypes = [vp]
+    for name in ("zpic_b200_species_handle", "zpic_b200_grid_handle"):
+        if hasattr(lib, name):
+            getattr(lib, name).restype = vp
+            getattr(lib, name).argtypes = [vp]
+    for name, (res, args) in {"zdev_set_push_timing": (None, [i]),
+                              "zdev_spec2d_push_timing": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i])}.items():
+        if hasattr(lib, name):
+            getattr(lib, name).restype = res
+            getattr(lib, name).argtypes = args
     if hasattr(lib, "zpic_b200_set_option"):
         lib.zpic_b200_set_option.restype = None
         lib.zpic_b200_set_option.argtypes = [C.c_char_p, i]
+
+
+def spec_handle(lib, spec_ptr):
+    """zdev_spec2d* behind a t_species (uploads / creates the device copy if needed)"""
+    return lib.zpic_b200_species_handle(spec_ptr)

@@ -95,7 +95,34 @@ struct zdev_spec2d {
 	int64_t np_host;                 // last known particle count
 	int ids_valid;                   // tags are a permutation of [0,np)
 	std::vector<int64_t>* h_off;     // host copy of tile_off
+	// optional device timing of the push kernel alone (bench roofline): ring of event pairs
+	std::vector<cudaEvent_t>* ev;    // 2*EV_RING events, created on first use
+	int ev_next, ev_pending;
+	double push_ms; int64_t push_launches, push_particles;
 };
+static const int EV_RING = 64;
+static int g_time_push = 0;
+
+extern "C" void zdev_set_push_timing(int on) { g_time_push = on; }
+
+static void spec_collect_timing(zdev_spec2d* s) {
+	if (!s->ev) return;
+	for (int k = 0; k < s->ev_pending; k++) {
+		int slot = (s->ev_next - s->ev_pending + k + EV_RING) % EV_RING;
+		float ms = 0;
+		ZDEV_CHECK(cudaEventSynchronize((*s->ev)[2 * slot + 1]));
+		ZDEV_CHECK(cudaEventElapsedTime(&ms, (*s->ev)[2 * slot], (*s->ev)[2 * slot + 1]));
+		s->push_ms += ms; s->push_launches++;
+	}
+	s->ev_pending = 0;
+}
+
+extern "C" void zdev_spec2d_push_timing(zdev_spec2d* s, double* total_ms, int64_t* launches, int reset) {
+	spec_collect_timing(s);
+	if (total_ms) *total_ms = s->push_ms;
+	if (launches) *launches = s->push_launches;
+	if (reset) { s->push_ms = 0; s->push_launches = 0; }
+}
 
 static const int PUSH_THREADS = 256;
 static const int PUSH_WARPS = PUSH_THREADS / 32;
@@ -130,9 +157,10 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 	s->nx = nx; s->ny = ny;
 	s->ppc_hint = ppc_hint > 0 ? ppc_hint : 1;
 	s->track_ids = track_ids;
-	// tile shape: aim at ~4096 particles per tile (amortises the field staging, keeps the
-	// per-step migration to a few percent, bounds the shared-memory index buffer)
-	int cells = 4096 / s->ppc_hint;
+	// tile shape: aim at ~8192 particles per tile (measured best on B200: amortises the field
+	// staging and the per-tile index sort, keeps the per-step migration to a few percent and
+	// the shared-memory index buffer small enough for two CTAs per SM)
+	int cells = 8192 / s->ppc_hint;
 	int tx = 16, ty = 16;
 	if (cells < 256) { tx = 16; ty = 8; }
 	if (cells < 128) { tx = 8; ty = 8; }
@@ -170,6 +198,7 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl);
+	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
 }
@@ -273,7 +302,15 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 		cudaFree(d_cnt);
 	}
-	spec_layout(s, cnt, np);
+	// keep the existing tile layout when the new population fits (repeated uploads in
+	// "coherent" mode would otherwise reallocate every step)
+	bool fits = s->cap_total > 0;
+	if (fits) {
+		const std::vector<int64_t>& off = *s->h_off;
+		for (int t = 0; t < s->ntiles && fits; t++) fits = cnt[t] <= off[t + 1] - off[t];
+	}
+	if (fits) ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+	else spec_layout(s, cnt, np);
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	spec_append_dev(s, d_aos, np, 0);
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -790,8 +827,19 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured = smem;
 	}
+	int slot = -1;
+	if (g_time_push) {
+		if (!s->ev) {
+			s->ev = new std::vector<cudaEvent_t>(2 * EV_RING);
+			for (auto& e : *s->ev) ZDEV_CHECK(cudaEventCreate(&e));
+		}
+		if (s->ev_pending == EV_RING) spec_collect_timing(s);
+		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
+		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
+	}
 	ZDEV_LAUNCH((k_push2d<TX, TY>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
 	            s->mig, s->mig_cap, s->ctl, E, B, J, g, prm);
+	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
 
 extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid2d* gcur, const zdev_push2d_params* prm) {

@@ -267,7 +267,18 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
 
 	spec->np = 0;
 	const int range[][2] = { {0, nx[0]-1}, {0, nx[1]-1} };
-	spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
+	if (zb_opt_device_init() && spec->density.type == UNIFORM) {
+		/* opt-in for populations too large for a host mirror: same distribution, generated by a
+		   counter-based generator on the device at the first step (one draw of the host stream
+		   seeds it, so runs stay reproducible and species differ) */
+		zb_spec* e = zb_spec_of(spec, 1);
+		e->device_init = 1;
+		e->device_seed = ((uint64_t) rand_uint32() << 32) | rand_uint32();
+		long long total = (long long) nx[0] * nx[1] * npc;
+		spec->np = (total > 0x7fffffffLL) ? 0x7fffffff : (int) total;
+	} else {
+		spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
+	}
 
 	spec->n_sort = 16;    /* kept for API compatibility; device tiles are re-binned every step */
 }
@@ -321,7 +332,7 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 	prm.shift_window = spec->moving_window &&
 		( ((spec->iter + 1) * spec->dt) > (spec->dx[0] * (spec->n_move + 1)) );
 
-	zdev_spec2d_advance(s->d, zb_dev(gf), zb_dev(gc), &prm);
+	zdev_spec2d_advance(zb_spec_dev(s), zb_dev(gf), zb_dev(gc), &prm);
 	s->host_stale = 1;
 	gc->j_host_stale = 1;
 	spec->iter += 1;
@@ -334,19 +345,17 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
 		t_part* col = NULL; int ncol = 0, ncol_max = 0;
 		spec_inject_into(spec, range, &col, &ncol, &ncol_max);
-		zdev_spec2d_append(s->d, col, ncol);
+		zdev_spec2d_append(zb_spec_dev(s), col, ncol);
 		free(col);
 		n_injected = ncol;
 	}
 
 	if (!zb_opt_lazy()) {
 		double esum; int64_t np;
-		zdev_spec2d_fetch(s->d, &esum, &np);
+		zdev_spec2d_fetch(zb_spec_dev(s), &esum, &np);
 		spec->energy = spec->q * spec->m_q * esum * spec->dx[0] * spec->dx[1];
 		spec->np = (int) (np + n_injected);
 		s->np_seen = spec->np;
-		spec_grow_buffer(spec, spec->np);
-		s->part_seen = spec->part;
 		push_count += spec->np;
 	} else {
 		push_count += spec->np;      /* population estimate; exact after the next sync */
@@ -360,7 +369,7 @@ void spec_deposit_charge( const t_species* spec, float* charge )
 {
 	zb_spec_to_device((t_species*) spec);
 	zb_spec* s = zb_spec_of(spec, 1);
-	zdev_spec2d_deposit_charge(s->d, spec->q, spec->moving_window, charge);
+	zdev_spec2d_deposit_charge(zb_spec_dev(s), spec->q, spec->moving_window, charge);
 }
 
 /* ------------------------------------------------------------------ reports (host, ZDF) */

@@ -11,16 +11,18 @@ static int n_grids = 0;
 static zb_spec specs[ZB_MAX];
 static int n_specs = 0;
 
-static int opt_lazy = -1, opt_ids = -1, opt_coherent = -1;
+static int opt_lazy = -1, opt_ids = -1, opt_coherent = -1, opt_devinit = -1;
 static int env_flag( const char* name ) { const char* e = getenv(name); return e && atoi(e) != 0; }
 int zb_opt_lazy( void ) { if (opt_lazy < 0) opt_lazy = env_flag("ZPIC_LAZY"); return opt_lazy; }
 int zb_opt_track_ids( void ) { if (opt_ids < 0) opt_ids = env_flag("ZPIC_TRACK_IDS"); return opt_ids; }
 int zb_opt_coherent( void ) { if (opt_coherent < 0) opt_coherent = env_flag("ZPIC_COHERENT"); return opt_coherent; }
+int zb_opt_device_init( void ) { if (opt_devinit < 0) opt_devinit = env_flag("ZPIC_DEVICE_INIT"); return opt_devinit; }
 
 void zpic_b200_set_option( const char* name, int value ) {
 	if (!strcmp(name, "lazy")) opt_lazy = value;
 	else if (!strcmp(name, "track_ids")) opt_ids = value;
 	else if (!strcmp(name, "coherent")) opt_coherent = value;
+	else if (!strcmp(name, "device_init")) opt_devinit = value;
 	else fprintf(stderr, "(*warning*) zpic_b200_set_option: unknown option %s\n", name);
 }
 
@@ -86,15 +88,22 @@ zb_spec* zb_spec_of( const t_species* spec, int create ) {
 	zb_spec* e = &specs[n_specs++];
 	memset(e, 0, sizeof(*e));
 	e->spec = spec;
-	e->d = zdev_spec2d_create(spec->nx[0], spec->nx[1], spec->ppc[0] * spec->ppc[1], zb_opt_track_ids());
 	e->dev_stale = 1;
 	return e;
+}
+
+zdev_spec2d* zb_spec_dev( zb_spec* e ) {
+	if (!e->d) {
+		const t_species* spec = e->spec;
+		e->d = zdev_spec2d_create(spec->nx[0], spec->nx[1], spec->ppc[0] * spec->ppc[1], zb_opt_track_ids());
+	}
+	return e->d;
 }
 
 void zb_spec_drop( const t_species* spec ) {
 	zb_spec* e = zb_spec_of(spec, 0);
 	if (!e) return;
-	zdev_spec2d_destroy(e->d);
+	if (e->d) zdev_spec2d_destroy(e->d);
 	*e = specs[--n_specs];
 }
 
@@ -136,11 +145,17 @@ void zb_cur_to_host( const t_current* cur ) {
 
 void zb_spec_to_device( t_species* spec ) {
 	zb_spec* e = zb_spec_of(spec, 1);
+	if (e->device_init) {
+		/* throughput configurations: the population never existed on the host */
+		zdev_spec2d_inject_uniform(zb_spec_dev(e), spec->ppc[0], spec->ppc[1], spec->ufl, spec->uth, e->device_seed);
+		e->device_init = 0; e->dev_stale = 0; e->host_stale = 1;
+		return;
+	}
 	/* host code that appended particles or reallocated the buffer did so on a current
 	   mirror (the Python layer syncs first); take the host copy as the truth then */
 	if (!e->host_stale && (e->part_seen != spec->part || e->np_seen != spec->np)) e->dev_stale = 1;
 	if (e->dev_stale) {
-		zdev_spec2d_upload(e->d, spec->part, spec->np);
+		zdev_spec2d_upload(zb_spec_dev(e), spec->part, spec->np);
 		e->dev_stale = 0; e->host_stale = 0;
 		e->part_seen = spec->part; e->np_seen = spec->np;
 	}
@@ -150,9 +165,9 @@ void zb_spec_to_host( const t_species* cspec ) {
 	t_species* spec = (t_species*) cspec;    /* the mirror is a cache of device state */
 	zb_spec* e = zb_spec_of(spec, 0);
 	if (!e || !e->host_stale) return;
-	int64_t np = zdev_spec2d_np(e->d);
+	int64_t np = zdev_spec2d_np(zb_spec_dev(e));
 	spec_grow_buffer(spec, (int) np);
-	spec->np = (int) zdev_spec2d_download(e->d, spec->part, spec->np_max);
+	spec->np = (int) zdev_spec2d_download(zb_spec_dev(e), spec->part, spec->np_max);
 	e->host_stale = 0;
 	e->part_seen = spec->part; e->np_seen = spec->np;
 }
@@ -185,3 +200,11 @@ void zpic_b200_touch_species( t_species* spec ) {
 void zpic_b200_sync_species( t_species* spec ) { zb_spec_to_host(spec); }
 void zpic_b200_sync_emf( t_emf* emf ) { zb_emf_to_host(emf); }
 void zpic_b200_sync_current( t_current* cur ) { zb_cur_to_host(cur); }
+
+/* device handles of the twins (zpic_dev.h objects), for tools that drive or time the
+   device seam directly (bench.py) */
+void* zpic_b200_species_handle( t_species* spec ) {
+	zb_spec_to_device(spec);
+	return zb_spec_dev(zb_spec_of(spec, 1));
+}
+void* zpic_b200_grid_handle( t_emf* emf ) { return zb_dev(zb_grid_of_emf(emf, 1)); }

@@ -26,7 +26,9 @@ typedef struct zb_grid {
 
 typedef struct zb_spec {
 	const t_species* spec;
-	zdev_spec2d* d;
+	zdev_spec2d* d;            /* NULL until first device use: see zb_spec_dev() */
+	int device_init;           /* population is generated on the device at first use (no host mirror yet) */
+	uint64_t device_seed;
 	int dev_stale;             /* host part[] newer than the device copy (or never uploaded) */
 	int host_stale;            /* device newer than host part[] */
 	const t_part* part_seen;   /* host buffer address / count at the last transfer: a change */
@@ -43,6 +45,7 @@ void zb_grid_drop_emf( const t_emf* emf );
 void zb_grid_drop_cur( const t_current* cur );
 
 zb_spec* zb_spec_of( const t_species* spec, int create );
+zdev_spec2d* zb_spec_dev( zb_spec* e );
 void zb_spec_drop( const t_species* spec );
 
 /* bring one side up to date */
@@ -56,6 +59,7 @@ void zb_spec_to_host( const t_species* spec );
 int zb_opt_lazy( void );        /* 1: do not fetch energy / np after every spec_advance */
 int zb_opt_track_ids( void );   /* 1: keep injection order recoverable in the host mirror */
 int zb_opt_coherent( void );    /* 1: host mirrors are refreshed before and after every sim_iter */
+int zb_opt_device_init( void ); /* 1: uniform species are initialised on the device (not the reference random stream) */
 
 void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max );
 
