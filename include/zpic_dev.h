@@ -50,6 +50,8 @@ float zdev_event_elapsed_ms( void* start, void* stop );   /* synchronises on sto
 void  zdev_event_destroy( void* ev );
 /* free / total device memory in bytes */
 void zdev_mem_info( size_t* free_b, size_t* total_b );
+/* enqueue all further work on a caller-owned cudaStream_t (NULL: back to the library stream) */
+void zdev_set_stream( void* stream );
 /* write `bytes` of scratch (>= L2 size) to evict the L2 between timed steps */
 void zdev_flush_l2( void );
 
@@ -105,6 +107,21 @@ void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c
 void zdev_yee_e( zdev_grid2d* g, zdev_grid2d* g_cur, float dt_dx, float dt_dy, float dt );  /* emf.c:531-562 */
 void zdev_emf_update_gc( zdev_grid2d* g, int moving_window );           /* emf.c:573-637 */
 void zdev_emf_move_window( zdev_grid2d* g );                            /* emf.c:659-670 */
+/* ---- pieces for the slab decomposition (halo exchange between the steps) ----
+ * pack / unpack: cell columns [i0, i0+ncols) x rows [j0, j0+nrows) of one grid <-> a dense device
+ * buffer of float3 [row][col]; add != 0 accumulates (the J guard fold across slabs,
+ * em2d/current.c:128-131), else overwrites (guard refresh, em2d/emf.c:583-607). */
+void zdev_grid2d_pack_cols( zdev_grid2d* g, int which, int i0, int ncols, int j0, int nrows, float* dev_out );
+void zdev_grid2d_unpack_cols( zdev_grid2d* g, int which, int i0, int ncols, int j0, int nrows, const float* dev_in, int add );
+/* y half of current_update_gc (em2d/current.c:142-157) */
+void zdev_current_fold_y( zdev_grid2d* g );
+/* pass list of current_smooth (em2d/current.c:427-459) and one [sa,sb,sa] pass; keep_x_guards = the
+ * moving-window rule (x guards not refreshed, current.c:346) - slabs refresh them by exchange */
+int  zdev_smooth_plan( int xtype, int ytype, int xlevel, int ylevel, int* dirs, float* sa, float* sb );
+void zdev_smooth_pass( zdev_grid2d* g, int dir, float sa, float sb, int keep_x_guards );
+/* emf_move_window's shift; zero_right = 0 for slabs whose right edge is interior (em2d/emf.c:659-670) */
+void zdev_emf_shift( zdev_grid2d* g, int zero_right );
+void zdev_emf_update_part_fld( zdev_grid2d* g );                        /* emf.c:838-914 */
 /* emf_get_energy: 6 interior sums of squares in double, scaled by 0.5*dx*dy by the
  * caller (em2d/emf.c:729-750).  Synchronises. */
 void zdev_emf_energy( zdev_grid2d* g, double sums[6] );
@@ -124,6 +141,8 @@ typedef struct zdev_push2d_params {
 	float q;        /* charge per particle */
 	int   moving_window;  /* 1: absorbing x, periodic y (particles.c:1237-1251) */
 	int   shift_window;   /* 1: all ix-- this step (particles.c:619-632) */
+	int   slab_left;      /* 1: the lower x edge is a slab boundary: leavers are exported, not wrapped/absorbed */
+	int   slab_right;     /* 1: same for the upper x edge */
 } zdev_push2d_params;
 
 /* Device species for an nx x ny grid.  ppc_hint = expected particles per cell
@@ -159,6 +178,14 @@ void zdev_spec2d_fetch( zdev_spec2d* s, double* energy_sum, int64_t* np );
 /* spec_deposit_charge on the device (em2d/particles.c:1289-1324): charge is a host
  * (nx+1)*(ny+1) float array that is ADDED to, like the reference does */
 void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, float* charge );
+/* Slab decomposition along x (one process per GPU).  After zdev_spec2d_advance
+ * with slab_left/right set, the particles that crossed a slab edge sit in two device lists of
+ * 28-byte t_part records whose ix is already expressed in the neighbour's frame (all slabs
+ * have the same width).  The caller moves them (NCCL / peer copy) and hands what it received to
+ * zdev_spec2d_append_device.  export_counts synchronises the stream. */
+void  zdev_spec2d_export_counts( zdev_spec2d* s, int64_t counts[2] );
+void* zdev_spec2d_export_ptr( zdev_spec2d* s, int side );
+void  zdev_spec2d_append_device( zdev_spec2d* s, const void* dev_part_aos, int64_t np );
 /* Device timing of the push kernel alone (k_push2d, not the migration pass): when enabled
  * every launch is bracketed by CUDA events on the library stream; the accumulated time and
  * launch count are read back (and optionally reset) per species.  Used by bench.py for

@@ -178,6 +178,25 @@ static void compensator(int n, float* sa, float* sb)
 	*sa = a / total; *sb = b / total;
 }
 
+/* single pass / pass list, for the slab-decomposition tests that exchange halos between passes */
+void orc2d_smooth_pass(float* J, int nx, int ny, int dir, float sa, float sb, int keep_x_guards)
+{
+	if (dir == 0) pass_x(J, nx, ny, sa, sb, keep_x_guards); else pass_y(J, nx, ny, sa, sb);
+}
+int orc2d_smooth_plan(int xtype, int ytype, int xlevel, int ylevel, int* dirs, float* sa, float* sb)
+{
+	int n = 0;
+	if (xtype) {
+		for (int k = 0; k < xlevel; k++) { dirs[n] = 0; sa[n] = 0.25f; sb[n] = 0.5f; n++; }
+		if (xtype == 2) { dirs[n] = 0; compensator(xlevel, &sa[n], &sb[n]); n++; }
+	}
+	if (ytype) {
+		for (int k = 0; k < xlevel; k++) { dirs[n] = 1; sa[n] = 0.25f; sb[n] = 0.5f; n++; }
+		if (ytype == 2) { dirs[n] = 1; compensator(ylevel, &sa[n], &sb[n]); n++; }
+	}
+	return n;
+}
+
 /* types: 0 none, 1 binomial, 2 compensated.  NB the y passes are counted with xlevel, as the
  * reference does (em2d/current.c:449) */
 void orc2d_current_smooth(float* J, int nx, int ny, int moving_window, int xtype, int ytype, int xlevel, int ylevel)

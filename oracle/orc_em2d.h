@@ -33,6 +33,8 @@ void orc2d_emf_advance(float* E, float* B, const float* J, int nx, int ny, float
                        int moving_window, int shift);
 void orc2d_emf_energy(const float* E, const float* B, int nx, int ny, double out[6]);
 void orc2d_current_gc(float* J, int nx, int ny, int moving_window);
+void orc2d_smooth_pass(float* J, int nx, int ny, int dir, float sa, float sb, int keep_x_guards);
+int orc2d_smooth_plan(int xtype, int ytype, int xlevel, int ylevel, int* dirs, float* sa, float* sb);
 void orc2d_current_smooth(float* J, int nx, int ny, int moving_window, int xtype, int ytype, int xlevel, int ylevel);
 double orc2d_spec_push(orc_part* part, int np, const float* E, const float* B, float* J, int nx, int ny,
                        const float prm[6]);

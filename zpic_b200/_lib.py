@@ -33,7 +33,8 @@ def load(code="em2d"):
 class PushParams2D(C.Structure):   # zdev_push2d_params (include/zpic_dev.h)
     _fields_ = [("tem", C.c_float), ("dt_dx", C.c_float), ("dt_dy", C.c_float),
                 ("qnx", C.c_float), ("qny", C.c_float), ("q", C.c_float),
-                ("moving_window", C.c_int), ("shift_window", C.c_int)]
+                ("moving_window", C.c_int), ("shift_window", C.c_int),
+                ("slab_left", C.c_int), ("slab_right", C.c_int)]
 
 
 def _declare_dev(lib):
@@ -71,6 +72,17 @@ def _declare_dev(lib):
         "zdev_spec2d_fetch": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "zdev_spec2d_deposit_charge": (None, [vp, f, i, fp]),
         "zdev_spec2d_tile_info": (None, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(C.c_int64)]),
+        "zdev_spec2d_export_counts": (None, [vp, C.POINTER(C.c_int64)]),
+        "zdev_spec2d_export_ptr": (vp, [vp, i]),
+        "zdev_spec2d_append_device": (None, [vp, vp, C.c_int64]),
+        "zdev_grid2d_pack_cols": (None, [vp, i, i, i, i, i, vp]),
+        "zdev_grid2d_unpack_cols": (None, [vp, i, i, i, i, i, vp, i]),
+        "zdev_current_fold_y": (None, [vp]),
+        "zdev_smooth_plan": (i, [i, i, i, i, C.POINTER(i), fp, fp]),
+        "zdev_smooth_pass": (None, [vp, i, f, f, i]),
+        "zdev_emf_shift": (None, [vp, i]),
+        "zdev_emf_update_part_fld": (None, [vp]),
+        "zdev_set_stream": (None, [vp]),
     }
     for table in (sig, sig2d):
         for name, (res, args) in table.items():

@@ -262,6 +262,52 @@ extern "C" void zdev_current_smooth(zdev_grid2d* g, int moving_window, int xtype
 	}
 }
 
+// the pass list of current_smooth (reference em2d/current.c:427-459) for callers that have to put a
+// halo exchange between passes: dirs[k] = 0 (x) / 1 (y), coefficients [sa, sb, sa]; returns the count
+extern "C" int zdev_smooth_plan(int xtype, int ytype, int xlevel, int ylevel, int* dirs, float* sa, float* sb) {
+	int n = 0;
+	if (xtype != 0) {
+		for (int i = 0; i < xlevel; i++) { dirs[n] = 0; sa[n] = 0.25f; sb[n] = 0.5f; n++; }
+		if (xtype == 2) { dirs[n] = 0; smooth_comp(xlevel, &sa[n], &sb[n]); n++; }
+	}
+	if (ytype != 0) {
+		for (int i = 0; i < xlevel; i++) { dirs[n] = 1; sa[n] = 0.25f; sb[n] = 0.5f; n++; }
+		if (ytype == 2) { dirs[n] = 1; smooth_comp(ylevel, &sa[n], &sb[n]); n++; }
+	}
+	return n;
+}
+extern "C" void zdev_smooth_pass(zdev_grid2d* g, int dir, float sa, float sb, int keep_x_guards) {
+	smooth_pass(g, dir, sa, sb, keep_x_guards);
+}
+extern "C" void zdev_current_fold_y(zdev_grid2d* g) {
+	need_J(g);
+	ZDEV_LAUNCH(k_fold_y, zdev_div_up(g->nrow, 128), 128, 0, g->J, g->ny, g->nrow);
+}
+
+// columns [i0, i0+ncols) x rows [j0, j0+nrows) of a grid <-> dense device buffer [row][col] of float3
+__global__ void k_pack_cols(const f3* __restrict__ G, int nrow, int i0, int ncols, int j0, int nrows, f3* __restrict__ out) {
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= ncols * nrows) return;
+	int r = k / ncols, c = k - r * ncols;
+	out[k] = G[cidx(i0 + c, j0 + r, nrow)];
+}
+__global__ void k_unpack_cols(f3* __restrict__ G, int nrow, int i0, int ncols, int j0, int nrows, const f3* __restrict__ in, int add) {
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= ncols * nrows) return;
+	int r = k / ncols, c = k - r * ncols;
+	f3 v = in[k];
+	f3* d = &G[cidx(i0 + c, j0 + r, nrow)];
+	if (add) { f3 o = *d; o.x += v.x; o.y += v.y; o.z += v.z; *d = o; } else *d = v;
+}
+extern "C" void zdev_grid2d_pack_cols(zdev_grid2d* g, int which, int i0, int ncols, int j0, int nrows, float* dev_out) {
+	int n = ncols * nrows;
+	ZDEV_LAUNCH(k_pack_cols, zdev_div_up(n, 256), 256, 0, grid_sel(g, which), g->nrow, i0, ncols, j0, nrows, (f3*) dev_out);
+}
+extern "C" void zdev_grid2d_unpack_cols(zdev_grid2d* g, int which, int i0, int ncols, int j0, int nrows, const float* dev_in, int add) {
+	int n = ncols * nrows;
+	ZDEV_LAUNCH(k_unpack_cols, zdev_div_up(n, 256), 256, 0, grid_sel(g, which), g->nrow, i0, ncols, j0, nrows, (const f3*) dev_in, add);
+}
+
 extern "C" void zdev_current_update(zdev_grid2d* g, int moving_window, int xtype, int ytype, int xlevel, int ylevel) {
 	zdev_current_update_gc(g, moving_window);
 	zdev_current_smooth(g, moving_window, xtype, ytype, xlevel, ylevel);
@@ -270,26 +316,31 @@ extern "C" void zdev_current_update(zdev_grid2d* g, int moving_window, int xtype
 // ------------------------------------------------------------------ moving window
 
 // new[i] = old[i+1] for i in [-1,nx-2]; columns nx-1..nx+1 zeroed (reference emf.c:659-670)
-__global__ void k_shift_left(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int nrows, int nrow) {
+// zero_right = 0 (slab whose right edge is not the box edge): columns nx-1, nx come from the halo,
+// column nx+1 keeps its old value until the caller refreshes the halo
+__global__ void k_shift_left(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int nrows, int nrow, int zero_right) {
 	int c = blockIdx.x * blockDim.x + threadIdx.x;   // buffer column
 	int r = blockIdx.y * blockDim.y + threadIdx.y;   // buffer row
 	if (c >= nrow || r >= nrows) return;
 	size_t k = (size_t) r * nrow + c;
 	f3 z = {0.f, 0.f, 0.f};
-	dst[k] = (c < nx) ? src[k + 1] : z;            // buffer column c = cell c-1
+	if (zero_right) dst[k] = (c < nx) ? src[k + 1] : z;            // buffer column c = cell c-1
+	else            dst[k] = (c < nrow - 1) ? src[k + 1] : src[k];
 }
 
-extern "C" void zdev_emf_move_window(zdev_grid2d* g) {
+extern "C" void zdev_emf_shift(zdev_grid2d* g, int zero_right) {
 	need_EB(g); need_tmp(g);
 	dim3 blk(64, 4), grd(zdev_div_up(g->nrow, 64), zdev_div_up(g->nrows, 4));
 	int alias_e = (g->Epart == g->E), alias_b = (g->Bpart == g->B);
-	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->E, g->nx, g->nrows, g->nrow);
+	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->E, g->nx, g->nrows, g->nrow, zero_right);
 	{ f3* t = g->E; g->E = g->tmp; g->tmp = t; }
-	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->B, g->nx, g->nrows, g->nrow);
+	ZDEV_LAUNCH(k_shift_left, grd, blk, 0, g->tmp, g->B, g->nx, g->nrows, g->nrow, zero_right);
 	{ f3* t = g->B; g->B = g->tmp; g->tmp = t; }
 	if (alias_e) g->Epart = g->E;
 	if (alias_b) g->Bpart = g->B;
 }
+
+extern "C" void zdev_emf_move_window(zdev_grid2d* g) { zdev_emf_shift(g, 1); }
 
 // ------------------------------------------------------------------ external fields
 
@@ -330,6 +381,8 @@ static void set_ext(zdev_grid2d* g, int is_b, int mode, const float v[3], const 
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	}
 }
+
+extern "C" void zdev_emf_update_part_fld(zdev_grid2d* g) { need_EB(g); update_part_fld(g); }
 
 extern "C" void zdev_emf_set_ext_uniform(zdev_grid2d* g, int e_on, const float e0[3], int b_on, const float b0[3]) {
 	set_ext(g, 0, e_on ? 1 : 0, e0, nullptr);

@@ -37,6 +37,16 @@ extern "C" int zdev_init(int device) {
 	return 0;
 }
 
+// run on a stream owned by the caller (e.g. torch's current stream so NCCL collectives issued by
+// torch.distributed are ordered with the kernels); nullptr restores the library stream
+static cudaStream_t zdev_own_strm = nullptr;
+extern "C" void zdev_set_stream(void* stream) {
+	zdev_require_init();
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	if (!zdev_own_strm) zdev_own_strm = zdev_strm;
+	zdev_strm = stream ? (cudaStream_t) stream : zdev_own_strm;
+}
+
 extern "C" int zdev_ready(void) { return zdev_is_ready; }
 extern "C" void zdev_sync(void) { zdev_require_init(); ZDEV_CHECK(cudaStreamSynchronize(zdev_strm)); }
 extern "C" void* zdev_stream(void) { zdev_require_init(); return (void*) zdev_strm; }

@@ -75,7 +75,9 @@ struct ctl2d {
 	double energy;                   // sum of utsq/(gamma+1)
 	unsigned long long np;           // live particles after the step
 	unsigned int n_mig;              // entries in the migrants list
-	unsigned int flags;              // 1: tile capacity overflow, 2: migrants list overflow
+	unsigned int flags;              // 1: tile capacity overflow, 2: migrants list overflow, 4: export list overflow
+	unsigned int n_exp[2];           // slab mode: particles handed to the left / right neighbour
+	unsigned int pad[2];
 };
 
 struct zdev_spec2d {
@@ -91,6 +93,8 @@ struct zdev_spec2d {
 	int* tile_np_q;                  // device, ntiles: slots in use in q
 	soa2d mig;                       // migrants list (global cell indices)
 	unsigned int mig_cap;
+	part_aos* exp_buf[2];            // slab mode: export lists (AoS, ix already in the neighbour's frame)
+	unsigned int exp_cap;
 	ctl2d* ctl;                      // device
 	int64_t np_host;                 // last known particle count
 	int ids_valid;                   // tags are a permutation of [0,np)
@@ -189,6 +193,8 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 }
 
 static void spec_free_particles(zdev_spec2d* s) {
+	for (int k = 0; k < 2; k++) { cudaFree(s->exp_buf[k]); s->exp_buf[k] = nullptr; }
+	s->exp_cap = 0;
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); soa_free(s->mig); }
 	s->cap_total = 0; s->mig_cap = 0;
 }
@@ -279,6 +285,10 @@ static void check_flags(zdev_spec2d* s, unsigned int flags) {
 	}
 	if (flags & 2u) {
 		fprintf(stderr, "(*error*) zpic-b200: particle migration list overflow (capacity %u), aborting.\n", s->mig_cap);
+		exit(-1);
+	}
+	if (flags & 4u) {
+		fprintf(stderr, "(*error*) zpic-b200: slab export list overflow (capacity %u), aborting.\n", s->exp_cap);
 		exit(-1);
 	}
 }
@@ -671,11 +681,13 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			x = x1; y = y1;
 			int ix = x0 + lx + di - prm.shift_window, iy = y0 + ly + dj;
 			// boundaries (reference particles.c:1237-1259)
+			// an x edge is either a slab boundary (particle handed to the neighbour rank through the
+			// migrants list, keeping its out-of-range index), absorbing (moving window) or periodic
 			fate = active ? 1 : 0;
-			if (prm.moving_window) {
-				if (ix < 0 || ix >= g.nx) fate = 0;
-			} else {
-				ix += ((ix < 0) ? g.nx : 0) - ((ix >= g.nx) ? g.nx : 0);
+			if (ix < 0) {
+				if (!prm.slab_left) { if (prm.moving_window) fate = 0; else ix += g.nx; }
+			} else if (ix >= g.nx) {
+				if (!prm.slab_right) { if (prm.moving_window) fate = 0; else ix -= g.nx; }
 			}
 			iy += ((iy < 0) ? g.ny : 0) - ((iy >= g.ny) ? g.ny : 0);
 			const int nlx = ix - x0, nly = iy - y0;
@@ -790,12 +802,23 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 
 // append the migrants to their destination tiles and count the population
 __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, soa2d mig,
-                            unsigned int mig_cap, ctl2d* __restrict__ ctl, int TX, int TY, int ntx) {
+                            unsigned int mig_cap, ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int nx,
+                            part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap) {
 	unsigned int n = ctl->n_mig;
 	if (n > mig_cap) n = mig_cap;
 	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		rec24 v = rec_load(mig.rec + k);
 		int ix = v.cell, iy = mig.iy[k];
+		if (ix < 0 || ix >= nx) {
+			// leaves the slab: export in the neighbour's frame (all slabs have the same width)
+			const int side = ix >= nx;
+			unsigned int slot = atomicAdd(&ctl->n_exp[side], 1u);
+			if (slot >= exp_cap) { atomicOr(&ctl->flags, 4u); continue; }
+			part_aos r; r.ix = side ? ix - nx : ix + nx; r.iy = iy;
+			r.x = v.x; r.y = v.y; r.ux = v.ux; r.uy = v.uy; r.uz = v.uz;
+			(side ? exp_r : exp_l)[slot] = r;
+			continue;
+		}
 		int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 		int slot = atomicAdd(&tile_np[t], 1);
 		int64_t d = tile_off[t] + slot;
@@ -859,9 +882,15 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	// B becomes the current buffer
 	{ soa2d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
+	if ((prm->slab_left || prm->slab_right) && !s->exp_cap) {
+		// a window shift sends a whole column at once: size the export lists for two columns
+		int64_t cap = (int64_t) 2 * s->ppc_hint * s->ny + 65536;
+		s->exp_cap = (unsigned int) cap;
+		for (int k = 0; k < 2; k++) ZDEV_CHECK(cudaMalloc(&s->exp_buf[k], (size_t) cap * sizeof(part_aos)));
+	}
 	ZDEV_LAUNCH(k_migrate2d, 2 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->mig_cap, s->ctl,
-	            s->TX, s->TY, s->ntx);
-	if (prm->moving_window) s->ids_valid = 0;
+	            s->TX, s->TY, s->ntx, s->nx, s->exp_buf[0], s->exp_buf[1], s->exp_cap);
+	if (prm->moving_window || prm->slab_left || prm->slab_right) s->ids_valid = 0;
 }
 
 extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* np) {
@@ -920,4 +949,26 @@ extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_w
 	ZDEV_CHECK(cudaMemcpyAsync(charge, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_rho);
+}
+
+// ------------------------------------------------------------------ slab decomposition support
+
+extern "C" void zdev_spec2d_export_counts(zdev_spec2d* s, int64_t counts[2]) {
+	ctl2d h;
+	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof(h), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	check_flags(s, h.flags);
+	counts[0] = h.n_exp[0]; counts[1] = h.n_exp[1];
+}
+extern "C" void* zdev_spec2d_export_ptr(zdev_spec2d* s, int side) { return s->exp_buf[side ? 1 : 0]; }
+
+extern "C" void zdev_spec2d_append_device(zdev_spec2d* s, const void* dev_aos, int64_t np) {
+	if (np <= 0) return;
+	if (!s->cap_total) {
+		fprintf(stderr, "(*error*) zdev_spec2d_append_device: species has no tile layout yet (upload or inject first)\n");
+		exit(-1);
+	}
+	spec_append_dev(s, (const part_aos*) dev_aos, np, 0);
+	s->np_host += np;
+	s->ids_valid = 0;
 }

@@ -328,6 +328,7 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 	prm.qny   = spec->q * spec->dx[1] / spec->dt;
 	prm.q     = spec->q;
 	prm.moving_window = spec->moving_window;
+	prm.slab_left = prm.slab_right = 0;      /* single-slab API path; slabs are driven through zpic_dev.h */
 	/* the window test uses the already incremented iteration (particles.c:1234-1240, :621) */
 	prm.shift_window = spec->moving_window &&
 		( ((spec->iter + 1) * spec->dt) > (spec->dx[0] * (spec->n_move + 1)) );
