@@ -321,7 +321,7 @@ def slab_step_phases(slab, comm, inject_column=None):
                 slab.import_particles(k, recv_r)
     for k in range(nsp):
         if shifts[k] and g.is_last and inject_column is not None:
-            slab.append_host_particles(k, inject_column(k))
+            slab.append_host_particles(k, inject_column(k, slab.species[k]["n_move"]))
 
     # ---- current: guard fold + smoothing ----------------------------------------------------------
     if interior:
@@ -436,3 +436,34 @@ def split_grid(arr, geom):
 def join_grids(local_arrays, nranks):
     """interior columns of the slabs' local buffers -> global interior (ny, nx, 3)"""
     return np.concatenate([a[1:-2, 1:-2, :] for a in local_arrays], axis=1)
+
+
+class HostColumnInjector:
+    """Moving-window injection for the last slab: runs the library's host injector (the reference's
+    sequential random stream, em2d/particles.c:476-492, 619-638) on the GLOBAL species description for
+    the right-most cell column and returns the new particles in the slab's local coordinates."""
+
+    def __init__(self, lib, species_array, geom):
+        from . import abi_em2d as A
+        self.A, self.lib, self.species, self.g = A, lib, species_array, geom
+        fn = lib.spec_inject_into
+        fn.restype = None
+        fn.argtypes = [C.POINTER(A.Species), C.c_void_p, C.POINTER(C.POINTER(A.Part)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        self.libc = C.CDLL(None)
+        self.libc.free.argtypes = [C.c_void_p]
+
+    def __call__(self, k, n_move):
+        A, g = self.A, self.g
+        sp = self.species[k]
+        sp.n_move = n_move
+        rng = ((C.c_int * 2) * 2)((C.c_int * 2)(g.nx_global - 1, g.nx_global - 1), (C.c_int * 2)(0, g.ny - 1))
+        buf, n, nmax = C.POINTER(A.Part)(), C.c_int(0), C.c_int(0)
+        self.lib.spec_inject_into(C.byref(sp), rng, C.byref(buf), C.byref(n), C.byref(nmax))
+        out = np.zeros(n.value, dtype=A.PART_DTYPE)
+        if n.value:
+            raw = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint8)), shape=(n.value * 28,))
+            out[:] = raw.view(A.PART_DTYPE)
+            out["ix"] -= g.x0
+        if buf:
+            self.libc.free(buf)
+        return out
