@@ -134,7 +134,7 @@ def run_slabs(args, lib, rank, world, local):
     import torch
     import torch.distributed as dist
     from zpic_b200 import parallel as P
-    lib.zdev_set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = P.share_stream_with_torch(lib)      # one stream for kernels, torch buffers and NCCL
     n, _ = fit_grid(lib, args.n, args.ppc * args.ppc)
     geom = P.Geometry(n * world, n, world, rank, moving_window=False)
     npc = args.ppc * args.ppc
@@ -446,9 +446,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096, help="grid cells per side per GPU")
+    ap.add_argument("--grid", dest="n", type=int, default=4096, help="grid cells per side per GPU")
     ap.add_argument("--ppc", type=int, default=8, help="particles per cell per direction (8 -> 64 ppc)")
-    ap.add_argument("--e2e-n", type=int, default=1024, dest="e2e_n")
+    ap.add_argument("--e2e-grid", type=int, default=1024, dest="e2e_n")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -19,10 +19,12 @@ def _setup(ours):
     assert ours.zdev_init(-1) == 0
     ours.zpic_b200_set_option(b"track_ids", 0)
     ours.zpic_b200_set_option(b"lazy", 0)
-    ours.zdev_set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = P.share_stream_with_torch(ours)
     yield
     ours.zdev_sync()
     ours.zdev_set_stream(None)
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    del stream
 
 
 def _slabs_from_deck(lib, deck, nranks, window, smooth):

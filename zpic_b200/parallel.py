@@ -253,6 +253,18 @@ class CudaSlab:
         self.lib.zdev_grid2d_destroy(self.grid)
 
 
+def share_stream_with_torch(lib):
+    """Run the library and torch (buffers, NCCL collectives) on ONE explicit CUDA stream so that
+    kernels, pack/unpack and send/recv are ordered without host synchronisation.  The legacy default
+    stream cannot be used for this (handle 0 means 'library stream' to zdev_set_stream and the library
+    stream is non-blocking), so a fresh torch stream is made current.  Returns it (keep a reference)."""
+    import torch
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    lib.zdev_set_stream(stream.cuda_stream)
+    return stream
+
+
 def _tensor_from_ptr(torch, ptr, n, dtype, device):
     """zero-copy torch view of device memory owned by the library"""
     class _Holder:
