@@ -1,0 +1,90 @@
+/* zpic-b200 :: ZDF output (reference em2d/zdf.h).
+ * Writer for the self-describing little-endian "ZDF1" container the reference uses
+ * for every diagnostic.  Files written here are byte-compatible
+ * with the reference writer, so python/lib/zdf.py and zpic_b200/zdf.py read both.
+ * Public types keep the reference's field order (they are part of its C API). */
+#ifndef ZPIC_B200_ZDF_H
+#define ZPIC_B200_ZDF_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#define zdf_max_dims 3
+
+enum zdf_data_type {
+	zdf_null, zdf_int8, zdf_uint8, zdf_int16, zdf_uint16, zdf_int32, zdf_uint32,
+	zdf_int64, zdf_uint64, zdf_float32, zdf_float64
+};
+enum zdf_file_access_mode { ZDF_CREATE, ZDF_READ, ZDF_UPDATE };
+
+typedef struct ZDF_File {
+	FILE *fp;
+	enum zdf_file_access_mode mode;
+	uint32_t ndatasets;
+} t_zdf_file;
+
+typedef struct ZDF_Dataset {
+	char* name;
+	enum zdf_data_type data_type;
+	uint32_t ndims;
+	uint64_t count[zdf_max_dims];
+	void* data;
+	uint64_t id;
+	uint64_t offset;
+} t_zdf_dataset;
+
+enum zdf_axis_type { zdf_linear, zdf_log10, zdf_log2 };
+
+typedef struct ZDF_GridAxis {
+	char* name;
+	enum zdf_axis_type type;
+	double min, max;
+	char* label;
+	char* units;
+} t_zdf_grid_axis;
+
+typedef struct ZDF_GridInfo {
+	char* name;
+	uint32_t ndims;
+	uint64_t count[zdf_max_dims];
+	char* label;
+	char* units;
+	t_zdf_grid_axis *axis;
+} t_zdf_grid_info;
+
+typedef struct ZDF_Iteration {
+	char* name;
+	int32_t n;
+	double t;
+	char* time_units;
+} t_zdf_iteration;
+
+typedef struct ZDF_PartInfo {
+	char* name;
+	char* label;
+	uint64_t np;
+	uint32_t nquants;
+	char** quants;
+	char** qlabels;
+	char** qunits;
+} t_zdf_part_info;
+
+size_t zdf_sizeof( enum zdf_data_type data_type );
+int zdf_open_file( t_zdf_file* zdf, const char* filename, enum zdf_file_access_mode mode );
+int zdf_close_file( t_zdf_file* zdf );
+size_t zdf_add_string( t_zdf_file* zdf, const char* name, const char* str );
+size_t zdf_add_int32( t_zdf_file* zdf, const char* name, const int32_t value );
+size_t zdf_add_double( t_zdf_file* zdf, const char* name, const double value );
+size_t zdf_add_iteration( t_zdf_file* zdf, const t_zdf_iteration* iter );
+size_t zdf_add_grid_info( t_zdf_file* zdf, const t_zdf_grid_info* grid );
+size_t zdf_add_part_info( t_zdf_file* zdf, const t_zdf_part_info* part );
+size_t zdf_add_dataset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+int zdf_open_grid_file( t_zdf_file *file, const t_zdf_grid_info *info,
+                        const t_zdf_iteration *iteration, char const path[] );
+int zdf_save_grid( const void* data, enum zdf_data_type data_type, const t_zdf_grid_info *info,
+                   const t_zdf_iteration *iteration, char const path[] );
+int zdf_open_part_file( t_zdf_file *file, t_zdf_part_info *info,
+                        const t_zdf_iteration *iteration, char const path[] );
+int zdf_add_quant_part_file( t_zdf_file *zdf, const char *name, const float* data, const uint64_t np );
+
+#endif

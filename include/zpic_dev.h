@@ -195,6 +195,62 @@ void zdev_spec2d_push_timing( zdev_spec2d* s, double* total_ms, int64_t* launche
 /* tile geometry chosen for this species (cells per tile in x,y; number of tiles) */
 void zdev_spec2d_tile_info( zdev_spec2d* s, int* tx, int* ty, int* ntiles, int64_t* capacity );
 
+/* ============================================================ em1d ============================ */
+/* Grids: nx+3 float3 cells, guards {1 lower, 2 upper} (em1d/emf.c:41-65, em1d/current.c:33-50).
+ * Boundary types are the reference enums: fields 0 none / 1 periodic / 2 open (Mur),
+ * current 0 none / 1 periodic (em1d/emf.h:83-87, em1d/current.h:29-32). */
+
+typedef struct zdev_grid1d zdev_grid1d;
+
+zdev_grid1d* zdev_grid1d_create( int nx );
+void zdev_grid1d_destroy( zdev_grid1d* g );
+void zdev_grid1d_upload( zdev_grid1d* g, int which, const float* host_buf );
+void zdev_grid1d_download( zdev_grid1d* g, int which, float* host_buf );
+/* current_zero (em1d/current.c:97-104) */
+void zdev_current1d_zero( zdev_grid1d* g );
+/* current_update minus iter++ (em1d/current.c:112-155, 265-333): guard fold when periodic, then
+ * xlevel binomial passes (+ compensator for xtype 2) */
+void zdev_current1d_update( zdev_grid1d* g, int bc_periodic, int xtype, int xlevel );
+/* emf_advance minus iter++ (em1d/emf.c:548-590): yee_b(dt/2), yee_e(dt), mur_abc when bc_type is open
+ * (em1d/emf.c:379-408), yee_b(dt/2), emf_update_gc when periodic (em1d/emf.c:470-502, incl. its
+ * one-cell upper refresh), external fields, window shift (em1d/emf.c:513-537) */
+void zdev_emf1d_advance( zdev_grid1d* g, zdev_grid1d* g_cur, float dt, float dx, int bc_type, int shift_window );
+/* Mur boundary state: mur_fld[2], mur_tmp[2] as 12 floats (host struct order) */
+void zdev_emf1d_set_mur( zdev_grid1d* g, const float state[12] );
+void zdev_emf1d_get_mur( zdev_grid1d* g, float state[12] );
+void zdev_emf1d_set_ext_uniform( zdev_grid1d* g, int e_on, const float e0[3], int b_on, const float b0[3] );
+void zdev_emf1d_set_ext_grid( zdev_grid1d* g, const float* host_ext_e, const float* host_ext_b );
+/* emf_get_energy sums (em1d/emf.c:600-620) */
+void zdev_emf1d_energy( zdev_grid1d* g, double sums[6] );
+
+typedef struct zdev_spec1d zdev_spec1d;
+
+/* per-step scalars (em1d/particles.c:925-931) */
+typedef struct zdev_push1d_params {
+	float tem;      /* (float)(0.5*dt/m_q) */
+	float dt_dx;    /* dt/dx */
+	float qnx;      /* q*dx/dt */
+	float q;
+	int   absorbing;      /* 1: moving window or PART_BC_OPEN (em1d/particles.c:1044-1057) */
+	int   shift_window;   /* 1: all ix-- this step (em1d/particles.c:663-684) */
+} zdev_push1d_params;
+
+zdev_spec1d* zdev_spec1d_create( int nx, int ppc_hint, int track_ids );
+void zdev_spec1d_destroy( zdev_spec1d* s );
+/* host records are the 20-byte t_part of em1d/particles.h:29-35 */
+void zdev_spec1d_upload( zdev_spec1d* s, const void* part_aos, int64_t np );
+void zdev_spec1d_append( zdev_spec1d* s, const void* part_aos, int64_t np );
+int64_t zdev_spec1d_download( zdev_spec1d* s, void* part_aos, int64_t max_np );
+int64_t zdev_spec1d_np( zdev_spec1d* s );
+void zdev_spec1d_inject_uniform( zdev_spec1d* s, int ppc, const float ufl[3], const float uth[3], uint64_t seed );
+/* spec_advance minus host bookkeeping (em1d/particles.c:936-1062): interpolate_fld (:864-886), Boris,
+ * dep_current_zamb (:707-779), boundaries / window shift, per-step re-binning */
+void zdev_spec1d_advance( zdev_spec1d* s, zdev_grid1d* g, zdev_grid1d* g_cur, const zdev_push1d_params* p );
+void zdev_spec1d_fetch( zdev_spec1d* s, double* energy_sum, int64_t* np );
+/* spec_deposit_charge (em1d/particles.c:1085-1106): charge has nx+1 entries, added to */
+void zdev_spec1d_deposit_charge( zdev_spec1d* s, float q, int moving_window, float* charge );
+void zdev_spec1d_push_timing( zdev_spec1d* s, double* total_ms, int64_t* launches, int reset );
+
 #ifdef __cplusplus
 }
 #endif

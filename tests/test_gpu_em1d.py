@@ -1,0 +1,88 @@
+"""GPU parity of the em1d path: product (CUDA) vs the unmodified reference, same calls on both."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests import helpers1d as H1
+from zpic_b200 import abi_em1d as A
+from zpic_b200 import load
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ref1():
+    lib = H1.load_ref()
+    if lib is None:
+        pytest.skip("oracle/_ref not built")
+    return lib
+
+
+@pytest.fixture()
+def ours1():
+    lib = load("em1d")
+    assert lib.zdev_init(-1) == 0
+    lib.zpic_b200_set_option(b"track_ids", 1)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    return lib
+
+
+def test_twostream_one_step_bit_exact(ours1, ref1):
+    a, b = H1.twostream(ours1, ppc=64, n_sort=0), H1.twostream(ref1, ppc=64, n_sort=0)
+    a.iter(1)
+    b.iter(1)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert sa["np"][k] == sb["np"][k]
+        assert np.array_equal(sa["parts"][k].view(np.uint8), sb["parts"][k].view(np.uint8))
+        assert abs(sa["energy"][k] - sb["energy"][k]) <= 1e-6 * abs(sb["energy"][k])
+    assert H.rel_l2(sa["J"], sb["J"]) < 1e-6
+
+
+def test_twostream_shipped_deck_100_steps(ours1, ref1):
+    """config 5 parity case: em1d/input/twostream.c as shipped (120 cells, 2 x 500 ppc)"""
+    a, b = H1.twostream(ours1, n_sort=0), H1.twostream(ref1, n_sort=0)
+    for cp in (1, 100):
+        a.iter(cp - a.sim.emf.iter)
+        b.iter(cp - b.sim.emf.iter)
+        sa, sb = a.snapshot(), b.snapshot()
+        for q in ("E", "J"):
+            assert H.rel_l2(sa[q], sb[q]) < TOL, (cp, q)
+        for k in range(2):
+            assert sa["np"][k] == sb["np"][k] == 60000
+            assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL
+            assert (sa["parts"][k]["ix"] != sb["parts"][k]["ix"]).sum() <= 2
+            assert abs(sa["energy"][k] - sb["energy"][k]) <= 1e-6 * abs(sb["energy"][k])
+        assert abs(a.emf_energy().sum() - b.emf_energy().sum()) <= 1e-5 * max(b.emf_energy().sum(), 1e-30)
+    for k in range(2):
+        assert H.rel_l2(a.charge(k), b.charge(k)) < 1e-6
+
+
+def test_open_boundaries_and_smoothing_bit_exact(ours1, ref1):
+    """fields only: Mur boundary + yee solver are deterministic, so every cell must match"""
+    a, b = H1.absorbing(ours1, 400), H1.absorbing(ref1, 400)
+    a.iter(300)
+    b.iter(300)
+    a.sync()
+    assert np.array_equal(a.E().view(np.uint32), b.E().view(np.uint32))
+    assert np.array_equal(a.B().view(np.uint32), b.B().view(np.uint32))
+
+
+def test_moving_window_with_injection(ours1, ref1):
+    a, b = H1.movwindow(ours1, n_sort=0), H1.movwindow(ref1, n_sort=0)
+    a.set_smooth(A.BINOMIAL, 2)
+    b.set_smooth(A.BINOMIAL, 2)
+    for cp in (1, 60, 200):
+        a.iter(cp - a.sim.emf.iter)
+        b.iter(cp - b.sim.emf.iter)
+        sa, sb = a.snapshot(), b.snapshot()
+        assert a.sim.emf.n_move == b.sim.emf.n_move and sa["np"][0] == sb["np"][0]
+        for q in ("E", "B", "J"):
+            assert H.rel_l2(sa[q], sb[q]) < TOL, (cp, q)
+        pa = np.sort(sa["parts"][0], order=["ix", "x", "ux"])
+        pb = np.sort(sb["parts"][0], order=["ix", "x", "ux"])
+        assert np.array_equal(pa["ix"], pb["ix"])
+    assert b.sim.emf.n_move > 20

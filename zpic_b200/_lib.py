@@ -26,8 +26,16 @@ def load(code="em2d"):
     if code == "em2d":
         from . import abi_em2d
         abi_em2d.declare(lib)
+    elif code == "em1d":
+        from . import abi_em1d
+        abi_em1d.declare(lib)
     _cache[code] = lib
     return lib
+
+
+class PushParams1D(C.Structure):   # zdev_push1d_params (include/zpic_dev.h)
+    _fields_ = [("tem", C.c_float), ("dt_dx", C.c_float), ("qnx", C.c_float), ("q", C.c_float),
+                ("absorbing", C.c_int), ("shift_window", C.c_int)]
 
 
 class PushParams2D(C.Structure):   # zdev_push2d_params (include/zpic_dev.h)
@@ -84,7 +92,23 @@ def _declare_dev(lib):
         "zdev_emf_update_part_fld": (None, [vp]),
         "zdev_set_stream": (None, [vp]),
     }
-    for table in (sig, sig2d):
+    sig1d = {
+        "zdev_grid1d_create": (vp, [i]), "zdev_grid1d_destroy": (None, [vp]),
+        "zdev_grid1d_upload": (None, [vp, i, vp]), "zdev_grid1d_download": (None, [vp, i, vp]),
+        "zdev_current1d_zero": (None, [vp]), "zdev_current1d_update": (None, [vp, i, i, i]),
+        "zdev_emf1d_advance": (None, [vp, vp, f, f, i, i]),
+        "zdev_emf1d_set_mur": (None, [vp, fp]), "zdev_emf1d_get_mur": (None, [vp, fp]),
+        "zdev_emf1d_energy": (None, [vp, C.POINTER(C.c_double)]),
+        "zdev_spec1d_create": (vp, [i, i, i]), "zdev_spec1d_destroy": (None, [vp]),
+        "zdev_spec1d_upload": (None, [vp, vp, C.c_int64]), "zdev_spec1d_append": (None, [vp, vp, C.c_int64]),
+        "zdev_spec1d_download": (C.c_int64, [vp, vp, C.c_int64]), "zdev_spec1d_np": (C.c_int64, [vp]),
+        "zdev_spec1d_inject_uniform": (None, [vp, i, fp, fp, C.c_uint64]),
+        "zdev_spec1d_advance": (None, [vp, vp, vp, C.POINTER(PushParams1D)]),
+        "zdev_spec1d_fetch": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+        "zdev_spec1d_deposit_charge": (None, [vp, f, i, fp]),
+        "zdev_spec1d_push_timing": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), i]),
+    }
+    for table in (sig, sig2d, sig1d):
         for name, (res, args) in table.items():
             if hasattr(lib, name):
                 fn = getattr(lib, name)

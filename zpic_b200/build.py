@@ -39,7 +39,12 @@ CODES = {
         "dev": ["zdev_runtime.cu", "zdev_grid2d.cu", "zdev_spec2d.cu"],
         "host_dir": "em2d",
     },
+    "em1d": {
+        "dev": ["zdev_runtime.cu", "zdev_grid1d.cu", "zdev_spec1d.cu"],
+        "host_dir": "em1d",
+    },
 }
+HOST_COMMON = "common"      # random.c, timer.c, zdf.c: identical in every reference code directory
 
 
 def _newer(target, sources):
@@ -83,11 +88,11 @@ def build(code="em2d", force=False, verbose=False):
             if verbose:
                 print(out)
         objs.append(obj)
-    hdir = os.path.join(CSRC, "host", cfg["host_dir"])
-    for f in sorted(os.listdir(hdir)) if os.path.isdir(hdir) else []:
-        if not f.endswith(".c"):
-            continue
-        src = os.path.join(hdir, f)
+    hsrc = []
+    for d in (os.path.join(CSRC, "host", HOST_COMMON), os.path.join(CSRC, "host", cfg["host_dir"])):
+        hsrc += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".c")] if os.path.isdir(d) else []
+    for src in hsrc:
+        f = os.path.basename(src)
         obj = os.path.join(OBJDIR, code, "host_" + f.replace(".c", ".o"))
         if force or _newer(obj, [src] + hdrs):
             _run([CC] + CC_FLAGS + ["-I" + os.path.join(REPO, "include", cfg["host_dir"]),

@@ -15,6 +15,7 @@
 extern uint64_t zdev_n_launch;
 extern cudaStream_t zdev_strm;
 extern int zdev_num_sm;
+extern int zdev_time_push;
 
 #define ZDEV_LAUNCH(kernel, grid, block, smem, ...) do { \
 	kernel<<<(grid), (block), (smem), zdev_strm>>>(__VA_ARGS__); \

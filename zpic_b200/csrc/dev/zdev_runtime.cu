@@ -47,6 +47,10 @@ extern "C" void zdev_set_stream(void* stream) {
 	zdev_strm = stream ? (cudaStream_t) stream : zdev_own_strm;
 }
 
+// per-launch CUDA-event timing of the push kernels (bench roofline), see zdev_spec*_push_timing
+int zdev_time_push = 0;
+extern "C" void zdev_set_push_timing(int on) { zdev_time_push = on; }
+
 extern "C" int zdev_ready(void) { return zdev_is_ready; }
 extern "C" void zdev_sync(void) { zdev_require_init(); ZDEV_CHECK(cudaStreamSynchronize(zdev_strm)); }
 extern "C" void* zdev_stream(void) { zdev_require_init(); return (void*) zdev_strm; }

@@ -105,9 +105,6 @@ struct zdev_spec2d {
 	double push_ms; int64_t push_launches, push_particles;
 };
 static const int EV_RING = 64;
-static int g_time_push = 0;
-
-extern "C" void zdev_set_push_timing(int on) { g_time_push = on; }
 
 static void spec_collect_timing(zdev_spec2d* s) {
 	if (!s->ev) return;
@@ -128,7 +125,10 @@ extern "C" void zdev_spec2d_push_timing(zdev_spec2d* s, double* total_ms, int64_
 	if (reset) { s->push_ms = 0; s->push_launches = 0; }
 }
 
-static const int PUSH_THREADS = 256;
+#ifndef PUSH_THREADS_N
+#define PUSH_THREADS_N 256
+#endif
+static const int PUSH_THREADS = PUSH_THREADS_N;
 static const int PUSH_WARPS = PUSH_THREADS / 32;
 #ifndef PUSH_MIN_BLOCKS
 #define PUSH_MIN_BLOCKS 2           // CTAs per SM the register allocation is sized for
@@ -847,7 +847,7 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		configured = smem;
 	}
 	int slot = -1;
-	if (g_time_push) {
+	if (zdev_time_push) {
 		if (!s->ev) {
 			s->ev = new std::vector<cudaEvent_t>(2 * EV_RING);
 			for (auto& e : *s->ev) ZDEV_CHECK(cudaEventCreate(&e));

@@ -1,0 +1,51 @@
+/* zpic-b200 :: host <-> device bookkeeping for the em1d API layer (internal; 1-D twin of
+ * csrc/host/em2d/zb_state.h - registry of device twins keyed by host object address + coherence flags) */
+#ifndef ZB_STATE_1D_H
+#define ZB_STATE_1D_H
+
+#include "zpic_dev.h"
+#include "simulation.h"
+
+typedef struct zb_grid {
+	const t_emf* emf;
+	const t_current* cur;
+	zdev_grid1d* g;            /* NULL until first device use */
+	int nx;
+	int eb_dev_stale, eb_host_stale, j_host_stale, part_host_stale;
+	int mur_dev_stale;         /* host mur_fld / mur_tmp newer than the device copy */
+} zb_grid;
+
+typedef struct zb_spec {
+	const t_species* spec;
+	zdev_spec1d* d;
+	int device_init;
+	uint64_t device_seed;
+	int dev_stale, host_stale;
+	const t_part* part_seen;
+	int np_seen;
+} zb_spec;
+
+zb_grid* zb_grid_of_emf( const t_emf* emf, int create );
+zb_grid* zb_grid_of_cur( const t_current* cur, int create );
+zdev_grid1d* zb_dev( zb_grid* e );
+void zb_grid_pair( const t_emf* emf, const t_current* cur );
+void zb_grid_drop_emf( const t_emf* emf );
+void zb_grid_drop_cur( const t_current* cur );
+zb_spec* zb_spec_of( const t_species* spec, int create );
+zdev_spec1d* zb_spec_dev( zb_spec* e );
+void zb_spec_drop( const t_species* spec );
+
+void zb_emf_to_device( t_emf* emf );
+void zb_emf_to_host( const t_emf* emf );
+void zb_cur_to_host( const t_current* cur );
+void zb_spec_to_device( t_species* spec );
+void zb_spec_to_host( const t_species* spec );
+
+int zb_opt_lazy( void );
+int zb_opt_track_ids( void );
+int zb_opt_coherent( void );
+int zb_opt_device_init( void );
+
+void spec_inject_into( t_species* spec, const int range[], t_part** buf, int* np, int* np_max );
+
+#endif
