@@ -52,8 +52,9 @@ def test_twostream_shipped_deck_100_steps(ours1, ref1):
         b.iter(cp - b.sim.emf.iter)
         sa, sb = a.snapshot(), b.snapshot()
         assert np.abs(sa["J"] - sb["J"]).max() < TOL * 0.2, cp          # see above: beams cancel
-        if cp > 1:
-            assert H.rel_l2(sa["E"], sb["E"]) < TOL * 10, cp                # E is still noise-level at step 100
+        # E_x = -int J_x dt of the CANCELLED current: still ~5e-5 at step 100 (instability at noise level),
+        # so its summation-order noise is measured on the scale of one beam's contribution, 0.2 * t
+        assert np.abs(sa["E"] - sb["E"]).max() < TOL * 0.2 * (cp * 0.1), cp
         for k in range(2):
             assert sa["np"][k] == sb["np"][k] == 60000
             assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL

@@ -93,6 +93,7 @@ struct zdev_spec2d {
 	int* tile_np_q;                  // device, ntiles: slots in use in q
 	soa2d mig;                       // migrants list (global cell indices)
 	unsigned int mig_cap;
+	part_aos* stage; int64_t stage_cap;   // persistent staging for appended host particles
 	part_aos* exp_buf[2];            // slab mode: export lists (AoS, ix already in the neighbour's frame)
 	unsigned int exp_cap;
 	ctl2d* ctl;                      // device
@@ -194,6 +195,7 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 
 static void spec_free_particles(zdev_spec2d* s) {
 	for (int k = 0; k < 2; k++) { cudaFree(s->exp_buf[k]); s->exp_buf[k] = nullptr; }
+	cudaFree(s->stage); s->stage = nullptr; s->stage_cap = 0;
 	s->exp_cap = 0;
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); soa_free(s->mig); }
 	s->cap_total = 0; s->mig_cap = 0;
@@ -329,18 +331,19 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 	s->ids_valid = s->track_ids;
 }
 
+// Appends are on the per-step path of a moving window (one injected column per move): the staging
+// buffer is kept, nothing is synchronised, and a capacity overflow is reported by the next fetch.
 extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np) {
 	if (np <= 0) return;
 	if (!s->cap_total) { zdev_spec2d_upload(s, part, np); return; }
-	part_aos* d_aos;
-	ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part_aos)));
-	ZDEV_CHECK(cudaMemcpyAsync(d_aos, part, (size_t) np * sizeof(part_aos), cudaMemcpyHostToDevice, zdev_strm));
-	spec_append_dev(s, d_aos, np, (int) s->np_host);
-	ctl2d h;
-	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof(h), cudaMemcpyDeviceToHost, zdev_strm));
-	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-	cudaFree(d_aos);
-	check_flags(s, h.flags);
+	if (np > s->stage_cap) {
+		if (s->stage) { ZDEV_CHECK(cudaStreamSynchronize(zdev_strm)); cudaFree(s->stage); }
+		s->stage_cap = np + np / 2 + 1024;
+		ZDEV_CHECK(cudaMalloc(&s->stage, (size_t) s->stage_cap * sizeof(part_aos)));
+	}
+	// pageable source: the copy is staged by the driver before the call returns, so `part` may be freed
+	ZDEV_CHECK(cudaMemcpyAsync(s->stage, part, (size_t) np * sizeof(part_aos), cudaMemcpyHostToDevice, zdev_strm));
+	spec_append_dev(s, s->stage, np, (int) s->np_host);
 	s->np_host += np;
 }
 

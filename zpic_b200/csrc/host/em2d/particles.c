@@ -179,7 +179,11 @@ static int place_particles( t_species* spec, const int range[][2], t_part* part,
 
 /* thermal momenta for part[first..last], cell-mean removed, fluid momentum added
  * (reference spec_set_u, particles.c:96-146; the cell index uses nx[1] as stride,
- * App. B item 5 - kept, it decides which particles share a mean) */
+ * App. B item 5 - kept, it decides which particles share a mean).
+ * The reference allocates and sweeps nx0*nx1 accumulators on every call, which is invisible next to its
+ * own push but would dominate a GPU step when a moving window injects one column per iteration.  The
+ * sums are order dependent only within a cell, so accumulating in particle order into a hash table of
+ * the cells actually touched gives bit-identical means at O(particles) cost. */
 static void draw_momenta( t_species* spec, t_part* part, int first, int last )
 {
 	for (int i = first; i <= last; i++) {
@@ -187,27 +191,39 @@ static void draw_momenta( t_species* spec, t_part* part, int first, int last )
 		part[i].uy = spec->uth[1] * rand_norm();
 		part[i].uz = spec->uth[2] * rand_norm();
 	}
+	const int n = last - first + 1;
+	if (n <= 0) return;
 
-	const int size = spec->nx[0] * spec->nx[1];
 	const int stride = spec->nx[1];
-	float3* mean = calloc(size, sizeof(float3));
-	int* count = calloc(size, sizeof(int));
+	size_t cap = 16;
+	while (cap < (size_t) 2 * n) cap <<= 1;
+	int* key = malloc(cap * sizeof(int));
+	int* count = calloc(cap, sizeof(int));
+	float3* mean = calloc(cap, sizeof(float3));
+	int* slot_of = malloc((size_t) n * sizeof(int));
+	memset(key, 0xff, cap * sizeof(int));              /* -1 = free */
+
 	for (int i = first; i <= last; i++) {
 		const int c = part[i].ix + stride * part[i].iy;
-		mean[c].x += part[i].ux; mean[c].y += part[i].uy; mean[c].z += part[i].uz;
-		count[c] += 1;
+		size_t h = ((size_t) (unsigned) c * 2654435761u) & (cap - 1);
+		while (key[h] != -1 && key[h] != c) h = (h + 1) & (cap - 1);
+		key[h] = c;
+		mean[h].x += part[i].ux; mean[h].y += part[i].uy; mean[h].z += part[i].uz;
+		count[h] += 1;
+		slot_of[i - first] = (int) h;
 	}
-	for (int c = 0; c < size; c++) {
-		const float norm = (count[c] > 0) ? 1.0f / count[c] : 0;
-		mean[c].x *= norm; mean[c].y *= norm; mean[c].z *= norm;
+	for (size_t h = 0; h < cap; h++) {
+		if (key[h] == -1) continue;
+		const float norm = 1.0f / count[h];
+		mean[h].x *= norm; mean[h].y *= norm; mean[h].z *= norm;
 	}
 	for (int i = first; i <= last; i++) {
-		const int c = part[i].ix + stride * part[i].iy;
-		part[i].ux += spec->ufl[0] - mean[c].x;
-		part[i].uy += spec->ufl[1] - mean[c].y;
-		part[i].uz += spec->ufl[2] - mean[c].z;
+		const int h = slot_of[i - first];
+		part[i].ux += spec->ufl[0] - mean[h].x;
+		part[i].uy += spec->ufl[1] - mean[h].y;
+		part[i].uz += spec->ufl[2] - mean[h].z;
 	}
-	free(count); free(mean);
+	free(slot_of); free(mean); free(count); free(key);
 }
 
 /* inject into an arbitrary AoS buffer (the species mirror at start-up, a scratch
