@@ -225,3 +225,23 @@ def test_external_uniform_fields(ours, ref):
         assert H.rel_l2(sa[q], sb[q]) < TOL_FIELD
     a.delete()
     b.delete()
+
+
+def test_kelvin_helmholtz_custom_density_and_xy_smoothing(ours, ref):
+    """BASELINE config 4 physics at 64x64: two counter-streaming half-box species from CUSTOM densities,
+    binomial smoothing in x and y (incl. the reference's xlevel-for-y quirk)"""
+    from tests.test_host_init import kh_deck
+    a, b = kh_deck(ours), kh_deck(ref)
+    for cp in (1, 60):
+        a.iter(cp - a.sim.emf.iter)
+        b.iter(cp - b.sim.emf.iter)
+        sa, sb = a.snapshot(), b.snapshot()
+        for q in ("E", "B", "J"):
+            assert H.rel_l2(sa[q], sb[q]) < TOL_FIELD, (cp, q)
+        for k in range(2):
+            assert sa["np"][k] == sb["np"][k]
+            same = (sa["parts"][k]["ix"] == sb["parts"][k]["ix"]) & (sa["parts"][k]["iy"] == sb["parts"][k]["iy"])
+            assert (~same).sum() <= (0 if cp == 1 else 3)
+            assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL_FIELD
+    a.delete()
+    b.delete()

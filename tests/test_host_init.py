@@ -41,3 +41,32 @@ def test_step_and_slab_injection_bit_exact(ours, ref):
         b = H.Deck(ref, (64, 32), (6.4, 3.2), 0.05, sp)
         assert a.species[0].np == b.species[0].np > 0
         assert np.array_equal(a.parts(0).view(np.uint8), b.parts(0).view(np.uint8))
+
+
+def _kh_species(lower):
+    """Kelvin-Helmholtz shear (BASELINE config 4): each species fills one half of the box in y through a
+    CUSTOM density (step function along y) and drifts along +x / -x"""
+    def step_y(y, data, lower=lower):
+        return 1.0 if ((y < 6.4) == lower) else 0.0
+    fn = A.DENSITY_FN(step_y)
+    dens = dict(type=A.CUSTOM, custom_y=fn)
+    return dict(name="lower" if lower else "upper", m_q=-1.0, ppc=(4, 2), ufl=(0.2 if lower else -0.2, 0, 0),
+                uth=(0.01, 0.01, 0.01), density=dens, n_sort=0), fn
+
+
+def kh_deck(lib, n=64):
+    a, fa = _kh_species(True)
+    b, fb = _kh_species(False)
+    d = H.Deck(lib, (n, n), (12.8, 12.8), 0.07, [a, b])
+    d._callbacks = (fa, fb)
+    d.set_smooth(xtype=A.BINOMIAL, ytype=A.BINOMIAL, xlevel=2, ylevel=2)
+    return d
+
+
+def test_custom_density_injection_bit_exact(ours, ref):
+    a, b = kh_deck(ours), kh_deck(ref)
+    for k in range(2):
+        assert a.species[k].np == b.species[k].np > 15000
+        assert np.array_equal(a.parts(k).view(np.uint8), b.parts(k).view(np.uint8))
+    # the trapezoidal inverse-CDF injector smears the step over the boundary cell row
+    assert a.parts(0)["iy"].max() == 30 and a.parts(1)["iy"].min() == 31
