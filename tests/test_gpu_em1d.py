@@ -64,7 +64,7 @@ def test_twostream_shipped_deck_100_steps(ours1, ref1):
         # diagnostic is compared on the scale of the total energy (1e-6 bar of the north star)
         assert abs(a.emf_energy().sum() - b.emf_energy().sum()) <= 1e-6 * sum(sb["energy"])
     for k in range(2):
-        assert H.rel_l2(a.charge(k), b.charge(k)) < 1e-6
+        assert H.rel_l2(a.charge(k), b.charge(k)) < TOL      # a field-type quantity of particles whose orbits differ by J summation-order noise
 
 
 def test_open_boundaries_and_smoothing_bit_exact(ours1, ref1):

@@ -245,3 +245,30 @@ def test_kelvin_helmholtz_custom_density_and_xy_smoothing(ours, ref):
             assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL_FIELD
     a.delete()
     b.delete()
+
+
+@pytest.mark.parametrize("zero_copy_min", ["1", "1000000000000"])
+def test_coherent_mode_round_trips_host_buffers(ours, ref, zero_copy_min, monkeypatch):
+    """ZPIC_COHERENT: every sim_iter re-uploads the host mirrors and refreshes them afterwards, through
+    the zero-copy (mapped pinned) path and through the staged path; host edits between steps must reach
+    the device exactly like they reach the reference's next step."""
+    monkeypatch.setenv("ZPIC_ZERO_COPY_MIN", zero_copy_min)
+    ours.zpic_b200_set_option(b"coherent", 1)
+    try:
+        a, b = H.weibel(ours, n=32, ppc=(2, 2), n_sort=0), H.weibel(ref, n=32, ppc=(2, 2), n_sort=0)
+        for step in range(4):
+            a.iter(1)
+            b.iter(1)
+            for d in (a, b):                      # edit raw buffers in place, no sync / touch calls
+                d.parts(0)["ux"][::7] += np.float32(0.01)
+                d.E()[5:9, 5:9, 2] += np.float32(1e-3)
+        for k in range(2):
+            pa, pb = a.parts(k), b.parts(k)
+            assert a.species[k].np == b.species[k].np
+            assert np.array_equal(pa["ix"], pb["ix"]) and H.rel_l2(pa["ux"], pb["ux"]) < 1e-6
+        for g in ("E", "B", "J"):
+            assert H.rel_l2(getattr(a, g)(), getattr(b, g)()) < TOL_FIELD
+        a.delete()
+        b.delete()
+    finally:
+        ours.zpic_b200_set_option(b"coherent", 0)

@@ -301,32 +301,71 @@ static void spec_append_dev(zdev_spec2d* s, const part_aos* d_aos, int64_t np, i
 	            s->p, s->tile_off, s->tile_np, s->ctl, tag0);
 }
 
+// Host buffers of at least this size are pinned + mapped once and then read / written by the binning
+// and gather kernels directly over PCIe (zero copy): no device staging copy of the population, and
+// repeated transfers of the same mirror (ZPIC_COHERENT) run at link speed instead of pageable speed.
+static const size_t MAP_MIN_BYTES = (size_t) 32 << 20;
+struct host_map { const void* ptr; size_t bytes; void* dev; };
+static host_map g_maps[8];
+
+static void* map_host(const void* ptr, size_t bytes) {
+	size_t min_bytes = MAP_MIN_BYTES;
+	if (const char* e = getenv("ZPIC_ZERO_COPY_MIN")) min_bytes = (size_t) atoll(e);     // tests: force / forbid
+	if (bytes < min_bytes || bytes == 0) return nullptr;
+	for (auto& m : g_maps) if (m.ptr == ptr && m.bytes >= bytes) return m.dev;
+	host_map* slot = &g_maps[0];
+	for (auto& m : g_maps) { if (m.ptr == ptr) { slot = &m; break; } if (!m.ptr) slot = &m; }
+	if (slot->ptr) { cudaHostUnregister((void*) slot->ptr); slot->ptr = nullptr; }
+	if (cudaHostRegister((void*) ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;                    // not pinnable (e.g. over the locked-memory limit): staged path
+	}
+	void* dev = nullptr;
+	if (cudaHostGetDevicePointer(&dev, (void*) ptr, 0) != cudaSuccess) { cudaGetLastError(); cudaHostUnregister((void*) ptr); return nullptr; }
+	slot->ptr = ptr; slot->bytes = bytes; slot->dev = dev;
+	return dev;
+}
+// a host buffer is about to be freed / reallocated by its owner
+extern "C" void zdev_host_forget(const void* ptr) {
+	for (auto& m : g_maps) if (m.ptr == ptr) { cudaHostUnregister((void*) m.ptr); m.ptr = nullptr; }
+}
+
 extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np) {
-	part_aos* d_aos = nullptr;
-	std::vector<int> cnt(s->ntiles, 0);
-	if (np > 0) {
-		ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part_aos)));
-		ZDEV_CHECK(cudaMemcpyAsync(d_aos, part, (size_t) np * sizeof(part_aos), cudaMemcpyHostToDevice, zdev_strm));
-		int* d_cnt; ZDEV_CHECK(cudaMalloc(&d_cnt, (size_t) s->ntiles * sizeof(int)));
-		ZDEV_CHECK(cudaMemsetAsync(d_cnt, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
-		ZDEV_LAUNCH(k_count_tiles, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->TY, s->ntx, d_cnt);
-		ZDEV_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+	const size_t bytes = (size_t) np * sizeof(part_aos);
+	part_aos* d_stage = nullptr;
+	const part_aos* src = (np > 0) ? (const part_aos*) map_host(part, bytes) : nullptr;
+	if (np > 0 && !src) {
+		ZDEV_CHECK(cudaMalloc(&d_stage, bytes));
+		ZDEV_CHECK(cudaMemcpyAsync(d_stage, part, bytes, cudaMemcpyHostToDevice, zdev_strm));
+		src = d_stage;
+	}
+	ctl2d h;
+	bool done = false;
+	if (np > 0 && s->cap_total > 0) {
+		// optimistic: bin straight into the existing tile layout, fall back if a tile overflows
+		ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+		ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
+		spec_append_dev(s, src, np, 0);
+		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(d_cnt);
+		done = !(h.flags & 1u);
 	}
-	// keep the existing tile layout when the new population fits (repeated uploads in
-	// "coherent" mode would otherwise reallocate every step)
-	bool fits = s->cap_total > 0;
-	if (fits) {
-		const std::vector<int64_t>& off = *s->h_off;
-		for (int t = 0; t < s->ntiles && fits; t++) fits = cnt[t] <= off[t + 1] - off[t];
+	if (!done) {
+		std::vector<int> cnt(s->ntiles, 0);
+		if (np > 0) {
+			int* d_cnt; ZDEV_CHECK(cudaMalloc(&d_cnt, (size_t) s->ntiles * sizeof(int)));
+			ZDEV_CHECK(cudaMemsetAsync(d_cnt, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+			ZDEV_LAUNCH(k_count_tiles, zdev_div_up(np, 256), 256, 0, src, np, s->TX, s->TY, s->ntx, d_cnt);
+			ZDEV_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+			cudaFree(d_cnt);
+		}
+		spec_layout(s, cnt, np);
+		ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
+		spec_append_dev(s, src, np, 0);
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	}
-	if (fits) ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
-	else spec_layout(s, cnt, np);
-	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
-	spec_append_dev(s, d_aos, np, 0);
-	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-	if (d_aos) cudaFree(d_aos);
+	if (d_stage) cudaFree(d_stage);
 	s->np_host = np;
 	s->ids_valid = s->track_ids;
 }
@@ -415,13 +454,15 @@ extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_
 		fprintf(stderr, "(*error*) zpic-b200: host particle buffer too small (%lld > %lld)\n", (long long) np, (long long) max_np);
 		exit(-1);
 	}
-	int64_t* d_prefix; part_aos* d_aos;
+	int64_t* d_prefix; part_aos* d_aos = nullptr;
 	ZDEV_CHECK(cudaMalloc(&d_prefix, (size_t) s->ntiles * sizeof(int64_t)));
-	ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part_aos)));
 	ZDEV_CHECK(cudaMemcpyAsync(d_prefix, prefix.data(), (size_t) s->ntiles * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
-	ZDEV_LAUNCH(k_gather_aos, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_prefix, d_aos,
+	// large mirrors are written by the gather kernel directly (mapped pinned host memory)
+	part_aos* dst = (part_aos*) map_host(part, (size_t) max_np * sizeof(part_aos));
+	if (!dst) { ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part_aos))); dst = d_aos; }
+	ZDEV_LAUNCH(k_gather_aos, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_prefix, dst,
 	            (s->track_ids && s->ids_valid) ? 1 : 0, s->TX, s->TY, s->ntx);
-	ZDEV_CHECK(cudaMemcpyAsync(part, d_aos, (size_t) np * sizeof(part_aos), cudaMemcpyDeviceToHost, zdev_strm));
+	if (d_aos) ZDEV_CHECK(cudaMemcpyAsync(part, d_aos, (size_t) np * sizeof(part_aos), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_prefix); cudaFree(d_aos);
 	return np;

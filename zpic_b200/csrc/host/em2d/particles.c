@@ -38,6 +38,7 @@ static void grow( t_part** buf, int* np_max, int size )
 
 void spec_grow_buffer( t_species* spec, const int size )
 {
+	if (size > spec->np_max && spec->part && zdev_ready()) zdev_host_forget(spec->part);   /* realloc may move it */
 	grow(&spec->part, &spec->np_max, size);
 }
 
@@ -302,6 +303,7 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
 void spec_delete( t_species* spec )
 {
 	zb_spec_drop(spec);
+	if (spec->part && zdev_ready()) zdev_host_forget(spec->part);
 	free(spec->part);
 	spec->part = NULL;
 	spec->np = -1;
