@@ -1,30 +1,36 @@
 // zpic-b200 :: em2d particle species on the device.
 //
 // Data layout in HBM.  The grid is cut into tiles of TX x TY cells; every tile owns a
-// fixed-capacity segment [tile_off[t], tile_off[t+1]) of
-//     rec[]  24-byte records {x, y, ux, uy, uz, cell}, cell = lx | ly<<16 (tile local),
-//            moved with three 64-bit accesses off one address register;
+// fixed-capacity segment [tile_off[t], tile_off[t+1]) of slots (a multiple of 32) in
+//     rec[]  chunks of 32 slots, each chunk six 128-byte rows  x[32] y[32] ux[32] uy[32] uz[32]
+//            cell[32]  (cell = lx | ly<<16, tile local): a warp reading 32 neighbouring slots
+//            touches one line per field, and two neighbouring slots of one field form an
+//            aligned 8-byte pair - the operand format of the packed fp32 pipe (FMUL2/FADD2/FFMA2);
 //     key[]  16-bit cell number lx + ly*TX (0xffff = empty slot), the only thing the
 //            index sort has to read;
 //     tag[]  optional injection index (parity runs),
 // of which the first tile_np[t] slots are in use.  There are two such buffers, A and B,
 // and every step streams A -> B.
 //
-// One CTA advances one tile (k_push2d):
+// One CTA advances one tile (k_push2d), every thread two particles at a time:
 //   phase A  an index-only counting sort of the tile's particles by cell, done in shared
 //            memory with native integer atomics: perm[] lists the live slots in cell
 //            order (empty slots drop out here, so compaction is free);
-//   phase B  warps walk perm[] in order with no block barriers: gather the particle from
-//            A, interpolate E/B from the shared-memory field tile, Boris push, move.
-//            Because the lanes of a warp now sit in the same one or two cells, the eight
-//            current contributions of the (non-crossing) particles are combined with a
-//            segmented warp scan and only the last lane of each run issues the 8 L2
-//            reductions.  The few particles that cross a cell face go to a warp-private
-//            queue and are split/deposited 32 at a time, so the rare path costs no
-//            divergence.  Survivors are written to B at their sorted position
-//            (coalesced); particles that left the tile go to a global migrants list and
-//            leave an empty slot behind.
-// k_migrate2d then appends the migrants to their destination tiles in B.
+//   phase B  each warp walks a contiguous range of perm[], 64 particles per iteration, lane l
+//            owning the sorted neighbours 2l and 2l+1.  The two particles travel through the
+//            Boris push as the two halves of packed fp32 registers: one FMUL2/FADD2/FFMA2 per
+//            operation of the reference's expression tree, each half rounded exactly like the
+//            scalar operation (no contraction).  E/B come from a shared-memory tile that stores
+//            the four corners of every cell as one float4 per component (6 LDS.128 per particle).
+//            Current: the lanes of a warp sit in one or two cells, so the eight contributions
+//            are accumulated per lane across iterations and reduced (transposed butterfly, 9
+//            shuffles) only when the warp moves on to the next cell.  Particles that cross a cell
+//            face (~9 %) go to a warp-private queue and are split/deposited 32 at a time.
+//            Survivors are written to B at their sorted position (coalesced 8-byte pairs);
+//            particles that left the tile go to the tile's migrants segment (unwrapped global
+//            cell indices) and leave an empty slot behind.
+// k_migrate2d then applies the boundary conditions to the migrants and appends them to their
+// destination tiles in B (or to the slab export lists).
 // Per step a particle is read once and written once (2 x 26 B; 56 B with the reference's
 // 28-byte record), plus the few percent that migrate.
 //
@@ -33,6 +39,7 @@
 // rebuilt every step instead of every n_sort steps).
 #include "zdev_common.cuh"
 #include "pic2d_core.cuh"
+#include "pic2d_packed.cuh"
 #include <vector>
 #include <cstring>
 
@@ -46,36 +53,46 @@ int zdev_grid2d_ny(zdev_grid2d* g);
 // host AoS record (include/em2d/particles.h t_part)
 struct part_aos { int ix, iy; float x, y, ux, uy, uz; };
 
-// device particle record, 24 bytes, 8-byte aligned
+// one particle as a value (registers); in memory its six words live in a 32-slot chunk, see above
 struct rec24 { float x, y, ux, uy, uz; int cell; };
-static_assert(sizeof(rec24) == 24, "rec24 must be 24 bytes");
 #define KEY_EMPTY 0xffffu
+#define REC_CHUNK_WORDS 192          // 6 rows x 32 slots
 
 // buffer view handed to kernels by value
 struct soa2d {
-	rec24* rec;          // tile buffers: cell = lx | ly<<16; migrants list: cell = global ix
-	unsigned short* key; // tile buffers only
-	int *iy;             // migrants list only: global iy
+	float* rec;          // chunked records, cell = lx | ly<<16
+	unsigned short* key;
 	int *tag;            // null unless ids are tracked
 };
+// migrants: one fixed segment per tile, [tile_off[t]/div, tile_off[t+1]/div), of reference-format records
+// carrying UNWRAPPED global cell indices (boundary conditions are applied by k_migrate2d)
+struct mig2d {
+	part_aos* rec;
+	int* tag;            // null unless ids are tracked
+	int* np;             // entries written per tile this step
+	int div;
+};
 
-__device__ __forceinline__ rec24 rec_load(const rec24* p) {
-	const float2* q = reinterpret_cast<const float2*>(p);
-	float2 a = q[0], b = q[1], c = q[2];
-	rec24 r; r.x = a.x; r.y = a.y; r.ux = b.x; r.uy = b.y; r.uz = c.x; r.cell = __float_as_int(c.y);
+// word index of slot `slot` (field f is 32*f words further)
+__device__ __forceinline__ size_t rec_word(int64_t slot) {
+	return (size_t) (slot >> 5) * REC_CHUNK_WORDS + (size_t) (slot & 31);
+}
+__device__ __forceinline__ rec24 rec_load(const float* __restrict__ rec, int64_t slot) {
+	const float* q = rec + rec_word(slot);
+	rec24 r; r.x = q[0]; r.y = q[32]; r.ux = q[64]; r.uy = q[96]; r.uz = q[128]; r.cell = __float_as_int(q[160]);
 	return r;
 }
-__device__ __forceinline__ void rec_store(rec24* p, float x, float y, float ux, float uy, float uz, int cell) {
-	float2* q = reinterpret_cast<float2*>(p);
-	q[0] = make_float2(x, y); q[1] = make_float2(ux, uy); q[2] = make_float2(uz, __int_as_float(cell));
+__device__ __forceinline__ void rec_store(float* __restrict__ rec, int64_t slot, float x, float y, float ux, float uy, float uz, int cell) {
+	float* q = rec + rec_word(slot);
+	q[0] = x; q[32] = y; q[64] = ux; q[96] = uy; q[128] = uz; q[160] = __int_as_float(cell);
 }
 
 // control block in device memory, zeroed at the start of every advance
 struct ctl2d {
 	double energy;                   // sum of utsq/(gamma+1)
 	unsigned long long np;           // live particles after the step
-	unsigned int n_mig;              // entries in the migrants list
-	unsigned int flags;              // 1: tile capacity overflow, 2: migrants list overflow, 4: export list overflow
+	unsigned int pad0;
+	unsigned int flags;              // 1: tile capacity overflow, 2: a tile's migrants segment overflowed, 4: export list overflow
 	unsigned int n_exp[2];           // slab mode: particles handed to the left / right neighbour
 	unsigned int pad[2];
 };
@@ -91,8 +108,8 @@ struct zdev_spec2d {
 	int64_t* tile_off;               // device, ntiles+1
 	int* tile_np;                    // device, ntiles: slots in use in p
 	int* tile_np_q;                  // device, ntiles: slots in use in q
-	soa2d mig;                       // migrants list (global cell indices)
-	unsigned int mig_cap;
+	mig2d mig;                       // per-tile migrants segments
+	int64_t mig_cap;                 // total entries allocated in mig.rec
 	part_aos* stage; int64_t stage_cap;   // persistent staging for appended host particles
 	part_aos* exp_buf[2];            // slab mode: export lists (AoS, ix already in the neighbour's frame)
 	unsigned int exp_cap;
@@ -134,20 +151,22 @@ static const int PUSH_WARPS = PUSH_THREADS / 32;
 #ifndef PUSH_MIN_BLOCKS
 #define PUSH_MIN_BLOCKS 2           // CTAs per SM the register allocation is sized for
 #endif
-static const int XQ_CAP = 64;        // warp-private queue of cell-crossing particles
 
-static void soa_alloc(soa2d& a, int64_t n, int with_tag, int is_mig) {
-	size_t nn = (size_t) (n > 0 ? n : 1);
+static void soa_alloc(soa2d& a, int64_t n, int with_tag) {
+	size_t nn = (size_t) (n > 0 ? n : 32);           // n is a multiple of 32 (whole chunks)
 	memset(&a, 0, sizeof(a));
-	ZDEV_CHECK(cudaMalloc(&a.rec, nn * sizeof(rec24)));
-	if (is_mig) ZDEV_CHECK(cudaMalloc(&a.iy, nn * 4));
-	else ZDEV_CHECK(cudaMalloc(&a.key, nn * 2));
+	ZDEV_CHECK(cudaMalloc(&a.rec, nn * 24));
+	ZDEV_CHECK(cudaMalloc(&a.key, nn * 2));
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&a.tag, nn * 4));
 }
 static void soa_free(soa2d& a) {
-	cudaFree(a.rec); cudaFree(a.key); cudaFree(a.iy); cudaFree(a.tag);
+	cudaFree(a.rec); cudaFree(a.key); cudaFree(a.tag);
 	memset(&a, 0, sizeof(a));
 }
+// migrants segments: 1/div of every tile's capacity.  A window shift empties a whole column of
+// every tile (1/TX of its particles) on top of the ordinary leavers, hence div = 4 there.
+static void mig_alloc(zdev_spec2d* s, int div);
+static void mig_free(zdev_spec2d* s);
 
 // supported tile shapes (kernel template instantiations)
 static bool tile_supported(int tx, int ty) {
@@ -157,6 +176,14 @@ static bool tile_supported(int tx, int ty) {
 
 extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int track_ids) {
 	zdev_require_init();
+	{	// the packed-multiply addend (pic2d_packed.cuh)
+		static bool negzero_set = false;
+		if (!negzero_set) {
+			const float2 nz = make_float2(-0.0f, -0.0f);
+			ZDEV_CHECK(cudaMemcpyToSymbol(c_negzero2, &nz, sizeof nz));
+			negzero_set = true;
+		}
+	}
 	zdev_spec2d* s = new zdev_spec2d();
 	memset(s, 0, sizeof(*s));
 	s->nx = nx; s->ny = ny;
@@ -193,12 +220,27 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 	return s;
 }
 
+static void mig_free(zdev_spec2d* s) {
+	cudaFree(s->mig.rec); cudaFree(s->mig.tag); cudaFree(s->mig.np);
+	memset(&s->mig, 0, sizeof(s->mig)); s->mig_cap = 0;
+}
+static void mig_alloc(zdev_spec2d* s, int div) {
+	mig_free(s);
+	s->mig.div = div;
+	s->mig_cap = s->cap_total / div + 32;
+	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) s->mig_cap * sizeof(part_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig.tag, (size_t) s->mig_cap * 4));
+	ZDEV_CHECK(cudaMalloc(&s->mig.np, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMemsetAsync(s->mig.np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+}
+
 static void spec_free_particles(zdev_spec2d* s) {
 	for (int k = 0; k < 2; k++) { cudaFree(s->exp_buf[k]); s->exp_buf[k] = nullptr; }
 	cudaFree(s->stage); s->stage = nullptr; s->stage_cap = 0;
 	s->exp_cap = 0;
-	if (s->cap_total) { soa_free(s->p); soa_free(s->q); soa_free(s->mig); }
-	s->cap_total = 0; s->mig_cap = 0;
+	if (s->cap_total) { soa_free(s->p); soa_free(s->q); }
+	mig_free(s);
+	s->cap_total = 0;
 }
 
 extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
@@ -234,21 +276,18 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 		off[t + 1] = off[t] + cap;
 		if (cap > max_cap) max_cap = cap;
 	}
-	if (max_cap * 4 > 160 * 1024) {
+	if (max_cap > 0xfff0) {
 		fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed the shared-memory index "
 		        "buffer; use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) max_cap, s->TX, s->TY);
 		exit(-1);
 	}
 	int64_t total = off[s->ntiles];
 	spec_free_particles(s);
-	soa_alloc(s->p, total, s->track_ids, 0);
-	soa_alloc(s->q, total, s->track_ids, 0);
+	soa_alloc(s->p, total, s->track_ids);
+	soa_alloc(s->q, total, s->track_ids);
 	s->cap_total = total;
 	s->max_cap = (int) max_cap;
-	int64_t mc = total / 8 + 65536;
-	if (mc > 0x7fffffff) mc = 0x7fffffff;
-	s->mig_cap = (unsigned int) mc;
-	soa_alloc(s->mig, s->mig_cap, s->track_ids, 1);
+	mig_alloc(s, 8);
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t),
 	                           cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
@@ -274,7 +313,7 @@ __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int 
 	int64_t d = off[t] + slot;
 	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
 	const int lx = r.ix - tx * TX, ly = r.iy - ty * TY;
-	rec_store(p.rec + d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
+	rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
 	p.key[d] = (unsigned short) (lx + ly * TX);
 	if (p.tag) p.tag[d] = tag0 + (int) k;
 }
@@ -286,7 +325,8 @@ static void check_flags(zdev_spec2d* s, unsigned int flags) {
 		exit(-1);
 	}
 	if (flags & 2u) {
-		fprintf(stderr, "(*error*) zpic-b200: particle migration list overflow (capacity %u), aborting.\n", s->mig_cap);
+		fprintf(stderr, "(*error*) zpic-b200: a tile's migrants segment overflowed (1/%d of the tile capacity); "
+		        "raise ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->mig.div, s->slack);
 		exit(-1);
 	}
 	if (flags & 4u) {
@@ -418,7 +458,7 @@ __global__ void k_gather_aos(soa2d p, const int64_t* __restrict__ off, const int
 		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
 		wbase = __shfl_sync(0xffffffffu, wbase, 0);
 		if (live) {
-			rec24 v = rec_load(p.rec + b + k);
+			rec24 v = rec_load(p.rec, b + k);
 			part_aos r;
 			r.ix = x0 + (v.cell & 0xffff); r.iy = y0 + (v.cell >> 16);
 			r.x = v.x; r.y = v.y; r.ux = v.ux; r.uy = v.uy; r.uz = v.uz;
@@ -525,7 +565,7 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		float a, b, c; normal3(seed, gid0 + k, a, b, c);
 		int kx = k % ppcx, ky = k / ppcx;
 		int64_t d = base + k;
-		rec_store(p.rec + d, (float) (dpcx * (kx + 0.5)), (float) (dpcy * (ky + 0.5)),
+		rec_store(p.rec, d, (float) (dpcx * (kx + 0.5)), (float) (dpcy * (ky + 0.5)),
 		          uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz), lx | (ly << 16));
 		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = (int) (gid0 + k);
@@ -578,39 +618,118 @@ __device__ __forceinline__ void deposit_seg_global(f3* __restrict__ J, int nrow,
 	red_weights(J + (s.ix + 1) + (s.iy + 1) * nrow, nrow, w);
 }
 
-// one queued cell-crossing move (warp-private shared-memory queue)
-struct xq_entry { int ix, iy, dij; float x0, y0, dx, dy, qvz; };
+// one queued move (warp-private shared-memory queue): a particle that crosses a cell face, or the second
+// particle of a thread when it sits in another cell than the first (dij = centre: one segment)
+struct __align__(16) xq_entry { int ix, iy, dij; float x0, y0, dx, dy, qvz; };
 
 // split + deposit up to 32 queued moves, one per lane
-__device__ __forceinline__ void drain_crossers(const xq_entry* q, int n, int lane, f3* __restrict__ J, int nrow,
-                                               float qnx, float qny) {
+__device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, f3* __restrict__ J, int nrow,
+                                            float qnx, float qny) {
 	if (lane < n) {
 		xq_entry e = q[lane];
 		seg2d vp[3];
 		int vnp = split_trajectory(e.ix, e.iy, (e.dij & 3) - 1, ((e.dij >> 2) & 3) - 1, e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
 		deposit_seg_global(J, nrow, vp[0], qnx, qny);
-		deposit_seg_global(J, nrow, vp[1], qnx, qny);
+		if (vnp > 1) deposit_seg_global(J, nrow, vp[1], qnx, qny);
 		if (vnp > 2) deposit_seg_global(J, nrow, vp[2], qnx, qny);
 	}
 }
 
-// One CTA per tile.  Dynamic shared memory: perm[max_cap] ints.
-// (A variant specialised for the plain periodic case - no window, slab or tag logic - was measured
-// 6 % SLOWER than this generic kernel on B200: 3.87 vs 3.66 ms at 67 M particles; not kept.)
+// Sum acc[0..7] over the 32 lanes (transposed butterfly: 9 shuffles for the 8 sums), after which lane 4*k
+// holds the total of contribution k, and add the totals to cell `cell` (= lx + ly*TX) of the tile.
+template <int TX>
+__device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lane, f3* __restrict__ J0, int nrow) {
+	float v4[4], v2[2], v1;
+	const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+	#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		float send = b16 ? acc[q] : acc[q + 4], keep = b16 ? acc[q + 4] : acc[q];
+		v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+	}
+	#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		float send = b8 ? v4[q] : v4[q + 2], keep = b8 ? v4[q + 2] : v4[q];
+		v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	}
+	{
+		float send = b4 ? v2[0] : v2[1], keep = b4 ? v2[1] : v2[0];
+		v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+	}
+	v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+	v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+	if ((lane & 3) == 0) {
+		const int k = lane >> 2;                       // contribution index, see seg_weights()
+		const int comp = (k < 2) ? 0 : ((k < 4) ? 1 : 2);
+		const int right = (k == 3) | (k == 5) | (k == 7);
+		const int up = (k == 1) | (k == 6) | (k == 7);
+		const int lx = cell & (TX - 1), ly = cell / TX;
+		float* a = reinterpret_cast<float*>(J0 + lx + right + (ly + up) * nrow) + comp;
+		atomicAdd(a, v1);
+	}
+}
+
+// the six words of the sorted neighbours (pa, pa+1), as loaded from their source slots
+struct pair_rec { f2 x, y, ux, uy, uz; int ca, cb, ta, tb; };
+
+#ifndef XQ_CAP_N
+#define XQ_CAP_N 96                  // 31 left over + 64 new entries at most
+#endif
+static const int XQ_CAP = XQ_CAP_N;
+
+// dynamic shared memory of k_push2d: [corner tile][queues | keys][perm | raw planes]
+static size_t push_smem_mid(int max_cap) {
+	size_t xq = (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	return xq > keys ? xq : keys;
+}
+static size_t push_smem_bytes(int TX, int TY, int max_cap) {
+	size_t plane = (size_t) (TX + 2) * (TY + 2);
+	size_t perm = (size_t) max_cap * 2, raw = 6 * plane * 4;
+	size_t tail = perm > raw ? perm : raw;
+	return 6 * plane * 16 + push_smem_mid(max_cap) + ((tail + 15) & ~(size_t) 15);
+}
+
+// --- TMA bulk copy (global -> shared, completion on an mbarrier): the tile's key segment is fetched by
+//     one thread while the CTA stages the fields
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
+	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	             "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+
+// One CTA per tile.  Dynamic shared memory: corner tile (float4 x 6 planes); the warps' queues (the tile's
+// keys live in the same bytes during the sort); perm[max_cap] (16-bit slot indices; the raw field planes
+// are staged in the same bytes before the sort).
 template <int TX, int TY>
 __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
-         int* __restrict__ tile_np_out, soa2d mig, unsigned int mig_cap,
+         int* __restrict__ tile_np_out, mig2d mig,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
-         push_geom g, zdev_push2d_params prm) {
+         push_geom g, zdev_push2d_params prm, unsigned smem_mid) {
 	constexpr int SROW = TX + 2;
 	constexpr int PLANE = SROW * (TY + 2);
 	constexpr int NC = TX * TY;
-	extern __shared__ int s_perm[];
-	__shared__ float s_fld[6 * PLANE];
+	static_assert((TX & (TX - 1)) == 0, "TX must be a power of two");
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	float4* const s_f4 = reinterpret_cast<float4*>(s_dyn);
+	xq_entry* const s_xq = reinterpret_cast<xq_entry*>(s_dyn + 6 * PLANE * 16);
+	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn + 6 * PLANE * 16);
+	unsigned char* const s_tail = s_dyn + 6 * PLANE * 16 + smem_mid;
+	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_tail);
+	float* const s_raw = reinterpret_cast<float*>(s_tail);
 	__shared__ int s_cnt[NC];
 	__shared__ int s_wsum[PUSH_WARPS];
-	__shared__ xq_entry s_xq[PUSH_WARPS][XQ_CAP];
+	__shared__ int s_nmig, s_done;
+	__shared__ __align__(8) unsigned long long s_bar;
 
 	const int t = blockIdx.x;
 	const int tx = t % g.ntx, ty = t / g.ntx;
@@ -620,22 +739,53 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
 
-	// ---- stage the field neighbourhood as planes: cells [x0-1, x0+cx] x [y0-1, y0+cy]
+	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
+	if (threadIdx.x == 0) {
+		s_nmig = 0; s_done = 0;
+		mbar_init(&s_bar, 1);
+		if (n > 0) bulk_load(s_dyn + 6 * PLANE * 16, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
+	}
+	// ---- stage the field neighbourhood: cells [x0-1, x0+cx] x [y0-1, y0+cy] as raw planes ...
 	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += PUSH_THREADS) {
 		int r = k / (cx + 2), c = k - r * (cx + 2);
 		int gi = (x0 + c) + (y0 + r) * g.nrow;        // buffer index of cell (x0-1+c, y0-1+r)
 		f3 e = E[gi], b = B[gi];
 		int o = c + r * SROW;
-		s_fld[o] = e.x; s_fld[o + PLANE] = e.y; s_fld[o + 2 * PLANE] = e.z;
-		s_fld[o + 3 * PLANE] = b.x; s_fld[o + 4 * PLANE] = b.y; s_fld[o + 5 * PLANE] = b.z;
+		s_raw[o] = e.x; s_raw[o + PLANE] = e.y; s_raw[o + 2 * PLANE] = e.z;
+		s_raw[o + 3 * PLANE] = b.x; s_raw[o + 4 * PLANE] = b.y; s_raw[o + 5 * PLANE] = b.z;
 	}
 	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
 	__syncthreads();
+	// ... then as the four corners of every cell (entries of the last row / column are never read)
+	for (int k = threadIdx.x; k < 6 * PLANE; k += PUSH_THREADS) {
+		const int pl = k / PLANE, o = k - pl * PLANE;
+		const int r = o / SROW, c = o - r * SROW;
+		const int o1 = (c + 1 < SROW) ? o + 1 : o, o2 = (r + 1 < TY + 2) ? o + SROW : o;
+		const int o3 = o2 + (o1 - o);
+		const float* P = s_raw + pl * PLANE;
+		s_f4[k] = make_float4(P[o], P[o2], P[o1], P[o3]);
+	}
+	if (n > 0) mbar_wait(&s_bar, 0);
+	__syncthreads();                                    // s_raw is dead: its bytes become perm[]
 
-	// ---- phase A: counting sort of slot indices by cell
-	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
-		unsigned c = A.key[base + i];
-		if (c != KEY_EMPTY) atomicAdd(&s_cnt[c], 1);
+	// ---- phase A: counting sort of slot indices by cell.  The keys arrive almost sorted (B was written in
+	//      cell order by the previous step), so 32 CONSECUTIVE keys would hammer one counter (shared-memory
+	//      atomics on one address serialise).  Instead every thread walks its own stretch of consecutive
+	//      keys: at any moment the lanes of a warp are a stretch apart, i.e. in different cells, and the
+	//      atomics spread over the counters.  Stretches are an odd number of 32-bit words long, so the
+	//      lanes also read distinct banks.  Plain uniform loops: no votes, nothing divergent.
+	const int wpt = (((n + PUSH_THREADS - 1) / PUSH_THREADS + 1) >> 1) | 1;     // words (key pairs) per thread
+	const int k0 = threadIdx.x * wpt * 2;
+	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + threadIdx.x * wpt;
+	#pragma unroll 4
+	for (int j = 0; j < wpt; j++) {
+		const int i = k0 + 2 * j;
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
+			if (c0 != KEY_EMPTY) atomicAdd(&s_cnt[c0], 1);
+			if (c1 != KEY_EMPTY) atomicAdd(&s_cnt[c1], 1);
+		}
 	}
 	__syncthreads();
 	int nlive;
@@ -652,221 +802,272 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		nlive = tot;
 		__syncthreads();
 	}
-	for (int i = threadIdx.x; i < n; i += PUSH_THREADS) {
-		unsigned c = A.key[base + i];
-		if (c != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c], 1)] = i;
+	#pragma unroll 4
+	for (int j = 0; j < wpt; j++) {
+		const int i = k0 + 2 * j;
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
+			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c0], 1)] = (unsigned short) i;
+			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c1], 1)] = (unsigned short) (i + 1);
+		}
 	}
-	__syncthreads();
+	__syncthreads();                                    // the keys are dead: their bytes become the queues
 
-	// ---- phase B: warps stream the sorted particles, no block barriers from here on
-	xq_entry* xq = s_xq[warp];
+	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
+	//      owns the particles l and l+32 of the iteration's block); no block barriers from here on
+	xq_entry* const xq = s_xq + warp * XQ_CAP;
+	const unsigned lt = (1u << lane) - 1u;
 	int nxq = 0;
-	float energy = 0.0f;      // per-thread partial in float (<= 64 terms), widened once per tile
+	float energy = 0.0f;      // per-thread partial in float (a few dozen terms), widened once per tile
 	f3* const J0 = J + (x0 + 1) + (y0 + 1) * g.nrow;          // cell (x0,y0)
+	const float* const Arec = A.rec + (size_t) (base >> 5) * REC_CHUNK_WORDS;
+	float* const Brec = Bo.rec + (size_t) (base >> 5) * REC_CHUNK_WORDS;
+	const int chunk = ((nlive + PUSH_WARPS * 64 - 1) / (PUSH_WARPS * 64)) * 64;
+	const int pbeg = warp * chunk, pend = min(pbeg + chunk, nlive);
+	const int mig_cap = (int) ((tile_off[t + 1] - base) / mig.div);
+	const int64_t mig_base = base / mig.div;
 
-	// software pipeline: the record of the next iteration is requested before the current one
-	// is processed, so its HBM/L2 latency hides behind ~600 instructions of arithmetic
-	rec24 nv; int ntag = 0;
-	const int first = (nlive > 0) ? s_perm[0] : 0;
-	{
-		const int pn = warp * 32 + lane;
-		const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
-		nv = rec_load(A.rec + k);
-		if (A.tag) ntag = A.tag[k];
-	}
+	// per-lane partial sums of the 8 contributions to cell `cur` (warp-uniform; -1: none)
+	float acc[8];
+	#pragma unroll
+	for (int q = 0; q < 8; q++) acc[q] = 0.0f;
+	int cur = -1;
 
-	for (int p0 = warp * 32; p0 < nlive; p0 += PUSH_THREADS) {
-		const int p = p0 + lane;
-		const bool active = p < nlive;
-		const rec24 v = nv;
-		const int tag = ntag;
+	// Current of 32 consecutive sorted particles (one per lane, zero for the lanes that deposit through the
+	// queue): accumulate per lane while the warp stays in one cell, reduce when it moves on.
+	auto deposit32 = [&](int key, float (&w)[8], bool act, int lx, int ly) {
+		const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+		const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) ? (key != cur) : (key != prev));
+		if (heads == 0u) {
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] += w[q];
+			return;
+		}
+		const int b = __ffs(heads) - 1;                // lanes below b continue cell `cur`
+		const bool lo = lane < b;
+		if (cur >= 0) {
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] += lo ? w[q] : 0.0f;
+			flush_cell<TX>(acc, cur, lane, J0, g.nrow);
+		}
+		if ((heads & (heads - 1u)) == 0u) {
+			// one new cell starts at lane b and runs to the end of the warp: it becomes `cur`
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] = lo ? 0.0f : w[q];
+			cur = __shfl_sync(0xffffffffu, key, 31);
+			if (cur >= NC) cur = -1;                   // the range ended inside these 32
+		} else {
+			// several cells start here: segmented inclusive scan, the last lane of each run holds its totals
+			#pragma unroll
+			for (int q = 0; q < 8; q++) w[q] = lo ? 0.0f : w[q];
+			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const bool take = (lane - d) >= start;
+				#pragma unroll
+				for (int q = 0; q < 8; q++) {
+					float u = __shfl_up_sync(0xffffffffu, w[q], d);
+					if (take) w[q] += u;
+				}
+			}
+			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+			if (tail && act && !lo) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] = 0.0f;
+			cur = -1;
+		}
+	};
+
+	// source slots of the particles (pa, pa+32); lanes past the end of the range read the range's first particle
+	auto load_pair = [&](int pa, pair_rec& r) {
+		const int ia = s_perm[pa < pend ? pa : pbeg], ib = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const float* qa = Arec + (ia >> 5) * REC_CHUNK_WORDS + (ia & 31);
+		const float* qb = Arec + (ib >> 5) * REC_CHUNK_WORDS + (ib & 31);
+		r.x = mk2(qa[0], qb[0]); r.y = mk2(qa[32], qb[32]);
+		r.ux = mk2(qa[64], qb[64]); r.uy = mk2(qa[96], qb[96]); r.uz = mk2(qa[128], qb[128]);
+		r.ca = __float_as_int(qa[160]); r.cb = __float_as_int(qb[160]);
+		r.ta = r.tb = 0;
+		if (A.tag) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
+	};
+
+	pair_rec nv;
+	if (pbeg < pend) load_pair(pbeg + lane, nv);
+
+	for (int p0 = pbeg; p0 < pend; p0 += 64) {
+		const int pa = p0 + lane, pb = pa + 32;
+		const bool actA = pa < pend, actB = pb < pend;
+		const pair_rec v = nv;
+		if (p0 + 64 < pend) load_pair(pa + 64, nv);        // software pipeline: next iteration's records
+
+		const int lxa = v.ca & 0xffff, lya = v.ca >> 16, lxb = v.cb & 0xffff, lyb = v.cb >> 16;
+		f2 x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
+		f2 dx, dy, qvz;
 		{
-			const int pn = p + PUSH_THREADS;
-			const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
-			nv = rec_load(A.rec + k);
-			if (A.tag) ntag = A.tag[k];
+			f2 Ex, Ey, Ez, Bx, By, Bz;
+			interp_EB_f4<SROW, PLANE>(s_f4, lxa, lya, x.x, y.x, Ex.x, Ey.x, Ez.x, Bx.x, By.x, Bz.x);
+			interp_EB_f4<SROW, PLANE>(s_f4, lxb, lyb, x.y, y.y, Ex.y, Ey.y, Ez.y, Bx.y, By.y, Bz.y);
+			const f2 en = boris2(Ex, Ey, Ez, Bx, By, Bz, prm.tem, ux, uy, uz);
+			energy += (actA ? en.x : 0.0f) + (actB ? en.y : 0.0f);
+		}
+		{
+			const f2 usq = add2(add2(add2(bc2(1.0f), mul2(ux, ux)), mul2(uy, uy)), mul2(uz, uz));
+			const f2 rg = div_exact2(bc2(1.0f), sqrt_exact2(usq));
+			dx = mul2(mul2(rg, prm.dt_dx), ux);
+			dy = mul2(mul2(rg, prm.dt_dy), uy);
+			qvz = mul2(mul2(uz, prm.q), rg);
+		}
+		const f2 x1 = add2(x, dx), y1 = add2(y, dy);
+		const int dia = ltrim(x1.x), dib = ltrim(x1.y), dja = ltrim(y1.x), djb = ltrim(y1.y);
+
+		// which particles deposit here, which through the queue
+		const bool xa = actA && ((dia | dja) != 0);
+		const bool xb = actB && ((dib | djb) != 0);
+		{
+			f2 w2[8];
+			const f2 kz = mk2((actA && !xa) ? 0.5f : 0.0f, (actB && !xb) ? 0.5f : 0.0f);
+			seg_weights2(x, y, x1, y1, dx, dy, qvz, mul2(kz, prm.qnx), mul2(kz, prm.qny), kz, w2);
+			float w[8];
+			#pragma unroll
+			for (int q = 0; q < 8; q++) w[q] = w2[q].x;
+			deposit32(actA ? lxa + lya * TX : 0x7fffffff, w, actA, lxa, lya);
+			#pragma unroll
+			for (int q = 0; q < 8; q++) w[q] = w2[q].y;
+			deposit32(actB ? lxb + lyb * TX : 0x7fffffff, w, actB, lxb, lyb);
 		}
 
-		// Lanes past the end of the tile (last iteration only) run the arithmetic on a copy of
-		// the tile's first particle and are masked out of every side effect below.
-		float w[8];
-		const int lx = v.cell & 0xffff, ly = v.cell >> 16;
-		const int key = active ? lx + ly * TX : 0x7fffffff;
-		float x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
-		int fate, ncell = -1, gix = 0, giy = 0;
-		bool crosses;
-		xq_entry xe;
+		// --- queue of the cell crossers; drain 32 at a time
 		{
-			f3 Ep, Bp;
-			interp_EB_planes<SROW, PLANE>(s_fld, lx, ly, x, y, Ep, Bp);
-			const float en = boris(Ep, Bp, prm.tem, ux, uy, uz);
-			energy += active ? en : 0.0f;
-
-			float rg = div_exact(1.0f, sqrt_exact(1.0f + ux * ux + uy * uy + uz * uz));
-			float dx = prm.dt_dx * rg * ux;
-			float dy = prm.dt_dy * rg * uy;
-			float x1 = x + dx, y1 = y + dy;
-			int di = ltrim(x1), dj = ltrim(y1);
-			x1 -= di; y1 -= dj;
-			float qvz = prm.q * uz * rg;
-
-			crosses = active && ((di | dj) != 0);
-			xe.ix = x0 + lx; xe.iy = y0 + ly; xe.dij = (di + 1) | ((dj + 1) << 2);
-			xe.x0 = x; xe.y0 = y; xe.dx = dx; xe.dy = dy; xe.qvz = qvz;
-			{
-				seg2d s0;
-				s0.x0 = x; s0.y0 = y; s0.dx = dx; s0.dy = dy; s0.x1 = x + dx; s0.y1 = y + dy;
-				s0.qvz = qvz * 0.5f; s0.ix = 0; s0.iy = 0;
-				seg_weights(s0, prm.qnx, prm.qny, w);
-				const bool zero = crosses || !active;      // crossers deposit through the queue
-				#pragma unroll
-				for (int q = 0; q < 8; q++) w[q] = zero ? 0.0f : w[q];
-			}
-
-			x = x1; y = y1;
-			int ix = x0 + lx + di - prm.shift_window, iy = y0 + ly + dj;
-			// boundaries (reference particles.c:1237-1259)
-			// an x edge is either a slab boundary (particle handed to the neighbour rank through the
-			// migrants list, keeping its out-of-range index), absorbing (moving window) or periodic
-			fate = active ? 1 : 0;
-			if (ix < 0) {
-				if (!prm.slab_left) { if (prm.moving_window) fate = 0; else ix += g.nx; }
-			} else if (ix >= g.nx) {
-				if (!prm.slab_right) { if (prm.moving_window) fate = 0; else ix -= g.nx; }
-			}
-			iy += ((iy < 0) ? g.ny : 0) - ((iy >= g.ny) ? g.ny : 0);
-			const int nlx = ix - x0, nly = iy - y0;
-			if (fate) {
-				if (nlx < 0 || nlx >= cx || nly < 0 || nly >= cy) { fate = 2; gix = ix; giy = iy; }
-				else ncell = nlx | (nly << 16);
+			const unsigned ma = __ballot_sync(0xffffffffu, xa), mb = __ballot_sync(0xffffffffu, xb);
+			if (ma | mb) {
+				if (xa) {
+					xq_entry e;
+					e.ix = x0 + lxa; e.iy = y0 + lya; e.dij = (dia + 1) | ((dja + 1) << 2);
+					e.x0 = x.x; e.y0 = y.x; e.dx = dx.x; e.dy = dy.x; e.qvz = qvz.x;
+					xq[nxq + __popc(ma & lt)] = e;
+				}
+				nxq += __popc(ma);
+				if (xb) {
+					xq_entry e;
+					e.ix = x0 + lxb; e.iy = y0 + lyb; e.dij = (dib + 1) | ((djb + 1) << 2);
+					e.x0 = x.y; e.y0 = y.y; e.dx = dx.y; e.dy = dy.y; e.qvz = qvz.y;
+					xq[nxq + __popc(mb & lt)] = e;
+				}
+				nxq += __popc(mb);
+				__syncwarp();
+				while (nxq >= 32) {
+					drain_queue(xq + nxq - 32, 32, lane, J, g.nrow, prm.qnx, prm.qny);
+					nxq -= 32;
+				}
+				__syncwarp();
 			}
 		}
 
-		// --- current of the non-crossing particles, combined per run of equal cell
+		// --- new positions; survivors go to their sorted slot in B, leavers to the tile's migrants segment
+		const f2 xn = sub2(x1, mk2((float) dia, (float) dib)), yn = sub2(y1, mk2((float) dja, (float) djb));
+		const int nlxa = lxa + dia - prm.shift_window, nlya = lya + dja;
+		const int nlxb = lxb + dib - prm.shift_window, nlyb = lyb + djb;
+		const bool sta = actA && (unsigned) nlxa < (unsigned) cx && (unsigned) nlya < (unsigned) cy;
+		const bool stb = actB && (unsigned) nlxb < (unsigned) cx && (unsigned) nlyb < (unsigned) cy;
+		if (actA) {
+			float* qd = Brec + (pa >> 5) * REC_CHUNK_WORDS + (pa & 31);
+			qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
+			qd[160] = __int_as_float(nlxa | (nlya << 16));
+			Bo.key[base + pa] = sta ? (unsigned short) (nlxa + nlya * TX) : (unsigned short) KEY_EMPTY;
+			if (Bo.tag) Bo.tag[base + pa] = v.ta;
+		}
+		if (actB) {
+			float* qd = Brec + (pb >> 5) * REC_CHUNK_WORDS + (pb & 31);
+			qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
+			qd[160] = __int_as_float(nlxb | (nlyb << 16));
+			Bo.key[base + pb] = stb ? (unsigned short) (nlxb + nlyb * TX) : (unsigned short) KEY_EMPTY;
+			if (Bo.tag) Bo.tag[base + pb] = v.tb;
+		}
 		{
-			const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-			const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
-			if (heads == 1u) {
-				// all 32 lanes in one cell: transposed butterfly, 9 shuffles for the 8 sums, after
-				// which lane 4*k holds the total of contribution k and issues its single reduction
-				float v4[4], v2[2], v1;
-				const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
-				#pragma unroll
-				for (int q = 0; q < 4; q++) {
-					float send = b16 ? w[q] : w[q + 4], keep = b16 ? w[q + 4] : w[q];
-					v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-				}
-				#pragma unroll
-				for (int q = 0; q < 2; q++) {
-					float send = b8 ? v4[q] : v4[q + 2], keep = b8 ? v4[q + 2] : v4[q];
-					v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-				}
-				{
-					float send = b4 ? v2[0] : v2[1], keep = b4 ? v2[1] : v2[0];
-					v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-				}
-				v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-				v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-				if ((lane & 3) == 0) {
-					const int k = lane >> 2;                       // contribution index, see seg_weights()
-					const int comp = (k < 2) ? 0 : ((k < 4) ? 1 : 2);
-					const int right = (k == 3) | (k == 5) | (k == 7);
-					const int up = (k == 1) | (k == 6) | (k == 7);
-					float* a = reinterpret_cast<float*>(J0 + lx + right + (ly + up) * g.nrow) + comp;
-					atomicAdd(a, v1);
-				}
-			} else {
-				// general case: segmented inclusive scan, the last lane of each run holds its totals
-				const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
-				#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const bool take = (lane - d) >= start;
-					#pragma unroll
-					for (int q = 0; q < 8; q++) {
-						float u = __shfl_up_sync(0xffffffffu, w[q], d);
-						if (take) w[q] += u;
+			const bool la = actA && !sta, lb = actB && !stb;
+			const unsigned ma = __ballot_sync(0xffffffffu, la), mb = __ballot_sync(0xffffffffu, lb);
+			if (ma | mb) {
+				int slot = 0;
+				if (lane == 0) slot = atomicAdd(&s_nmig, __popc(ma) + __popc(mb));
+				slot = __shfl_sync(0xffffffffu, slot, 0);
+				if (la) {
+					const int d = slot + __popc(ma & lt);
+					if (d < mig_cap) {
+						part_aos r; r.ix = x0 + nlxa; r.iy = y0 + nlya;
+						r.x = xn.x; r.y = yn.x; r.ux = ux.x; r.uy = uy.x; r.uz = uz.x;
+						mig.rec[mig_base + d] = r;
+						if (mig.tag) mig.tag[mig_base + d] = v.ta;
 					}
 				}
-				const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-				if (tail && active) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
-			}
-		}
-
-		// --- cell crossers: queue, drain 32 at a time
-		{
-			const unsigned xm = __ballot_sync(0xffffffffu, crosses);
-			if (xm) {
-				if (crosses) xq[nxq + __popc(xm & ((1u << lane) - 1))] = xe;
-				nxq += __popc(xm);
-				__syncwarp();
-				if (nxq >= 32) {
-					drain_crossers(xq + nxq - 32, 32, lane, J, g.nrow, prm.qnx, prm.qny);
-					nxq -= 32;
-					__syncwarp();
+				if (lb) {
+					const int d = slot + __popc(ma) + __popc(mb & lt);
+					if (d < mig_cap) {
+						part_aos r; r.ix = x0 + nlxb; r.iy = y0 + nlyb;
+						r.x = xn.y; r.y = yn.y; r.ux = ux.y; r.uy = uy.y; r.uz = uz.y;
+						mig.rec[mig_base + d] = r;
+						if (mig.tag) mig.tag[mig_base + d] = v.tb;
+					}
 				}
 			}
 		}
-
-		// --- write the survivors to their sorted slot in B, route the leavers
-		if (active) {
-			const int64_t d = base + p;
-			Bo.key[d] = (fate == 1) ? (unsigned short) ((ncell & 0xffff) + (ncell >> 16) * TX) : (unsigned short) KEY_EMPTY;
-			if (fate == 1) {
-				rec_store(Bo.rec + d, x, y, ux, uy, uz, ncell);
-				if (Bo.tag) Bo.tag[d] = tag;
-			}
-		}
-		const unsigned mig_m = __ballot_sync(0xffffffffu, fate == 2);
-		if (mig_m) {
-			unsigned int mbase = 0;
-			if (lane == 0) mbase = atomicAdd(&ctl->n_mig, (unsigned int) __popc(mig_m));
-			mbase = __shfl_sync(0xffffffffu, mbase, 0);
-			if (fate == 2) {
-				unsigned int d = mbase + __popc(mig_m & ((1u << lane) - 1));
-				if (d < mig_cap) {
-					rec_store(mig.rec + d, x, y, ux, uy, uz, gix);
-					mig.iy[d] = giy;
-					if (mig.tag) mig.tag[d] = tag;
-				} else atomicOr(&ctl->flags, 2u);
-			}
-		}
 	}
-	if (nxq) drain_crossers(xq, nxq, lane, J, g.nrow, prm.qnx, prm.qny);
+	if (cur >= 0) flush_cell<TX>(acc, cur, lane, J0, g.nrow);
+	if (nxq) drain_queue(xq, nxq, lane, J, g.nrow, prm.qnx, prm.qny);
 
-	// ---- tile epilogue (no block barrier: warps retire independently): slots in use, energy
+	// ---- tile epilogue (no block barrier: warps retire independently): slots in use, energy, migrants
 	double e = (double) energy;
 	for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-	if (lane == 0 && nlive > 0) atomicAdd(&ctl->energy, e);
-	if (threadIdx.x == 0) tile_np_out[t] = nlive;
+	if (lane == 0) {
+		if (nlive > 0) atomicAdd(&ctl->energy, e);
+		__threadfence_block();
+		if (atomicAdd(&s_done, 1) == PUSH_WARPS - 1) {
+			// last warp out: every reservation in s_nmig has been made
+			const int nm = atomicAdd(&s_nmig, 0);
+			if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
+			mig.np[t] = min(nm, mig_cap);
+			tile_np_out[t] = nlive;
+		}
+	}
 }
 
-// append the migrants to their destination tiles and count the population
-__global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, soa2d mig,
-                            unsigned int mig_cap, ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int nx,
+// Boundary conditions for the particles that left their tile (reference particles.c:1237-1259: periodic y
+// always; x periodic, absorbing under a moving window, or handed to the neighbour slab), then append them
+// to their destination tiles.  One warp per tile segment.
+__global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig2d mig,
+                            ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int ntiles, int nx, int ny,
+                            int moving_window, int slab_left, int slab_right,
                             part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap) {
-	unsigned int n = ctl->n_mig;
-	if (n > mig_cap) n = mig_cap;
-	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-		rec24 v = rec_load(mig.rec + k);
-		int ix = v.cell, iy = mig.iy[k];
-		if (ix < 0 || ix >= nx) {
-			// leaves the slab: export in the neighbour's frame (all slabs have the same width)
-			const int side = ix >= nx;
-			unsigned int slot = atomicAdd(&ctl->n_exp[side], 1u);
-			if (slot >= exp_cap) { atomicOr(&ctl->flags, 4u); continue; }
-			part_aos r; r.ix = side ? ix - nx : ix + nx; r.iy = iy;
-			r.x = v.x; r.y = v.y; r.ux = v.ux; r.uy = v.uy; r.uz = v.uz;
-			(side ? exp_r : exp_l)[slot] = r;
-			continue;
+	const int lane = threadIdx.x & 31;
+	const int nwarp = (gridDim.x * blockDim.x) >> 5;
+	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
+		const int n = mig.np[ts];
+		const int64_t mb = tile_off[ts] / mig.div;
+		for (int k = lane; k < n; k += 32) {
+			part_aos r = mig.rec[mb + k];
+			int ix = r.ix, iy = r.iy;
+			iy += ((iy < 0) ? ny : 0) - ((iy >= ny) ? ny : 0);
+			if (ix < 0 || ix >= nx) {
+				const int side = ix >= nx;
+				if (side ? slab_right : slab_left) {
+					// leaves the slab: export in the neighbour's frame (all slabs have the same width)
+					unsigned int slot = atomicAdd(&ctl->n_exp[side], 1u);
+					if (slot >= exp_cap) { atomicOr(&ctl->flags, 4u); continue; }
+					r.ix = side ? ix - nx : ix + nx; r.iy = iy;
+					(side ? exp_r : exp_l)[slot] = r;
+					continue;
+				}
+				if (moving_window) continue;                 // absorbed
+				ix += side ? -nx : nx;
+			}
+			int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
+			int slot = atomicAdd(&tile_np[t], 1);
+			int64_t d = tile_off[t] + slot;
+			if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
+			const int lx = ix - tx * TX, ly = iy - ty * TY;
+			rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
+			p.key[d] = (unsigned short) (lx + ly * TX);
+			if (p.tag) p.tag[d] = mig.tag[mb + k];
 		}
-		int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
-		int slot = atomicAdd(&tile_np[t], 1);
-		int64_t d = tile_off[t] + slot;
-		if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
-		const int lx = ix - tx * TX, ly = iy - ty * TY;
-		rec_store(p.rec + d, v.x, v.y, v.ux, v.uy, v.uz, lx | (ly << 16));
-		p.key[d] = (unsigned short) (lx + ly * TX);
-		if (p.tag) p.tag[d] = mig.tag[k];
 	}
 }
 
@@ -884,7 +1085,7 @@ __global__ void k_count_total(soa2d p, const int64_t* __restrict__ off, const in
 
 template <int TX, int TY>
 static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const push_geom& g, const zdev_push2d_params& prm) {
-	size_t smem = (size_t) s->max_cap * sizeof(int);
+	size_t smem = push_smem_bytes(TX, TY, s->max_cap);
 	static size_t configured = 0;
 	if (smem > configured) {
 		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -901,7 +1102,7 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
 	ZDEV_LAUNCH((k_push2d<TX, TY>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-	            s->mig, s->mig_cap, s->ctl, E, B, J, g, prm);
+	            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
 
@@ -912,6 +1113,8 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	}
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
+	// a window shift sends a whole column of every tile through the migrants segments
+	if (prm->moving_window && s->mig.div > 4) mig_alloc(s, 4);
 	push_geom g = { s->nx, s->ny, s->nx + 3, s->ntx };
 	const f3* E = zdev_grid2d_Epart(grid); const f3* B = zdev_grid2d_Bpart(grid); f3* J = zdev_grid2d_J(gcur);
 	if      (s->TX == 16 && s->TY == 16) launch_push<16, 16>(s, E, B, J, g, *prm);
@@ -928,8 +1131,9 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 		s->exp_cap = (unsigned int) cap;
 		for (int k = 0; k < 2; k++) ZDEV_CHECK(cudaMalloc(&s->exp_buf[k], (size_t) cap * sizeof(part_aos)));
 	}
-	ZDEV_LAUNCH(k_migrate2d, 2 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->mig_cap, s->ctl,
-	            s->TX, s->TY, s->ntx, s->nx, s->exp_buf[0], s->exp_buf[1], s->exp_cap);
+	ZDEV_LAUNCH(k_migrate2d, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
+	            s->TX, s->TY, s->ntx, s->ntiles, s->nx, s->ny, prm->moving_window, prm->slab_left, prm->slab_right,
+	            s->exp_buf[0], s->exp_buf[1], s->exp_cap);
 	if (prm->moving_window || prm->slab_left || prm->slab_right) s->ids_valid = 0;
 }
 
@@ -961,7 +1165,7 @@ __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const
 	int64_t b = off[t];
 	for (int k = threadIdx.x; k < n; k += blockDim.x) {
 		if (p.key[b + k] == KEY_EMPTY) continue;
-		rec24 v = rec_load(p.rec + b + k);
+		rec24 v = rec_load(p.rec, b + k);
 		int idx = (x0 + (v.cell & 0xffff)) + nrow * (y0 + (v.cell >> 16));
 		float w1 = v.x, w2 = v.y;
 		atomicAdd(&rho[idx], (1.0f - w1) * (1.0f - w2) * q);
