@@ -601,44 +601,50 @@ struct push_geom {
 	int ntx;                 // tiles per row
 };
 
-// scatter one segment's 8 contributions into the global J grid (L2 reductions)
-__device__ __forceinline__ void red_weights(f3* __restrict__ c, int nrow, const float w[8]) {
-	atomicAdd(&c[0].x, w[0]);
-	atomicAdd(&c[nrow].x, w[1]);
-	atomicAdd(&c[0].y, w[2]);
-	atomicAdd(&c[1].y, w[3]);
-	atomicAdd(&c[0].z, w[4]);
-	atomicAdd(&c[1].z, w[5]);
-	atomicAdd(&c[nrow].z, w[6]);
-	atomicAdd(&c[nrow + 1].z, w[7]);
+// Where the current goes: the global J grid itself, through L2 float reductions (RED.ADD.F32).  v points
+// at the tile's cell (-1,-1), W3 = 3*nrow; component k of tile cell (lx,ly) = (lx+1)*3 + (ly+1)*W3 + k.
+// (Measured alternatives on B200: a shared-memory tile of floats or of 64-bit fixed point compiles to
+// compare-and-swap loops, 34 vs 50 Gpush/s; a tile of 32-bit coarse+fine fixed-point pairs with native
+// integer atomics 53 vs 56 Gpush/s.)
+struct jtile { float* v; };
+__device__ __forceinline__ void jt_add(const jtile& t, int idx, float w) { atomicAdd(t.v + idx, w); }
+// the 8 contributions of one segment in cell c (index of its first component), W3 = 3 * row length
+__device__ __forceinline__ void jt_weights(const jtile& t, int c, int W3, const float w[8]) {
+	jt_add(t, c, w[0]);
+	jt_add(t, c + W3, w[1]);
+	jt_add(t, c + 1, w[2]);
+	jt_add(t, c + 3 + 1, w[3]);
+	jt_add(t, c + 2, w[4]);
+	jt_add(t, c + 3 + 2, w[5]);
+	jt_add(t, c + W3 + 2, w[6]);
+	jt_add(t, c + W3 + 3 + 2, w[7]);
 }
-__device__ __forceinline__ void deposit_seg_global(f3* __restrict__ J, int nrow, const seg2d& s, float qnx, float qny) {
+__device__ __forceinline__ void deposit_seg(const jtile& t, int W3, const seg2d& s, float qnx, float qny) {
 	float w[8];
 	seg_weights(s, qnx, qny, w);
-	red_weights(J + (s.ix + 1) + (s.iy + 1) * nrow, nrow, w);
+	jt_weights(t, (s.ix + 1) * 3 + (s.iy + 1) * W3, W3, w);
 }
 
-// one queued move (warp-private shared-memory queue): a particle that crosses a cell face, or the second
-// particle of a thread when it sits in another cell than the first (dij = centre: one segment)
+// one queued move (warp-private shared-memory queue): what is left of a move after its first cell face;
+// ix, iy tile local, dij: the face it still has to cross, if any
 struct __align__(16) xq_entry { int ix, iy, dij; float x0, y0, dx, dy, qvz; };
 
 // split + deposit up to 32 queued moves, one per lane
-__device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, f3* __restrict__ J, int nrow,
+__device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, const jtile& t, int W3,
                                             float qnx, float qny) {
 	if (lane < n) {
 		xq_entry e = q[lane];
-		seg2d vp[3];
-		int vnp = split_trajectory(e.ix, e.iy, (e.dij & 3) - 1, ((e.dij >> 2) & 3) - 1, e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
-		deposit_seg_global(J, nrow, vp[0], qnx, qny);
-		if (vnp > 1) deposit_seg_global(J, nrow, vp[1], qnx, qny);
-		if (vnp > 2) deposit_seg_global(J, nrow, vp[2], qnx, qny);
+		seg2d vp[2];
+		int vnp = split_once(e.ix, e.iy, (e.dij & 3) - 1, ((e.dij >> 2) & 3) - 1, e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
+		deposit_seg(t, W3, vp[0], qnx, qny);
+		if (vnp > 1) deposit_seg(t, W3, vp[1], qnx, qny);
 	}
 }
 
 // Sum acc[0..7] over the 32 lanes (transposed butterfly: 9 shuffles for the 8 sums), after which lane 4*k
 // holds the total of contribution k, and add the totals to cell `cell` (= lx + ly*TX) of the tile.
 template <int TX>
-__device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lane, f3* __restrict__ J0, int nrow) {
+__device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lane, const jtile& t, int W3) {
 	float v4[4], v2[2], v1;
 	const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
 	#pragma unroll
@@ -663,8 +669,7 @@ __device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lan
 		const int right = (k == 3) | (k == 5) | (k == 7);
 		const int up = (k == 1) | (k == 6) | (k == 7);
 		const int lx = cell & (TX - 1), ly = cell / TX;
-		float* a = reinterpret_cast<float*>(J0 + lx + right + (ly + up) * nrow) + comp;
-		atomicAdd(a, v1);
+		jt_add(t, (lx + right + 1) * 3 + (ly + up + 1) * W3 + comp, v1);
 	}
 }
 
@@ -709,7 +714,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 // One CTA per tile.  Dynamic shared memory: corner tile (float4 x 6 planes); the warps' queues (the tile's
 // keys live in the same bytes during the sort); perm[max_cap] (16-bit slot indices; the raw field planes
 // are staged in the same bytes before the sort).
-template <int TX, int TY>
+template <int TX, int TY, bool TAGS>
 __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, mig2d mig,
@@ -726,9 +731,10 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	unsigned char* const s_tail = s_dyn + 6 * PLANE * 16 + smem_mid;
 	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_tail);
 	float* const s_raw = reinterpret_cast<float*>(s_tail);
+	const int JW3 = 3 * g.nrow;
 	__shared__ int s_cnt[NC];
 	__shared__ int s_wsum[PUSH_WARPS];
-	__shared__ int s_nmig, s_done;
+	__shared__ int s_nmig;
 	__shared__ __align__(8) unsigned long long s_bar;
 
 	const int t = blockIdx.x;
@@ -741,7 +747,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 
 	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
 	if (threadIdx.x == 0) {
-		s_nmig = 0; s_done = 0;
+		s_nmig = 0;
 		mbar_init(&s_bar, 1);
 		if (n > 0) bulk_load(s_dyn + 6 * PLANE * 16, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
 	}
@@ -820,7 +826,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const unsigned lt = (1u << lane) - 1u;
 	int nxq = 0;
 	float energy = 0.0f;      // per-thread partial in float (a few dozen terms), widened once per tile
-	f3* const J0 = J + (x0 + 1) + (y0 + 1) * g.nrow;          // cell (x0,y0)
+	jtile jt;
+	jt.v = reinterpret_cast<float*>(J + x0 + y0 * g.nrow);       // tile cell (-1,-1) = buffer cell (x0, y0)
 	const float* const Arec = A.rec + (size_t) (base >> 5) * REC_CHUNK_WORDS;
 	float* const Brec = Bo.rec + (size_t) (base >> 5) * REC_CHUNK_WORDS;
 	const int chunk = ((nlive + PUSH_WARPS * 64 - 1) / (PUSH_WARPS * 64)) * 64;
@@ -849,7 +856,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (cur >= 0) {
 			#pragma unroll
 			for (int q = 0; q < 8; q++) acc[q] += lo ? w[q] : 0.0f;
-			flush_cell<TX>(acc, cur, lane, J0, g.nrow);
+			flush_cell<TX>(acc, cur, lane, jt, JW3);
 		}
 		if ((heads & (heads - 1u)) == 0u) {
 			// one new cell starts at lane b and runs to the end of the warp: it becomes `cur`
@@ -872,7 +879,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				}
 			}
 			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-			if (tail && act && !lo) red_weights(J0 + lx + ly * g.nrow, g.nrow, w);
+			if (tail && act && !lo) jt_weights(jt, (lx + 1) * 3 + (ly + 1) * JW3, JW3, w);
 			#pragma unroll
 			for (int q = 0; q < 8; q++) acc[q] = 0.0f;
 			cur = -1;
@@ -888,17 +895,21 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		r.ux = mk2(qa[64], qb[64]); r.uy = mk2(qa[96], qb[96]); r.uz = mk2(qa[128], qb[128]);
 		r.ca = __float_as_int(qa[160]); r.cb = __float_as_int(qb[160]);
 		r.ta = r.tb = 0;
-		if (A.tag) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
+		if (TAGS) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
 	};
 
+#ifndef PUSH_PREFETCH
+#define PUSH_PREFETCH 1              // software pipeline: request the next iteration's records before the math
+#endif
 	pair_rec nv;
-	if (pbeg < pend) load_pair(pbeg + lane, nv);
+	if (PUSH_PREFETCH && pbeg < pend) load_pair(pbeg + lane, nv);
 
 	for (int p0 = pbeg; p0 < pend; p0 += 64) {
 		const int pa = p0 + lane, pb = pa + 32;
 		const bool actA = pa < pend, actB = pb < pend;
+		if (!PUSH_PREFETCH) load_pair(pa, nv);
 		const pair_rec v = nv;
-		if (p0 + 64 < pend) load_pair(pa + 64, nv);        // software pipeline: next iteration's records
+		if (PUSH_PREFETCH && p0 + 64 < pend) load_pair(pa + 64, nv);
 
 		const int lxa = v.ca & 0xffff, lya = v.ca >> 16, lxb = v.cb & 0xffff, lyb = v.cb >> 16;
 		f2 x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
@@ -920,43 +931,75 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		const f2 x1 = add2(x, dx), y1 = add2(y, dy);
 		const int dia = ltrim(x1.x), dib = ltrim(x1.y), dja = ltrim(y1.x), djb = ltrim(y1.y);
 
-		// which particles deposit here, which through the queue
+		// Every move deposits its FIRST in-cell piece - up to the first cell face it crosses, the whole move
+		// for the 91 % that cross none - through the lanes (its cell is the cell of its neighbours in the
+		// sorted order).  Only the remainder of a crossing move goes to the queue: 1 piece (2 for a corner
+		// cut) in the neighbouring cell.  The pieces join at (xe, ye), so charge is conserved exactly as in
+		// the reference's split (particles.c:785-879), which cuts the same straight line at the same faces.
 		const bool xa = actA && ((dia | dja) != 0);
 		const bool xb = actB && ((dib | djb) != 0);
+		const f2 fx = mk2(dia > 0 ? 1.0f : 0.0f, dib > 0 ? 1.0f : 0.0f), fy = mk2(dja > 0 ? 1.0f : 0.0f, djb > 0 ? 1.0f : 0.0f);
+		f2 tx = __fmul2_rn(sub2(fx, x), rcp_approx2(dx)), ty = __fmul2_rn(sub2(fy, y), rcp_approx2(dy));
+		tx.x = dia ? tx.x : 2.0f; tx.y = dib ? tx.y : 2.0f;
+		ty.x = dja ? ty.x : 2.0f; ty.y = djb ? ty.y : 2.0f;
+		const f2 t1 = mk2(fmaxf(fminf(fminf(tx.x, ty.x), 1.0f), 0.0f), fmaxf(fminf(fminf(tx.y, ty.y), 1.0f), 0.0f));
+		const bool xfa = dia != 0 && tx.x <= ty.x, xfb = dib != 0 && tx.y <= ty.y;       // the x face comes first
+		const bool yfa = dja != 0 && !xfa, yfb = djb != 0 && !xfb;
+		const f2 dx0 = __fmul2_rn(dx, t1), dy0 = __fmul2_rn(dy, t1);
+		f2 xe = add2(x, dx0), ye = add2(y, dy0);
+		xe.x = xfa ? fx.x : xe.x; xe.y = xfb ? fx.y : xe.y;
+		ye.x = yfa ? fy.x : ye.x; ye.y = yfb ? fy.y : ye.y;
 		{
 			f2 w2[8];
-			const f2 kz = mk2((actA && !xa) ? 0.5f : 0.0f, (actB && !xb) ? 0.5f : 0.0f);
-			seg_weights2(x, y, x1, y1, dx, dy, qvz, mul2(kz, prm.qnx), mul2(kz, prm.qny), kz, w2);
+			const f2 kz = mk2(actA ? 0.5f : 0.0f, actB ? 0.5f : 0.0f);
+			seg_weights2(x, y, xe, ye, dx0, dy0, __fmul2_rn(qvz, t1), mul2(kz, prm.qnx), mul2(kz, prm.qny), kz, w2);
 			float w[8];
 			#pragma unroll
 			for (int q = 0; q < 8; q++) w[q] = w2[q].x;
+#ifndef ABL_NO_DEPOSIT
 			deposit32(actA ? lxa + lya * TX : 0x7fffffff, w, actA, lxa, lya);
 			#pragma unroll
 			for (int q = 0; q < 8; q++) w[q] = w2[q].y;
 			deposit32(actB ? lxb + lyb * TX : 0x7fffffff, w, actB, lxb, lyb);
+#else
+			acc[0] += w[0] + w[1] + w[2] + w[3] + w[4] + w[5] + w[6] + w[7];
+			#pragma unroll
+			for (int q = 0; q < 8; q++) w[q] = w2[q].y;
+			acc[1] += w[0] + w[1] + w[2] + w[3] + w[4] + w[5] + w[6] + w[7];
+#endif
 		}
 
-		// --- queue of the cell crossers; drain 32 at a time
+		// --- queue of the remainders; drain 32 at a time
 		{
+#ifdef ABL_NO_QUEUE
+			const unsigned ma = 0, mb = 0;
+#else
 			const unsigned ma = __ballot_sync(0xffffffffu, xa), mb = __ballot_sync(0xffffffffu, xb);
+#endif
 			if (ma | mb) {
 				if (xa) {
+					const float rem = 1.0f - t1.x;
 					xq_entry e;
-					e.ix = x0 + lxa; e.iy = y0 + lya; e.dij = (dia + 1) | ((dja + 1) << 2);
-					e.x0 = x.x; e.y0 = y.x; e.dx = dx.x; e.dy = dy.x; e.qvz = qvz.x;
+					e.ix = lxa + (xfa ? dia : 0); e.iy = lya + (yfa ? dja : 0);
+					e.dij = ((xfa ? 0 : dia) + 1) | (((yfa ? 0 : dja) + 1) << 2);
+					e.x0 = xfa ? 1.0f - fx.x : xe.x; e.y0 = yfa ? 1.0f - fy.x : ye.x;
+					e.dx = dx.x * rem; e.dy = dy.x * rem; e.qvz = qvz.x * rem;
 					xq[nxq + __popc(ma & lt)] = e;
 				}
 				nxq += __popc(ma);
 				if (xb) {
+					const float rem = 1.0f - t1.y;
 					xq_entry e;
-					e.ix = x0 + lxb; e.iy = y0 + lyb; e.dij = (dib + 1) | ((djb + 1) << 2);
-					e.x0 = x.y; e.y0 = y.y; e.dx = dx.y; e.dy = dy.y; e.qvz = qvz.y;
+					e.ix = lxb + (xfb ? dib : 0); e.iy = lyb + (yfb ? djb : 0);
+					e.dij = ((xfb ? 0 : dib) + 1) | (((yfb ? 0 : djb) + 1) << 2);
+					e.x0 = xfb ? 1.0f - fx.y : xe.y; e.y0 = yfb ? 1.0f - fy.y : ye.y;
+					e.dx = dx.y * rem; e.dy = dy.y * rem; e.qvz = qvz.y * rem;
 					xq[nxq + __popc(mb & lt)] = e;
 				}
 				nxq += __popc(mb);
 				__syncwarp();
 				while (nxq >= 32) {
-					drain_queue(xq + nxq - 32, 32, lane, J, g.nrow, prm.qnx, prm.qny);
+					drain_queue(xq + nxq - 32, 32, lane, jt, JW3, prm.qnx, prm.qny);
 					nxq -= 32;
 				}
 				__syncwarp();
@@ -971,17 +1014,23 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		const bool stb = actB && (unsigned) nlxb < (unsigned) cx && (unsigned) nlyb < (unsigned) cy;
 		if (actA) {
 			float* qd = Brec + (pa >> 5) * REC_CHUNK_WORDS + (pa & 31);
-			qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
-			qd[160] = __int_as_float(nlxa | (nlya << 16));
+#ifdef ABL_NO_STORE
+			if (xn.x == 12345.0f)
+#endif
+			{ qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
+			qd[160] = __int_as_float(nlxa | (nlya << 16)); }
 			Bo.key[base + pa] = sta ? (unsigned short) (nlxa + nlya * TX) : (unsigned short) KEY_EMPTY;
-			if (Bo.tag) Bo.tag[base + pa] = v.ta;
+			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
 		if (actB) {
 			float* qd = Brec + (pb >> 5) * REC_CHUNK_WORDS + (pb & 31);
-			qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
-			qd[160] = __int_as_float(nlxb | (nlyb << 16));
+#ifdef ABL_NO_STORE
+			if (xn.y == 12345.0f)
+#endif
+			{ qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
+			qd[160] = __int_as_float(nlxb | (nlyb << 16)); }
 			Bo.key[base + pb] = stb ? (unsigned short) (nlxb + nlyb * TX) : (unsigned short) KEY_EMPTY;
-			if (Bo.tag) Bo.tag[base + pb] = v.tb;
+			if (TAGS) Bo.tag[base + pb] = v.tb;
 		}
 		{
 			const bool la = actA && !sta, lb = actB && !stb;
@@ -996,7 +1045,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 						part_aos r; r.ix = x0 + nlxa; r.iy = y0 + nlya;
 						r.x = xn.x; r.y = yn.x; r.ux = ux.x; r.uy = uy.x; r.uz = uz.x;
 						mig.rec[mig_base + d] = r;
-						if (mig.tag) mig.tag[mig_base + d] = v.ta;
+						if (TAGS) mig.tag[mig_base + d] = v.ta;
 					}
 				}
 				if (lb) {
@@ -1005,28 +1054,25 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 						part_aos r; r.ix = x0 + nlxb; r.iy = y0 + nlyb;
 						r.x = xn.y; r.y = yn.y; r.ux = ux.y; r.uy = uy.y; r.uz = uz.y;
 						mig.rec[mig_base + d] = r;
-						if (mig.tag) mig.tag[mig_base + d] = v.tb;
+						if (TAGS) mig.tag[mig_base + d] = v.tb;
 					}
 				}
 			}
 		}
 	}
-	if (cur >= 0) flush_cell<TX>(acc, cur, lane, J0, g.nrow);
-	if (nxq) drain_queue(xq, nxq, lane, J, g.nrow, prm.qnx, prm.qny);
+	if (cur >= 0) flush_cell<TX>(acc, cur, lane, jt, JW3);
+	if (nxq) drain_queue(xq, nxq, lane, jt, JW3, prm.qnx, prm.qny);
 
-	// ---- tile epilogue (no block barrier: warps retire independently): slots in use, energy, migrants
+	// ---- tile epilogue: energy, slots in use, migrants
 	double e = (double) energy;
 	for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-	if (lane == 0) {
-		if (nlive > 0) atomicAdd(&ctl->energy, e);
-		__threadfence_block();
-		if (atomicAdd(&s_done, 1) == PUSH_WARPS - 1) {
-			// last warp out: every reservation in s_nmig has been made
-			const int nm = atomicAdd(&s_nmig, 0);
-			if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
-			mig.np[t] = min(nm, mig_cap);
-			tile_np_out[t] = nlive;
-		}
+	if (lane == 0 && nlive > 0) atomicAdd(&ctl->energy, e);
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const int nm = s_nmig;
+		if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
+		mig.np[t] = min(nm, mig_cap);
+		tile_np_out[t] = nlive;
 	}
 }
 
@@ -1088,7 +1134,8 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 	size_t smem = push_smem_bytes(TX, TY, s->max_cap);
 	static size_t configured = 0;
 	if (smem > configured) {
-		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured = smem;
 	}
 	int slot = -1;
@@ -1101,8 +1148,12 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
-	ZDEV_LAUNCH((k_push2d<TX, TY>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-	            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
+	if (s->track_ids)
+		ZDEV_LAUNCH((k_push2d<TX, TY, true>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
+	else
+		ZDEV_LAUNCH((k_push2d<TX, TY, false>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
 
