@@ -664,13 +664,13 @@ __device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lan
 	v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
 	v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
 	if ((lane & 3) == 0) {
-		const int k = lane >> 2;                       // contribution index, see seg_weights()
+		const int k = lane >> 2;
 		const int comp = (k < 2) ? 0 : ((k < 4) ? 1 : 2);
 		const int right = (k == 3) | (k == 5) | (k == 7);
 		const int up = (k == 1) | (k == 6) | (k == 7);
-		const int lx = cell & (TX - 1), ly = cell / TX;
-		jt_add(t, (lx + right + 1) * 3 + (ly + up + 1) * W3 + comp, v1);
+		jt_add(t, ((cell & (TX - 1)) + 1) * 3 + (cell / TX + 1) * W3 + comp + right * 3 + up * W3, v1);
 	}
+
 }
 
 // the six words of the sorted neighbours (pa, pa+1), as loaded from their source slots
@@ -734,7 +734,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int JW3 = 3 * g.nrow;
 	__shared__ int s_cnt[NC];
 	__shared__ int s_wsum[PUSH_WARPS];
-	__shared__ int s_nmig;
+	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
 	const int t = blockIdx.x;
@@ -747,7 +747,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 
 	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
 	if (threadIdx.x == 0) {
-		s_nmig = 0;
+		s_nmig = 0; s_done = 0;
 		mbar_init(&s_bar, 1);
 		if (n > 0) bulk_load(s_dyn + 6 * PLANE * 16, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
 	}
@@ -1012,23 +1012,18 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		const int nlxb = lxb + dib - prm.shift_window, nlyb = lyb + djb;
 		const bool sta = actA && (unsigned) nlxa < (unsigned) cx && (unsigned) nlya < (unsigned) cy;
 		const bool stb = actB && (unsigned) nlxb < (unsigned) cx && (unsigned) nlyb < (unsigned) cy;
+		// p0 is a multiple of 64: pa sits in chunk p0/32 at lane, pb in the next chunk at lane
 		if (actA) {
 			float* qd = Brec + (pa >> 5) * REC_CHUNK_WORDS + (pa & 31);
-#ifdef ABL_NO_STORE
-			if (xn.x == 12345.0f)
-#endif
-			{ qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
-			qd[160] = __int_as_float(nlxa | (nlya << 16)); }
+			qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
+			qd[160] = __int_as_float(nlxa | (nlya << 16));
 			Bo.key[base + pa] = sta ? (unsigned short) (nlxa + nlya * TX) : (unsigned short) KEY_EMPTY;
 			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
 		if (actB) {
 			float* qd = Brec + (pb >> 5) * REC_CHUNK_WORDS + (pb & 31);
-#ifdef ABL_NO_STORE
-			if (xn.y == 12345.0f)
-#endif
-			{ qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
-			qd[160] = __int_as_float(nlxb | (nlyb << 16)); }
+			qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
+			qd[160] = __int_as_float(nlxb | (nlyb << 16));
 			Bo.key[base + pb] = stb ? (unsigned short) (nlxb + nlyb * TX) : (unsigned short) KEY_EMPTY;
 			if (TAGS) Bo.tag[base + pb] = v.tb;
 		}
@@ -1063,16 +1058,19 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	if (cur >= 0) flush_cell<TX>(acc, cur, lane, jt, JW3);
 	if (nxq) drain_queue(xq, nxq, lane, jt, JW3, prm.qnx, prm.qny);
 
-	// ---- tile epilogue: energy, slots in use, migrants
+	// ---- tile epilogue (no block barrier: warps retire independently): energy, slots in use, migrants
 	double e = (double) energy;
 	for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
 	if (lane == 0 && nlive > 0) atomicAdd(&ctl->energy, e);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		const int nm = s_nmig;
-		if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
-		mig.np[t] = min(nm, mig_cap);
-		tile_np_out[t] = nlive;
+	if (lane == 0) {
+		__threadfence_block();
+		if (atomicAdd(&s_done, 1) == PUSH_WARPS - 1) {
+			// last warp out: every reservation in s_nmig has been made
+			const int nm = atomicAdd(&s_nmig, 0);
+			if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
+			mig.np[t] = min(nm, mig_cap);
+			tile_np_out[t] = nlive;
+		}
 	}
 }
 
