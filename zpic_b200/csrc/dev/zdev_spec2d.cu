@@ -681,16 +681,16 @@ struct pair_rec { f2 x, y, ux, uy, uz; int ca, cb, ta, tb; };
 #endif
 static const int XQ_CAP = XQ_CAP_N;
 
-// dynamic shared memory of k_push2d: [corner tile][queues | keys][perm | raw planes]
-static size_t push_smem_mid(int max_cap) {
-	size_t xq = (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
-	return xq > keys ? xq : keys;
+// dynamic shared memory of k_push2d: [keys during the sort | corner tile + queues afterwards][perm][raw planes]
+static size_t push_smem_front(int TX, int TY, int max_cap) {
+	size_t plane = (size_t) (TX + 2) * (TY + 2);
+	size_t late = 6 * plane * 16 + (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	return late > keys ? late : keys;
 }
 static size_t push_smem_bytes(int TX, int TY, int max_cap) {
 	size_t plane = (size_t) (TX + 2) * (TY + 2);
-	size_t perm = (size_t) max_cap * 2, raw = 6 * plane * 4;
-	size_t tail = perm > raw ? perm : raw;
-	return 6 * plane * 16 + push_smem_mid(max_cap) + ((tail + 15) & ~(size_t) 15);
+	size_t perm = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	return push_smem_front(TX, TY, max_cap) + perm + 6 * plane * 4;
 }
 
 // --- TMA bulk copy (global -> shared, completion on an mbarrier): the tile's key segment is fetched by
@@ -711,15 +711,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
 	             "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(bar)), "r"(phase) : "memory");
 }
 
-// One CTA per tile.  Dynamic shared memory: corner tile (float4 x 6 planes); the warps' queues (the tile's
-// keys live in the same bytes during the sort); perm[max_cap] (16-bit slot indices; the raw field planes
-// are staged in the same bytes before the sort).
+// One CTA per tile.  Dynamic shared memory: the tile's keys during the sort, afterwards the corner tile
+// (float4 x 6 planes) and the warps' queues in the same bytes; perm[max_cap] (16-bit slot indices); the raw
+// field planes.
 template <int TX, int TY, bool TAGS>
 __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, mig2d mig,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
-         push_geom g, zdev_push2d_params prm, unsigned smem_mid) {
+         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm) {
 	constexpr int SROW = TX + 2;
 	constexpr int PLANE = SROW * (TY + 2);
 	constexpr int NC = TX * TY;
@@ -727,13 +727,11 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	float4* const s_f4 = reinterpret_cast<float4*>(s_dyn);
 	xq_entry* const s_xq = reinterpret_cast<xq_entry*>(s_dyn + 6 * PLANE * 16);
-	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn + 6 * PLANE * 16);
-	unsigned char* const s_tail = s_dyn + 6 * PLANE * 16 + smem_mid;
-	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_tail);
-	float* const s_raw = reinterpret_cast<float*>(s_tail);
+	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
+	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
+	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
 	const int JW3 = 3 * g.nrow;
-	__shared__ int s_cnt[NC];
-	__shared__ int s_wsum[PUSH_WARPS];
+	__shared__ int s_cnt[NC], s_cur[NC];
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
@@ -749,7 +747,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	if (threadIdx.x == 0) {
 		s_nmig = 0; s_done = 0;
 		mbar_init(&s_bar, 1);
-		if (n > 0) bulk_load(s_dyn + 6 * PLANE * 16, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
+		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
 	}
 	// ---- stage the field neighbourhood: cells [x0-1, x0+cx] x [y0-1, y0+cy] as raw planes ...
 	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += PUSH_THREADS) {
@@ -762,17 +760,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	}
 	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
 	__syncthreads();
-	// ... then as the four corners of every cell (entries of the last row / column are never read)
-	for (int k = threadIdx.x; k < 6 * PLANE; k += PUSH_THREADS) {
-		const int pl = k / PLANE, o = k - pl * PLANE;
-		const int r = o / SROW, c = o - r * SROW;
-		const int o1 = (c + 1 < SROW) ? o + 1 : o, o2 = (r + 1 < TY + 2) ? o + SROW : o;
-		const int o3 = o2 + (o1 - o);
-		const float* P = s_raw + pl * PLANE;
-		s_f4[k] = make_float4(P[o], P[o2], P[o1], P[o3]);
-	}
 	if (n > 0) mbar_wait(&s_bar, 0);
-	__syncthreads();                                    // s_raw is dead: its bytes become perm[]
 
 	// ---- phase A: counting sort of slot indices by cell.  The keys arrive almost sorted (B was written in
 	//      cell order by the previous step), so 32 CONSECUTIVE keys would hammer one counter (shared-memory
@@ -795,7 +783,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	}
 	__syncthreads();
 	int nlive;
-	{	// exclusive scan of s_cnt (NC <= 256 == PUSH_THREADS): s_cnt becomes the write cursor
+	{	// exclusive scan of s_cnt (NC <= 256 == PUSH_THREADS)
+		__shared__ int s_wsum[PUSH_WARPS];
 		int v = (threadIdx.x < NC) ? s_cnt[threadIdx.x] : 0;
 		int incl = v;
 		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
@@ -804,7 +793,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		int woff = 0, tot = 0;
 		#pragma unroll
 		for (int w = 0; w < PUSH_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
-		if (threadIdx.x < NC) s_cnt[threadIdx.x] = woff + incl - v;
+		if (threadIdx.x < NC) s_cur[threadIdx.x] = woff + incl - v;
 		nlive = tot;
 		__syncthreads();
 	}
@@ -814,11 +803,21 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (i < n) {
 			const unsigned two = s_key2[j];
 			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c0], 1)] = (unsigned short) i;
-			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cnt[c1], 1)] = (unsigned short) (i + 1);
+			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
+			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
 		}
 	}
-	__syncthreads();                                    // the keys are dead: their bytes become the queues
+	__syncthreads();                                    // the keys are dead: their bytes become corner tile + queues
+	// ---- the fields as the four corners of every cell (entries of the last row / column are never read)
+	for (int k = threadIdx.x; k < 6 * PLANE; k += PUSH_THREADS) {
+		const int pl = k / PLANE, o = k - pl * PLANE;
+		const int r = o / SROW, c = o - r * SROW;
+		const int o1 = (c + 1 < SROW) ? o + 1 : o, o2 = (r + 1 < TY + 2) ? o + SROW : o;
+		const int o3 = o2 + (o1 - o);
+		const float* P = s_raw + pl * PLANE;
+		s_f4[k] = make_float4(P[o], P[o2], P[o1], P[o3]);
+	}
+	__syncthreads();
 
 	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
 	//      owns the particles l and l+32 of the iteration's block); no block barriers from here on
@@ -853,21 +852,23 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		}
 		const int b = __ffs(heads) - 1;                // lanes below b continue cell `cur`
 		const bool lo = lane < b;
+		// masks as multipliers: the selects would all land on the (half-rate) ALU pipe
+		const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
 		if (cur >= 0) {
 			#pragma unroll
-			for (int q = 0; q < 8; q++) acc[q] += lo ? w[q] : 0.0f;
+			for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
 			flush_cell<TX>(acc, cur, lane, jt, JW3);
 		}
 		if ((heads & (heads - 1u)) == 0u) {
 			// one new cell starts at lane b and runs to the end of the warp: it becomes `cur`
 			#pragma unroll
-			for (int q = 0; q < 8; q++) acc[q] = lo ? 0.0f : w[q];
+			for (int q = 0; q < 8; q++) acc[q] = w[q] * mhi;
 			cur = __shfl_sync(0xffffffffu, key, 31);
 			if (cur >= NC) cur = -1;                   // the range ended inside these 32
 		} else {
 			// several cells start here: segmented inclusive scan, the last lane of each run holds its totals
 			#pragma unroll
-			for (int q = 0; q < 8; q++) w[q] = lo ? 0.0f : w[q];
+			for (int q = 0; q < 8; q++) w[q] *= mhi;
 			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 			#pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
@@ -977,23 +978,24 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			const unsigned ma = __ballot_sync(0xffffffffu, xa), mb = __ballot_sync(0xffffffffu, xb);
 #endif
 			if (ma | mb) {
+				// what is left of the two moves, in the frame of the cell behind the face
 				if (xa) {
-					const float rem = 1.0f - t1.x;
 					xq_entry e;
 					e.ix = lxa + (xfa ? dia : 0); e.iy = lya + (yfa ? dja : 0);
 					e.dij = ((xfa ? 0 : dia) + 1) | (((yfa ? 0 : dja) + 1) << 2);
+					{ const float r1 = 1.0f - t1.x;
 					e.x0 = xfa ? 1.0f - fx.x : xe.x; e.y0 = yfa ? 1.0f - fy.x : ye.x;
-					e.dx = dx.x * rem; e.dy = dy.x * rem; e.qvz = qvz.x * rem;
+					e.dx = dx.x * r1; e.dy = dy.x * r1; e.qvz = qvz.x * r1; }
 					xq[nxq + __popc(ma & lt)] = e;
 				}
 				nxq += __popc(ma);
 				if (xb) {
-					const float rem = 1.0f - t1.y;
 					xq_entry e;
 					e.ix = lxb + (xfb ? dib : 0); e.iy = lyb + (yfb ? djb : 0);
 					e.dij = ((xfb ? 0 : dib) + 1) | (((yfb ? 0 : djb) + 1) << 2);
+					{ const float r1 = 1.0f - t1.y;
 					e.x0 = xfb ? 1.0f - fx.y : xe.y; e.y0 = yfb ? 1.0f - fy.y : ye.y;
-					e.dx = dx.y * rem; e.dy = dy.y * rem; e.qvz = qvz.y * rem;
+					e.dx = dx.y * r1; e.dy = dy.y * r1; e.qvz = qvz.y * r1; }
 					xq[nxq + __popc(mb & lt)] = e;
 				}
 				nxq += __popc(mb);
@@ -1148,10 +1150,10 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 	}
 	if (s->track_ids)
 		ZDEV_LAUNCH((k_push2d<TX, TY, true>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
+		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_front(TX, TY, s->max_cap), (unsigned) ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15)));
 	else
 		ZDEV_LAUNCH((k_push2d<TX, TY, false>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_mid(s->max_cap));
+		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_front(TX, TY, s->max_cap), (unsigned) ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15)));
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
 
