@@ -152,8 +152,9 @@ zdev_spec2d* zdev_spec2d_create( int nx, int ny, int ppc_hint, int track_ids );
 void zdev_spec2d_destroy( zdev_spec2d* s );
 /* host AoS -> device tiles (replaces the whole population) */
 void zdev_spec2d_upload( zdev_spec2d* s, const void* part_aos, int64_t np );
-/* Host buffers >= 32 MB passed to upload / download are pinned + mapped on first use and then accessed by
- * the kernels directly (zero copy); call this before such a buffer is freed or reallocated. */
+/* With ZPIC_ZERO_COPY_MIN=<bytes> set, host buffers of at least that size passed to upload / download are
+ * pinned + mapped on first use and then accessed by the kernels directly (zero copy, off by default); call
+ * this before such a buffer is freed or reallocated. */
 void zdev_host_forget( const void* host_ptr );
 /* append host AoS particles (moving-window injection, Species.add) */
 void zdev_spec2d_append( zdev_spec2d* s, const void* part_aos, int64_t np );

@@ -186,6 +186,41 @@ def test_charge_deposit(ours, ref):
     b.delete()
 
 
+def _gauss_residual(deck, rho0):
+    """div E - rho + rho(0) on the interior nodes, Yee staggering (Ex at i+1/2, Ey at j+1/2, rho at nodes).
+    E(0) = 0 and the deck has no neutralising background, so exact charge conservation of the deposit
+    means div E(t) - rho(t) stays at its initial value -rho(0)."""
+    deck.sync()
+    E = deck.E().astype(np.float64)                 # (ny+3, nx+3, 3), cell (0,0) at [1,1]
+    ny, nx = E.shape[0] - 3, E.shape[1] - 3
+    dx = float(deck.sim.emf.dx[0])
+    dy = float(deck.sim.emf.dx[1])
+    ex, ey = E[1:ny + 1, :, 0], E[:, 1:nx + 1, 1]
+    div = (ex[:, 1:nx + 1] - ex[:, 0:nx]) / dx + (ey[1:ny + 1, :] - ey[0:ny, :]) / dy        # nodes (0..nx-1, 0..ny-1)
+    rho = sum(deck.charge(k).astype(np.float64) for k in range(deck.n_species))[:ny, :nx]
+    return div - rho + rho0[:ny, :nx], rho
+
+
+def test_charge_conservation_residual(ours, ref):
+    """north_star: the div E vs rho residual must agree with the reference within 1e-6 relative.  Both codes
+    deposit an exactly charge-conserving current, so the residual is rounding noise on the scale of the
+    species' charge density (|rho_species| ~ 1)."""
+    a, b = H.weibel(ours, n=64, ppc=(4, 4), n_sort=0), H.weibel(ref, n=64, ppc=(4, 4), n_sort=0)
+    rho0 = [sum(d.charge(k).astype(np.float64) for k in range(2)) for d in (a, b)]
+    assert np.array_equal(rho0[0], rho0[1])
+    for steps in (1, 30):
+        a.iter(steps - a.sim.emf.iter)
+        b.iter(steps - b.sim.emf.iter)
+        ra, _ = _gauss_residual(a, rho0[0])
+        rb, _ = _gauss_residual(b, rho0[1])
+        scale = np.abs(a.charge(0)).max()           # one species' density: the two species cancel in rho
+        assert np.abs(rb).max() < 1e-5 * scale      # the reference conserves charge to rounding ...
+        assert np.abs(ra).max() < 1e-5 * scale      # ... and so does the CUDA deposit
+        assert abs(np.sqrt((ra ** 2).mean()) - np.sqrt((rb ** 2).mean())) < 1e-6 * scale, steps
+    a.delete()
+    b.delete()
+
+
 def test_lwfa_moving_window(ours, ref):
     """laser + moving window + absorbing x + compensated smoothing + window injection"""
     kw = dict(nx=(256, 64), box=(5.12, 12.8), dt=0.014, ppc=(2, 2), start=4.0, laser_start=3.5, a0=1.0, n_sort=0)

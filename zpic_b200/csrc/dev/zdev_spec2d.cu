@@ -341,10 +341,11 @@ static void spec_append_dev(zdev_spec2d* s, const part_aos* d_aos, int64_t np, i
 	            s->p, s->tile_off, s->tile_np, s->ctl, tag0);
 }
 
-// Host buffers of at least this size are pinned + mapped once and then read / written by the binning
-// and gather kernels directly over PCIe (zero copy): no device staging copy of the population, and
-// repeated transfers of the same mirror (ZPIC_COHERENT) run at link speed instead of pageable speed.
-static const size_t MAP_MIN_BYTES = (size_t) 32 << 20;
+// Zero-copy option (ZPIC_ZERO_COPY_MIN=<bytes>): host buffers of at least that size are pinned + mapped once
+// and then read / written by the binning and gather kernels directly over PCIe, without a device staging
+// copy of the population.  Off by default: measured on B200 (PCIe Gen5) the gather kernel's 28-byte record
+// writes into mapped memory run at ~9 GB/s, half the speed of gather-to-HBM + one bulk copy.
+static const size_t MAP_MIN_BYTES = ~(size_t) 0;
 struct host_map { const void* ptr; size_t bytes; void* dev; };
 static host_map g_maps[8];
 
