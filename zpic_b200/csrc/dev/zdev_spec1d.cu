@@ -1,18 +1,23 @@
 // zpic-b200 :: em1d particle species on the device.
 //
 // One-dimensional twin of zdev_spec2d.cu (see there for the design): the grid is cut into tiles of TX
-// cells, each tile owns a fixed-capacity segment of 20-byte records {x, ux, uy, uz, cell} plus a 16-bit
-// sort key per slot, double buffered (A -> B every step).  One CTA per tile: stage the E/B neighbourhood
-// in shared memory, counting-sort the slot indices by cell, then stream the particles in cell order with
-// a software-pipelined loop; the five current contributions of non-crossing particles are combined per
-// run of equal cell with a segmented warp scan, cell-crossing particles go through a warp-private queue
-// and are split into their two segments 32 at a time.
+// cells, each tile owns a fixed-capacity segment of slots in chunks of 32, a chunk being five 128-byte
+// rows  x[32] ux[32] uy[32] uz[32] cell[32]  (cell = tile-local index), plus a 16-bit sort key per slot,
+// double buffered (A -> B every step).  One CTA per tile: TMA bulk load of the tile's keys while the E/B
+// neighbourhood is staged, counting sort of the slot indices by cell in shared memory, then every warp
+// streams a contiguous range of the sorted particles, 64 per iteration, two particles per thread as the
+// halves of packed fp32 registers (FFMA2 / FADD2 / FMUL2, each half rounded like the scalar reference
+// operation).  Every move deposits its first in-cell piece through a per-lane accumulator that is reduced
+// across the warp only when the warp moves on to the next cell; the remainder of a cell-crossing move
+// (19 % of the particles of the two-stream deck) goes through a warp-private queue, one segment each.
 //
 // Replaces reference em1d/particles.c:919-1074 (spec_advance: interpolate_fld :864-886, Boris push,
 // dep_current_zamb :707-779, periodic / open / moving-window boundaries) and :791-850 (spec_sort).
-// Arithmetic order follows the reference exactly (--fmad=false): one step is bit-identical.
+// Arithmetic order follows the reference exactly (no contraction): one step is bit-identical.
 #include "zdev_common.cuh"
-#include "pic2d_core.cuh"      // div_exact / sqrt_exact / ltrim
+#include "pic2d_core.cuh"      // ltrim
+#include "pic2d_packed.cuh"    // packed fp32 arithmetic, boris2
+#include "zdev_tma.cuh"
 #include <vector>
 #include <cstring>
 
@@ -22,20 +27,35 @@ f3* zdev_grid1d_J(zdev_grid1d* g);
 int zdev_grid1d_nx(zdev_grid1d* g);
 
 struct part1_aos { int ix; float x, ux, uy, uz; };           // host record (em1d/particles.h:29-35)
-struct rec20 { float x, ux, uy, uz; int cell; };             // device record; cell = tile-local index
+struct rec20 { float x, ux, uy, uz; int cell; };             // one particle as a value; cell = tile-local index
 #define KEY1_EMPTY 0xffffu
+#define REC1_CHUNK_WORDS 160          // 5 rows x 32 slots
 
 struct buf1d {
-	rec20* rec;
-	unsigned short* key;     // tile buffers only
+	float* rec;              // chunked records
+	unsigned short* key;
 	int* tag;                // optional
 };
+// migrants: one fixed segment per tile, [tile_off[t]/div, tile_off[t+1]/div), of reference-format records
+// carrying UNWRAPPED global cell indices (boundary conditions are applied by k1_migrate)
+struct mig1d { part1_aos* rec; int* tag; int* np; int div; };
+
+__device__ __forceinline__ size_t rec1_word(int64_t slot) { return (size_t) (slot >> 5) * REC1_CHUNK_WORDS + (size_t) (slot & 31); }
+__device__ __forceinline__ rec20 rec1_load(const float* __restrict__ rec, int64_t slot) {
+	const float* q = rec + rec1_word(slot);
+	rec20 r; r.x = q[0]; r.ux = q[32]; r.uy = q[64]; r.uz = q[96]; r.cell = __float_as_int(q[128]);
+	return r;
+}
+__device__ __forceinline__ void rec1_store(float* __restrict__ rec, int64_t slot, const rec20& r) {
+	float* q = rec + rec1_word(slot);
+	q[0] = r.x; q[32] = r.ux; q[64] = r.uy; q[96] = r.uz; q[128] = __int_as_float(r.cell);
+}
 
 struct ctl1d {
 	double energy;
 	unsigned long long np;
-	unsigned int n_mig;
-	unsigned int flags;      // 1 tile overflow, 2 migrants overflow
+	unsigned int pad0;
+	unsigned int flags;      // 1 tile overflow, 2 a tile's migrants segment overflowed
 };
 
 struct zdev_spec1d {
@@ -46,8 +66,7 @@ struct zdev_spec1d {
 	buf1d p, q;
 	int64_t* tile_off;
 	int *tile_np, *tile_np_q;
-	rec20* mig; int* mig_tag;        // migrants: cell = GLOBAL cell index
-	unsigned int mig_cap;
+	mig1d mig;                       // per-tile migrants segments
 	ctl1d* ctl;
 	int64_t np_host;
 	int ids_valid;
@@ -57,13 +76,14 @@ struct zdev_spec1d {
 
 static const int P1_THREADS = 256;
 static const int P1_WARPS = P1_THREADS / 32;
-static const int XQ1_CAP = 64;
+static const int XQ1_CAP = 96;       // 31 left over + 64 new entries at most
 static const int EV1_RING = 64;
 
 static void buf_alloc(buf1d& b, int64_t n, int with_tag) {
 	size_t nn = (size_t) (n > 0 ? n : 1);
 	memset(&b, 0, sizeof b);
-	ZDEV_CHECK(cudaMalloc(&b.rec, nn * sizeof(rec20)));
+	if (nn & 31) nn = (nn + 31) & ~(size_t) 31;      // whole chunks
+	ZDEV_CHECK(cudaMalloc(&b.rec, nn * 20));
 	ZDEV_CHECK(cudaMalloc(&b.key, nn * 2));
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&b.tag, nn * 4));
 }
@@ -71,6 +91,14 @@ static void buf_free(buf1d& b) { cudaFree(b.rec); cudaFree(b.key); cudaFree(b.ta
 
 extern "C" zdev_spec1d* zdev_spec1d_create(int nx, int ppc_hint, int track_ids) {
 	zdev_require_init();
+	{	// the packed-multiply addend (pic2d_packed.cuh)
+		static bool negzero_set = false;
+		if (!negzero_set) {
+			const float2 nz = make_float2(-0.0f, -0.0f);
+			ZDEV_CHECK(cudaMemcpyToSymbol(c_negzero2, &nz, sizeof nz));
+			negzero_set = true;
+		}
+	}
 	zdev_spec1d* s = new zdev_spec1d();
 	memset(s, 0, sizeof(*s));
 	s->nx = nx; s->ppc_hint = ppc_hint > 0 ? ppc_hint : 1; s->track_ids = track_ids;
@@ -93,8 +121,10 @@ extern "C" zdev_spec1d* zdev_spec1d_create(int nx, int ppc_hint, int track_ids) 
 }
 
 static void free_particles(zdev_spec1d* s) {
-	if (s->cap_total) { buf_free(s->p); buf_free(s->q); cudaFree(s->mig); cudaFree(s->mig_tag); s->mig = nullptr; s->mig_tag = nullptr; }
-	s->cap_total = 0; s->mig_cap = 0;
+	if (s->cap_total) { buf_free(s->p); buf_free(s->q); }
+	cudaFree(s->mig.rec); cudaFree(s->mig.tag); cudaFree(s->mig.np);
+	memset(&s->mig, 0, sizeof s->mig);
+	s->cap_total = 0;
 }
 
 extern "C" void zdev_spec1d_destroy(zdev_spec1d* s) {
@@ -122,7 +152,7 @@ static void layout(zdev_spec1d* s, const std::vector<int>& cnt, int64_t np) {
 		off[t + 1] = off[t] + cap;
 		if (cap > max_cap) max_cap = cap;
 	}
-	if (max_cap * 4 > 160 * 1024) {
+	if (max_cap > 0xfff0) {
 		fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %d-cell tile exceed the shared-memory index "
 		        "buffer; use smaller tiles (ZPIC_TILE_X1D)\n", (long long) max_cap, s->TX);
 		exit(-1);
@@ -132,11 +162,13 @@ static void layout(zdev_spec1d* s, const std::vector<int>& cnt, int64_t np) {
 	buf_alloc(s->p, total, s->track_ids);
 	buf_alloc(s->q, total, s->track_ids);
 	s->cap_total = total; s->max_cap = (int) max_cap;
-	int64_t mc = total / 8 + 65536;
-	if (mc > 0x7fffffff) mc = 0x7fffffff;
-	s->mig_cap = (unsigned int) mc;
-	ZDEV_CHECK(cudaMalloc(&s->mig, (size_t) mc * sizeof(rec20)));
-	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig_tag, (size_t) mc * 4));
+	// migrants segments: 1/4 of every tile (two-stream decks move ~10 % of a 32-cell tile per step, a window
+	// shift a whole cell's worth on top)
+	s->mig.div = 4;
+	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) (total / s->mig.div + 32) * sizeof(part1_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig.tag, (size_t) (total / s->mig.div + 32) * 4));
+	ZDEV_CHECK(cudaMalloc(&s->mig.np, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMemsetAsync(s->mig.np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -158,7 +190,7 @@ __global__ void k1_scatter(const part1_aos* __restrict__ a, int64_t np, int TX, 
 	int64_t d = off[t] + slot;
 	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
 	rec20 v = { r.x, r.ux, r.uy, r.uz, r.ix - t * TX };
-	p.rec[d] = v;
+	rec1_store(p.rec, d, v);
 	p.key[d] = (unsigned short) v.cell;
 	if (p.tag) p.tag[d] = tag0 + (int) k;
 }
@@ -169,7 +201,11 @@ static void check_flags(zdev_spec1d* s, unsigned int flags) {
 		        "(current %.2f) and rerun, aborting.\n", s->TX, s->slack);
 		exit(-1);
 	}
-	if (flags & 2u) { fprintf(stderr, "(*error*) zpic-b200: particle migration list overflow (capacity %u), aborting.\n", s->mig_cap); exit(-1); }
+	if (flags & 2u) {
+		fprintf(stderr, "(*error*) zpic-b200: a tile's migrants segment overflowed (1/%d of the tile capacity); raise "
+		        "ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->mig.div, s->slack);
+		exit(-1);
+	}
 }
 
 extern "C" void zdev_spec1d_upload(zdev_spec1d* s, const void* part, int64_t np) {
@@ -235,7 +271,7 @@ __global__ void k1_gather(buf1d p, const int64_t* __restrict__ off, const int* _
 		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
 		wbase = __shfl_sync(0xffffffffu, wbase, 0);
 		if (live) {
-			rec20 v = p.rec[b + k];
+			rec20 v = rec1_load(p.rec, b + k);
 			part1_aos r = { t * TX + v.cell, v.x, v.ux, v.uy, v.uz };
 			int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
 			out[d] = r;
@@ -317,7 +353,7 @@ __global__ void k1_inject_uniform(buf1d p, const int64_t* __restrict__ off, int*
 	for (int k = lane; k < ppc; k += 32) {
 		float a, b, c; normal3_1d(seed, gid0 + k, a, b, c);
 		rec20 v = { (float) ((k + 0.5) / ppc), uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz), lc };
-		p.rec[base + k] = v; p.key[base + k] = (unsigned short) lc;
+		rec1_store(p.rec, base + k, v); p.key[base + k] = (unsigned short) lc;
 		if (p.tag) p.tag[base + k] = (int) (gid0 + k);
 	}
 	if (lc == 0 && lane == 0) { int cx = (t + 1) * TX <= nx ? TX : nx - t * TX; tile_np[t] = cx * ppc; }
@@ -336,72 +372,158 @@ extern "C" void zdev_spec1d_inject_uniform(zdev_spec1d* s, int ppc, const float 
 
 // ------------------------------------------------------------------ the push
 
-struct seg1d { float x0, x1, dx, qvy, qvz; int ix; };
+// one queued remainder of a cell-crossing move (a single in-cell segment, already in the frame of the cell
+// behind the face): 5 words, odd stride = conflict-free shared-memory stores
+struct xq1_entry { int lx; float x0, dx, qvy, qvz; };
 
-// the 5 contributions of one in-cell segment (em1d/particles.c:763-777): Jx[ix]; Jy[ix], Jy[ix+1]; Jz[ix], Jz[ix+1]
-__device__ __forceinline__ void seg1_weights(const seg1d& s, float qnx, float w[5]) {
-	float S0x0 = 1.0f - s.x0, S0x1 = s.x0, S1x0 = 1.0f - s.x1, S1x1 = s.x1;
-	w[0] = qnx * s.dx;
-	w[1] = s.qvy * (S0x0 + S1x0 + (S0x0 - S1x0) / 2.0f);
-	w[2] = s.qvy * (S0x1 + S1x1 + (S0x1 - S1x1) / 2.0f);
-	w[3] = s.qvz * (S0x0 + S1x0 + (S0x0 - S1x0) / 2.0f);
-	w[4] = s.qvz * (S0x1 + S1x1 + (S0x1 - S1x1) / 2.0f);
+// The five current contributions of an in-cell segment x0 -> x1 (em1d/particles.c:763-777):
+// Jx[ix]; Jy[ix], Jy[ix+1]; Jz[ix], Jz[ix+1], with qvy, qvz already halved and scaled to the segment:
+//   S0x0 + S1x0 + (S0x0 - S1x0)/2 = 1.5 (1-x0) + 0.5 (1-x1) = 2 - (1.5 x0 + 0.5 x1)
+// J is compared by tolerance (summation order), so this uses fused multiply-adds.
+__device__ __forceinline__ void seg1_weights(float x0, float x1, float dx, float qvy, float qvz, float qnx, float w[5]) {
+	const float a1 = __fmaf_rn(1.5f, x0, 0.5f * x1), a0 = 2.0f - a1;
+	w[0] = qnx * dx;
+	w[1] = qvy * a0; w[2] = qvy * a1;
+	w[3] = qvz * a0; w[4] = qvz * a1;
 }
+// scatter into the global J grid (L2 reductions); c = cell of the segment
 __device__ __forceinline__ void red1(f3* __restrict__ c, const float w[5]) {
 	atomicAdd(&c[0].x, w[0]);
 	atomicAdd(&c[0].y, w[1]); atomicAdd(&c[1].y, w[2]);
 	atomicAdd(&c[0].z, w[3]); atomicAdd(&c[1].z, w[4]);
 }
-
-struct xq1_entry { int ix, di; float x0, dx, qvy, qvz; };
-
-// split a cell-crossing move into its two segments (em1d/particles.c:723-757) and deposit both
-__device__ __forceinline__ void drain1(const xq1_entry* q, int n, int lane, f3* __restrict__ J, float qnx) {
-	if (lane >= n) return;
-	xq1_entry e = q[lane];
-	seg1d a, b;
-	a.x0 = e.x0; a.dx = e.dx; a.x1 = e.x0 + e.dx; a.qvy = e.qvy * 0.5f; a.qvz = e.qvz * 0.5f; a.ix = e.ix;
-	const int ib = (e.di == 1);
-	const float delta = (e.x0 + e.dx - ib) / e.dx;
-	b.x0 = 1 - ib; b.x1 = (e.x0 + e.dx) - e.di; b.dx = e.dx * delta; b.ix = e.ix + e.di;
-	b.qvy = a.qvy * delta; b.qvz = a.qvz * delta;
-	a.x1 = ib; a.dx *= (1.0f - delta); a.qvy *= (1.0f - delta); a.qvz *= (1.0f - delta);
+// Deposit up to 32 queued remainders, one per lane.  The queue is filled in sorted cell order, so entries with
+// the same destination cell sit next to each other (all of them, when the species drifts one way): combine
+// each run with a segmented warp scan and issue the five L2 reductions once per run - 32 lanes hammering the
+// same five addresses serialise in the L2 atomic unit.
+__device__ __forceinline__ void drain1(const xq1_entry* q, int n, int lane, f3* __restrict__ J0, float qnx) {
+	const bool act = lane < n;
 	float w[5];
-	seg1_weights(a, qnx, w); red1(J + a.ix + 1, w);
-	seg1_weights(b, qnx, w); red1(J + b.ix + 1, w);
+	int key = 0x7fffffff;
+	if (act) {
+		const xq1_entry e = q[lane];
+		seg1_weights(e.x0, e.x0 + e.dx, e.dx, e.qvy, e.qvz, qnx, w);
+		key = e.lx;
+	} else {
+		#pragma unroll
+		for (int k = 0; k < 5; k++) w[k] = 0.0f;
+	}
+	const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+	const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+	const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const bool take = (lane - d) >= start;
+		#pragma unroll
+		for (int k = 0; k < 5; k++) { float u = __shfl_up_sync(0xffffffffu, w[k], d); if (take) w[k] += u; }
+	}
+	const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+	if (tail && act) red1(J0 + key, w);
 }
 
-// dynamic shared memory: perm[max_cap] ints, then 6 field planes of (TX+2) floats, then cnt[TX]
+// Sum acc[0..4] over the 32 lanes with the transposed butterfly of the 2-D kernel (slots 5..7 are zero) and
+// add the totals to cell `cell` of the tile: lane 4*k ends up with contribution k.
+__device__ __forceinline__ void flush_cell1(const float acc[5], int cell, int lane, f3* __restrict__ J0) {
+	const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+	// stage 1 (xor 16): pairs (0,4) (1,5) (2,6) (3,7) with 5..7 = 0
+	float v4[4];
+	{
+		float send = b16 ? acc[0] : acc[4], keep = b16 ? acc[4] : acc[0];
+		v4[0] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+		#pragma unroll
+		for (int q = 1; q < 4; q++) {
+			float s2 = b16 ? acc[q] : 0.0f, k2 = b16 ? 0.0f : acc[q];
+			v4[q] = k2 + __shfl_xor_sync(0xffffffffu, s2, 16);
+		}
+	}
+	float v2[2], v1;
+	#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		float send = b8 ? v4[q] : v4[q + 2], keep = b8 ? v4[q + 2] : v4[q];
+		v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+	}
+	{
+		float send = b4 ? v2[0] : v2[1], keep = b4 ? v2[1] : v2[0];
+		v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+	}
+	v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+	v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+	const int k = lane >> 2;
+	if ((lane & 3) == 0 && k < 5) {
+		const int comp = (k == 0) ? 0 : ((k < 3) ? 1 : 2);
+		const int right = (k == 2) | (k == 4);
+		atomicAdd(reinterpret_cast<float*>(J0 + cell + right) + comp, v1);
+	}
+}
+
+struct pair1_rec { f2 x, ux, uy, uz; int ca, cb, ta, tb; };
+
+// dynamic shared memory of k_push1d: [keys during the sort | field pairs + queues afterwards][perm][raw planes]
+static size_t push1_smem_front(int TX, int max_cap) {
+	size_t late = (size_t) 6 * (TX + 2) * 8 + (size_t) P1_WARPS * XQ1_CAP * sizeof(xq1_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	late = (late + 15) & ~(size_t) 15;
+	return late > keys ? late : keys;
+}
+static size_t push1_smem_bytes(int TX, int max_cap) {
+	return push1_smem_front(TX, max_cap) + (((size_t) max_cap * 2 + 15) & ~(size_t) 15) + (size_t) 6 * (TX + 2) * 4;
+}
+
+template <bool TAGS>
 __global__ void __launch_bounds__(P1_THREADS, 2)
 k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np, int* __restrict__ tile_np_out,
-         rec20* __restrict__ mig, int* __restrict__ mig_tag, unsigned int mig_cap, ctl1d* __restrict__ ctl,
-         const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J, int nx, int TX, int max_cap,
-         zdev_push1d_params prm) {
-	extern __shared__ int smem[];
-	int* s_perm = smem;
-	float* s_fld = reinterpret_cast<float*>(smem + max_cap);
-	int* s_cnt = reinterpret_cast<int*>(s_fld + 6 * (TX + 2));
+         mig1d mig, ctl1d* __restrict__ ctl,
+         const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J, int nx, int TX,
+         zdev_push1d_params prm, unsigned smem_front, unsigned smem_perm) {
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	const int PL = TX + 2;
+	f2* const s_f2 = reinterpret_cast<f2*>(s_dyn);                     // 6 planes of (F[k], F[k+1])
+	xq1_entry* const s_xq = reinterpret_cast<xq1_entry*>(s_dyn + 6 * PL * 8);
+	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
+	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
+	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
+	__shared__ int s_cnt[512], s_cur[512];
 	__shared__ int s_wsum[P1_WARPS];
-	__shared__ xq1_entry s_xq[P1_WARPS][XQ1_CAP];
+	__shared__ int s_nmig, s_done;
+	__shared__ __align__(8) unsigned long long s_bar;
 
 	const int t = blockIdx.x, x0 = t * TX, cx = min(TX, nx - x0);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
-	const int PL = TX + 2;
 
+	if (threadIdx.x == 0) {
+		s_nmig = 0; s_done = 0;
+		mbar_init(&s_bar, 1);
+		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
+	}
 	for (int k = threadIdx.x; k < cx + 2; k += P1_THREADS) {        // cells x0-1 .. x0+cx
 		f3 e = E[x0 + k], b = B[x0 + k];
-		s_fld[k] = e.x; s_fld[k + PL] = e.y; s_fld[k + 2 * PL] = e.z;
-		s_fld[k + 3 * PL] = b.x; s_fld[k + 4 * PL] = b.y; s_fld[k + 5 * PL] = b.z;
+		s_raw[k] = e.x; s_raw[k + PL] = e.y; s_raw[k + 2 * PL] = e.z;
+		s_raw[k + 3 * PL] = b.x; s_raw[k + 4 * PL] = b.y; s_raw[k + 5 * PL] = b.z;
 	}
 	for (int k = threadIdx.x; k < TX; k += P1_THREADS) s_cnt[k] = 0;
 	__syncthreads();
+	if (n > 0) mbar_wait(&s_bar, 0);
 
-	// ---- phase A: index sort by cell
-	for (int i = threadIdx.x; i < n; i += P1_THREADS) {
-		unsigned c = A.key[base + i];
-		if (c != KEY1_EMPTY) atomicAdd(&s_cnt[c], 1);
+	// ---- phase A: counting sort of slot indices by cell (see zdev_spec2d.cu: every thread walks its own
+	//      stretch of consecutive keys, an odd number of words long, so that the lanes of a warp are in
+	//      different cells and banks at any moment)
+	// Lane l owns the words [l*S, (l+1)*S) of the key array (S odd: the lanes of a warp read distinct banks
+	// and sit S*2 keys apart, i.e. in different cells as long as a cell holds fewer particles than that);
+	// the warps split every lane's stretch into WARPS consecutive pieces.
+	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	const int ws = (S + P1_WARPS - 1) / P1_WARPS;
+	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
+	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
+			if (c0 != KEY1_EMPTY) atomicAdd(&s_cnt[c0], 1);
+			if (c1 != KEY1_EMPTY) atomicAdd(&s_cnt[c1], 1);
+		}
 	}
 	__syncthreads();
 	int nlive;
@@ -416,93 +538,76 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		#pragma unroll
 		for (int w = 0; w < P1_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
 		const int ex = woff + incl - v;
-		if (i0 < TX) s_cnt[i0] = ex;
-		if (i0 + 1 < TX) s_cnt[i0 + 1] = ex + a;
+		if (i0 < TX) s_cur[i0] = ex;
+		if (i0 + 1 < TX) s_cur[i0 + 1] = ex + a;
 		nlive = tot;
 		__syncthreads();
 	}
-	for (int i = threadIdx.x; i < n; i += P1_THREADS) {
-		unsigned c = A.key[base + i];
-		if (c != KEY1_EMPTY) s_perm[atomicAdd(&s_cnt[c], 1)] = i;
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
+			if (c0 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
+			if (c1 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
+		}
+	}
+	__syncthreads();                                    // the keys are dead: their bytes become field pairs + queues
+	// ---- the fields as (F[k], F[k+1]) pairs: one LDS.64 per component and particle
+	for (int k = threadIdx.x; k < 6 * PL; k += P1_THREADS) {
+		const int pl = k / PL, o = k - pl * PL;
+		const int o1 = (o + 1 < PL) ? k + 1 : k;
+		s_f2[k] = mk2(s_raw[k], s_raw[o1]);
 	}
 	__syncthreads();
 
-	// ---- phase B
-	xq1_entry* xq = s_xq[warp];
+	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
+	//      owns the particles l and l+32 of the block); no block barriers from here on
+	xq1_entry* const xq = s_xq + warp * XQ1_CAP;
+	const unsigned lt = (1u << lane) - 1u;
 	int nxq = 0;
 	float energy = 0.0f;
-	f3* const J0 = J + x0 + 1;
-	const float* Ex = s_fld + 1;          // plane index 0 is cell -1 of the tile
-	const int first = (nlive > 0) ? s_perm[0] : 0;
-	rec20 nv; int ntag = 0;
-	{
-		const int pn = warp * 32 + lane;
-		const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
-		nv = A.rec[k];
-		if (A.tag) ntag = A.tag[k];
-	}
-	for (int p0 = warp * 32; p0 < nlive; p0 += P1_THREADS) {
-		const int p = p0 + lane;
-		const bool active = p < nlive;
-		const rec20 v = nv;
-		const int tag = ntag;
-		{
-			const int pn = p + P1_THREADS;
-			const int64_t k = base + ((pn < nlive) ? s_perm[pn] : first);
-			nv = A.rec[k];
-			if (A.tag) ntag = A.tag[k];
-		}
-		const int lx = v.cell;
-		const int key = active ? lx : 0x7fffffff;
-		float x = v.x, ux = v.ux, uy = v.uy, uz = v.uz;
-		float w[5];
-		int fate, ncell = -1, gix = 0;
-		bool crosses;
-		xq1_entry xe;
-		{
-			// interpolate_fld (em1d/particles.c:864-886)
-			const int h = (x < 0.5f) ? 1 : 0;
-			const float w1 = x, w1h = x + (h ? 0.5f : -0.5f);
-			const int i = lx, ih = lx - h;
-			f3 Ep, Bp;
-			Ep.x = Ex[ih] * (1.0f - w1h) + Ex[ih + 1] * w1h;
-			Ep.y = Ex[i + PL] * (1.0f - w1) + Ex[i + 1 + PL] * w1;
-			Ep.z = Ex[i + 2 * PL] * (1.0f - w1) + Ex[i + 1 + 2 * PL] * w1;
-			Bp.x = Ex[i + 3 * PL] * (1.0f - w1) + Ex[i + 1 + 3 * PL] * w1;
-			Bp.y = Ex[ih + 4 * PL] * (1.0f - w1h) + Ex[ih + 1 + 4 * PL] * w1h;
-			Bp.z = Ex[ih + 5 * PL] * (1.0f - w1h) + Ex[ih + 1 + 5 * PL] * w1h;
-			// Boris (em1d/particles.c:953-1000): same rotation as 2D; energy term u2/(1+gamma)
-			const float en = boris(Ep, Bp, prm.tem, ux, uy, uz);
-			energy += active ? en : 0.0f;
+	f3* const J0 = J + x0 + 1;                                   // cell x0
+	const f2* const F2 = s_f2 + 1;                               // plane index 0 is cell -1 of the tile
+	const float* const Arec = A.rec + (size_t) (base >> 5) * REC1_CHUNK_WORDS;
+	float* const Brec = Bo.rec + (size_t) (base >> 5) * REC1_CHUNK_WORDS;
+	const int chunk = ((nlive + P1_WARPS * 64 - 1) / (P1_WARPS * 64)) * 64;
+	const int pbeg = warp * chunk, pend = min(pbeg + chunk, nlive);
+	const int mig_cap = (int) ((tile_off[t + 1] - base) / mig.div);
+	const int64_t mig_base = base / mig.div;
 
-			const float rg = div_exact(1.0f, sqrt_exact(1.0f + ux * ux + uy * uy + uz * uz));
-			const float dx = prm.dt_dx * rg * ux;
-			float x1 = x + dx;
-			const int di = ltrim(x1);
-			x1 -= di;
-			const float qvy = prm.q * uy * rg, qvz = prm.q * uz * rg;
+	float acc[5];
+	#pragma unroll
+	for (int q = 0; q < 5; q++) acc[q] = 0.0f;
+	int cur = -1;
 
-			crosses = active && (di != 0);
-			xe.ix = x0 + lx; xe.di = di; xe.x0 = x; xe.dx = dx; xe.qvy = qvy; xe.qvz = qvz;
-			seg1d s0; s0.x0 = x; s0.dx = dx; s0.x1 = x + dx; s0.qvy = qvy * 0.5f; s0.qvz = qvz * 0.5f; s0.ix = 0;
-			seg1_weights(s0, prm.qnx, w);
-			const bool zero = crosses || !active;
+	// current of 32 consecutive sorted particles (one per lane): accumulate per lane while the warp stays in
+	// one cell, reduce when it moves on; several cells per 32 lanes: segmented scan
+	auto deposit32 = [&](int key, float (&w)[5], bool act) {
+		const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+		const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) ? (key != cur) : (key != prev));
+		if (heads == 0u) {
 			#pragma unroll
-			for (int q = 0; q < 5; q++) w[q] = zero ? 0.0f : w[q];
-
-			x = x1;
-			int ix = x0 + lx + di - prm.shift_window;
-			fate = active ? 1 : 0;
-			if (prm.absorbing) { if (ix < 0 || ix >= nx) fate = 0; }
-			else ix += ((ix < 0) ? nx : 0) - ((ix >= nx) ? nx : 0);
-			const int nlx = ix - x0;
-			if (fate) { if (nlx < 0 || nlx >= cx) { fate = 2; gix = ix; } else ncell = nlx; }
+			for (int q = 0; q < 5; q++) acc[q] += w[q];
+			return;
 		}
-
-		// current of the non-crossing particles: segmented inclusive scan over runs of equal cell
-		{
-			const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-			const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+		const int b = __ffs(heads) - 1;
+		const bool lo = lane < b;
+		const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
+		if (cur >= 0) {
+			#pragma unroll
+			for (int q = 0; q < 5; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
+			flush_cell1(acc, cur, lane, J0);
+		}
+		if ((heads & (heads - 1u)) == 0u) {
+			#pragma unroll
+			for (int q = 0; q < 5; q++) acc[q] = w[q] * mhi;
+			cur = __shfl_sync(0xffffffffu, key, 31);
+			if (cur >= TX) cur = -1;
+		} else {
+			#pragma unroll
+			for (int q = 0; q < 5; q++) w[q] *= mhi;
 			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
 			#pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
@@ -511,59 +616,201 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				for (int q = 0; q < 5; q++) { float u = __shfl_up_sync(0xffffffffu, w[q], d); if (take) w[q] += u; }
 			}
 			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
-			if (tail && active) red1(J0 + lx, w);
+			if (tail && act && !lo) red1(J0 + key, w);
+			#pragma unroll
+			for (int q = 0; q < 5; q++) acc[q] = 0.0f;
+			cur = -1;
+		}
+	};
+
+	auto load_pair = [&](int pa, pair1_rec& r) {
+		const int ia = s_perm[pa < pend ? pa : pbeg], ib = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const float* qa = Arec + (ia >> 5) * REC1_CHUNK_WORDS + (ia & 31);
+		const float* qb = Arec + (ib >> 5) * REC1_CHUNK_WORDS + (ib & 31);
+		r.x = mk2(qa[0], qb[0]); r.ux = mk2(qa[32], qb[32]); r.uy = mk2(qa[64], qb[64]); r.uz = mk2(qa[96], qb[96]);
+		r.ca = __float_as_int(qa[128]); r.cb = __float_as_int(qb[128]);
+		r.ta = r.tb = 0;
+		if (TAGS) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
+	};
+
+	pair1_rec nv;
+	if (pbeg < pend) load_pair(pbeg + lane, nv);
+
+	for (int p0 = pbeg; p0 < pend; p0 += 64) {
+		const int pa = p0 + lane, pb = pa + 32;
+		const bool actA = pa < pend, actB = pb < pend;
+		const pair1_rec v = nv;
+		if (p0 + 64 < pend) load_pair(pa + 64, nv);        // software pipeline: next iteration's records
+
+		const int lxa = v.ca, lxb = v.cb;
+		f2 x = v.x, ux = v.ux, uy = v.uy, uz = v.uz;
+		f2 dx, qvy, qvz;
+		{
+			// interpolate_fld (em1d/particles.c:864-886): F[i]*(1-w) + F[i+1]*w, the two products as one FFMA2
+			f2 Ex, Ey, Ez, Bx, By, Bz;
+			#pragma unroll
+			for (int h2 = 0; h2 < 2; h2++) {
+				const float xx = h2 ? x.y : x.x;
+				const int lx = h2 ? lxb : lxa;
+				const int h = (xx < 0.5f) ? 1 : 0;
+				const float w1h = xx + (h ? 0.5f : -0.5f);
+				const f2 wn = mk2(1.0f - xx, xx), wh = mk2(1.0f - w1h, w1h);
+				const int i = lx, ih = lx - h;
+				f2 m;
+				float ex, ey, ez, bx, by, bz;
+				m = mul2(F2[ih], wh);          ex = m.x + m.y;
+				m = mul2(F2[i + PL], wn);      ey = m.x + m.y;
+				m = mul2(F2[i + 2 * PL], wn);  ez = m.x + m.y;
+				m = mul2(F2[i + 3 * PL], wn);  bx = m.x + m.y;
+				m = mul2(F2[ih + 4 * PL], wh); by = m.x + m.y;
+				m = mul2(F2[ih + 5 * PL], wh); bz = m.x + m.y;
+				if (h2) { Ex.y = ex; Ey.y = ey; Ez.y = ez; Bx.y = bx; By.y = by; Bz.y = bz; }
+				else    { Ex.x = ex; Ey.x = ey; Ez.x = ez; Bx.x = bx; By.x = by; Bz.x = bz; }
+			}
+			// Boris (em1d/particles.c:953-1000): same rotation as 2D; energy term u2/(1+gamma)
+			const f2 en = boris2(Ex, Ey, Ez, Bx, By, Bz, prm.tem, ux, uy, uz);
+			energy += (actA ? en.x : 0.0f) + (actB ? en.y : 0.0f);
 		}
 		{
-			const unsigned xm = __ballot_sync(0xffffffffu, crosses);
-			if (xm) {
-				if (crosses) xq[nxq + __popc(xm & ((1u << lane) - 1))] = xe;
-				nxq += __popc(xm);
+			const f2 usq = add2(add2(add2(bc2(1.0f), mul2(ux, ux)), mul2(uy, uy)), mul2(uz, uz));
+			const f2 rg = div_exact2(bc2(1.0f), sqrt_exact2(usq));
+			dx = mul2(mul2(rg, prm.dt_dx), ux);
+			qvy = mul2(mul2(uy, prm.q), rg);
+			qvz = mul2(mul2(uz, prm.q), rg);
+		}
+		const f2 x1 = add2(x, dx);
+		const int dia = ltrim(x1.x), dib = ltrim(x1.y);
+		const bool xa = actA && dia != 0, xb = actB && dib != 0;
+
+		// first in-cell piece of every move through the lanes (the whole move when no face is crossed)
+		const f2 fx = mk2(dia > 0 ? 1.0f : 0.0f, dib > 0 ? 1.0f : 0.0f);
+		f2 t1 = __fmul2_rn(sub2(fx, x), rcp_approx2(dx));
+		t1.x = dia ? fminf(fmaxf(t1.x, 0.0f), 1.0f) : 1.0f;
+		t1.y = dib ? fminf(fmaxf(t1.y, 0.0f), 1.0f) : 1.0f;
+		const f2 dx0 = __fmul2_rn(dx, t1);
+		f2 xe = add2(x, dx0);
+		xe.x = dia ? fx.x : xe.x; xe.y = dib ? fx.y : xe.y;
+		{
+			const f2 kh = mk2(actA ? 0.5f : 0.0f, actB ? 0.5f : 0.0f);
+			const f2 qy = __fmul2_rn(__fmul2_rn(qvy, kh), t1), qz = __fmul2_rn(__fmul2_rn(qvz, kh), t1);
+			const f2 a1 = fma2(bc2(1.5f), x, __fmul2_rn(bc2(0.5f), xe)), a0 = sub2(bc2(2.0f), a1);
+			const f2 w0 = __fmul2_rn(__fmul2_rn(dx0, mk2(actA ? 1.0f : 0.0f, actB ? 1.0f : 0.0f)), bc2(prm.qnx));
+			const f2 w1 = __fmul2_rn(qy, a0), w2 = __fmul2_rn(qy, a1), w3 = __fmul2_rn(qz, a0), w4 = __fmul2_rn(qz, a1);
+			float w[5];
+			w[0] = w0.x; w[1] = w1.x; w[2] = w2.x; w[3] = w3.x; w[4] = w4.x;
+			deposit32(actA ? lxa : 0x7fffffff, w, actA);
+			w[0] = w0.y; w[1] = w1.y; w[2] = w2.y; w[3] = w3.y; w[4] = w4.y;
+			deposit32(actB ? lxb : 0x7fffffff, w, actB);
+		}
+
+		// --- queue of the remainders (always a single segment in 1D); drain 32 at a time
+		{
+			const unsigned ma = __ballot_sync(0xffffffffu, xa), mb = __ballot_sync(0xffffffffu, xb);
+			if (ma | mb) {
+				if (xa) {
+					const float rem = 1.0f - t1.x;
+					xq1_entry e; e.lx = lxa + dia; e.x0 = 1.0f - fx.x; e.dx = dx.x * rem;
+					e.qvy = qvy.x * 0.5f * rem; e.qvz = qvz.x * 0.5f * rem;
+					xq[nxq + __popc(ma & lt)] = e;
+				}
+				nxq += __popc(ma);
+				if (xb) {
+					const float rem = 1.0f - t1.y;
+					xq1_entry e; e.lx = lxb + dib; e.x0 = 1.0f - fx.y; e.dx = dx.y * rem;
+					e.qvy = qvy.y * 0.5f * rem; e.qvz = qvz.y * 0.5f * rem;
+					xq[nxq + __popc(mb & lt)] = e;
+				}
+				nxq += __popc(mb);
 				__syncwarp();
-				if (nxq >= 32) { drain1(xq + nxq - 32, 32, lane, J, prm.qnx); nxq -= 32; __syncwarp(); }
+				while (nxq >= 32) { drain1(xq + nxq - 32, 32, lane, J0, prm.qnx); nxq -= 32; }
+				__syncwarp();
 			}
 		}
-		if (active) {
-			const int64_t d = base + p;
-			Bo.key[d] = (fate == 1) ? (unsigned short) ncell : (unsigned short) KEY1_EMPTY;
-			if (fate == 1) {
-				rec20 o = { x, ux, uy, uz, ncell };
-				Bo.rec[d] = o;
-				if (Bo.tag) Bo.tag[d] = tag;
-			}
+
+		// --- new positions; survivors go to their sorted slot in B, leavers to the tile's migrants segment
+		const f2 xn = sub2(x1, mk2((float) dia, (float) dib));
+		const int nlxa = lxa + dia - prm.shift_window, nlxb = lxb + dib - prm.shift_window;
+		const bool sta = actA && (unsigned) nlxa < (unsigned) cx, stb = actB && (unsigned) nlxb < (unsigned) cx;
+		if (actA) {
+			float* qd = Brec + (pa >> 5) * REC1_CHUNK_WORDS + (pa & 31);
+			qd[0] = xn.x; qd[32] = ux.x; qd[64] = uy.x; qd[96] = uz.x; qd[128] = __int_as_float(nlxa);
+			Bo.key[base + pa] = sta ? (unsigned short) nlxa : (unsigned short) KEY1_EMPTY;
+			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
-		const unsigned mig_m = __ballot_sync(0xffffffffu, fate == 2);
-		if (mig_m) {
-			unsigned int mbase = 0;
-			if (lane == 0) mbase = atomicAdd(&ctl->n_mig, (unsigned int) __popc(mig_m));
-			mbase = __shfl_sync(0xffffffffu, mbase, 0);
-			if (fate == 2) {
-				unsigned int d = mbase + __popc(mig_m & ((1u << lane) - 1));
-				if (d < mig_cap) { rec20 o = { x, ux, uy, uz, gix }; mig[d] = o; if (mig_tag) mig_tag[d] = tag; }
-				else atomicOr(&ctl->flags, 2u);
+		if (actB) {
+			float* qd = Brec + (pb >> 5) * REC1_CHUNK_WORDS + (pb & 31);
+			qd[0] = xn.y; qd[32] = ux.y; qd[64] = uy.y; qd[96] = uz.y; qd[128] = __int_as_float(nlxb);
+			Bo.key[base + pb] = stb ? (unsigned short) nlxb : (unsigned short) KEY1_EMPTY;
+			if (TAGS) Bo.tag[base + pb] = v.tb;
+		}
+		{
+			const bool la = actA && !sta, lb = actB && !stb;
+			const unsigned ma = __ballot_sync(0xffffffffu, la), mb = __ballot_sync(0xffffffffu, lb);
+			if (ma | mb) {
+				int slot = 0;
+				if (lane == 0) slot = atomicAdd(&s_nmig, __popc(ma) + __popc(mb));
+				slot = __shfl_sync(0xffffffffu, slot, 0);
+				if (la) {
+					const int d = slot + __popc(ma & lt);
+					if (d < mig_cap) {
+						part1_aos r = { x0 + nlxa, xn.x, ux.x, uy.x, uz.x };
+						mig.rec[mig_base + d] = r;
+						if (TAGS) mig.tag[mig_base + d] = v.ta;
+					}
+				}
+				if (lb) {
+					const int d = slot + __popc(ma) + __popc(mb & lt);
+					if (d < mig_cap) {
+						part1_aos r = { x0 + nlxb, xn.y, ux.y, uy.y, uz.y };
+						mig.rec[mig_base + d] = r;
+						if (TAGS) mig.tag[mig_base + d] = v.tb;
+					}
+				}
 			}
 		}
 	}
-	if (nxq) drain1(xq, nxq, lane, J, prm.qnx);
+	if (cur >= 0) flush_cell1(acc, cur, lane, J0);
+	if (nxq) drain1(xq, nxq, lane, J0, prm.qnx);
 
 	double e = (double) energy;
 	for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
 	if (lane == 0 && nlive > 0) atomicAdd(&ctl->energy, e);
-	if (threadIdx.x == 0) tile_np_out[t] = nlive;
+	if (lane == 0) {
+		__threadfence_block();
+		if (atomicAdd(&s_done, 1) == P1_WARPS - 1) {
+			const int nm = atomicAdd(&s_nmig, 0);
+			if (nm > mig_cap) atomicOr(&ctl->flags, 2u);
+			mig.np[t] = min(nm, mig_cap);
+			tile_np_out[t] = nlive;
+		}
+	}
 }
 
-__global__ void k1_migrate(buf1d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, const rec20* __restrict__ mig,
-                           const int* __restrict__ mig_tag, unsigned int mig_cap, ctl1d* __restrict__ ctl, int TX) {
-	unsigned int n = ctl->n_mig;
-	if (n > mig_cap) n = mig_cap;
-	for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-		rec20 v = mig[k];
-		int t = v.cell / TX;
-		int slot = atomicAdd(&tile_np[t], 1);
-		int64_t d = tile_off[t] + slot;
-		if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
-		v.cell -= t * TX;
-		p.rec[d] = v; p.key[d] = (unsigned short) v.cell;
-		if (p.tag) p.tag[d] = mig_tag[k];
+// Boundary conditions for the particles that left their tile (em1d/particles.c:1044-1060: absorbing under a
+// moving window or open boundaries, else periodic), then append them to their destination tiles.
+__global__ void k1_migrate(buf1d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig1d mig,
+                           ctl1d* __restrict__ ctl, int TX, int ntiles, int nx, int absorbing) {
+	const int lane = threadIdx.x & 31;
+	const int nwarp = (gridDim.x * blockDim.x) >> 5;
+	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
+		const int n = mig.np[ts];
+		const int64_t mb = tile_off[ts] / mig.div;
+		for (int k = lane; k < n; k += 32) {
+			part1_aos r = mig.rec[mb + k];
+			int ix = r.ix;
+			if (ix < 0 || ix >= nx) {
+				if (absorbing) continue;
+				ix += (ix < 0) ? nx : -nx;
+			}
+			int t = ix / TX;
+			int slot = atomicAdd(&tile_np[t], 1);
+			int64_t d = tile_off[t] + slot;
+			if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
+			rec20 v = { r.x, r.ux, r.uy, r.uz, ix - t * TX };
+			rec1_store(p.rec, d, v);
+			p.key[d] = (unsigned short) v.cell;
+			if (p.tag) p.tag[d] = mig.tag[mb + k];
+		}
 	}
 }
 
@@ -601,10 +848,11 @@ extern "C" void zdev_spec1d_advance(zdev_spec1d* s, zdev_grid1d* grid, zdev_grid
 	}
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl1d), zdev_strm));
 	if (!s->cap_total) return;
-	size_t smem = (size_t) s->max_cap * sizeof(int) + (size_t) 6 * (s->TX + 2) * sizeof(float) + (size_t) s->TX * sizeof(int);
+	size_t smem = push1_smem_bytes(s->TX, s->max_cap);
 	static size_t configured = 0;
 	if (smem > configured) {
-		ZDEV_CHECK(cudaFuncSetAttribute(k_push1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		ZDEV_CHECK(cudaFuncSetAttribute(k_push1d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		ZDEV_CHECK(cudaFuncSetAttribute(k_push1d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		configured = smem;
 	}
 	int slot = -1;
@@ -614,12 +862,17 @@ extern "C" void zdev_spec1d_advance(zdev_spec1d* s, zdev_grid1d* grid, zdev_grid
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV1_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
-	ZDEV_LAUNCH(k_push1d, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->mig_tag,
-	            s->mig_cap, s->ctl, zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, s->max_cap, *prm);
+	const unsigned front = (unsigned) push1_smem_front(s->TX, s->max_cap), permb = (unsigned) (((size_t) s->max_cap * 2 + 15) & ~(size_t) 15);
+	if (s->track_ids)
+		ZDEV_LAUNCH(k_push1d<true>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
+		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
+	else
+		ZDEV_LAUNCH(k_push1d<false>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
+		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 	{ buf1d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
-	ZDEV_LAUNCH(k1_migrate, 2 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->mig_tag, s->mig_cap, s->ctl, s->TX);
+	ZDEV_LAUNCH(k1_migrate, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl, s->TX, s->ntiles, s->nx, prm->absorbing);
 	if (prm->absorbing) s->ids_valid = 0;
 }
 
@@ -644,7 +897,7 @@ __global__ void k1_deposit_charge(buf1d p, const int64_t* __restrict__ off, cons
 	int64_t b = off[t];
 	for (int k = threadIdx.x; k < n; k += blockDim.x) {
 		if (p.key[b + k] == KEY1_EMPTY) continue;
-		rec20 v = p.rec[b + k];
+		rec20 v = rec1_load(p.rec, b + k);
 		int idx = t * TX + v.cell;
 		atomicAdd(&rho[idx], (1.0f - v.x) * q);
 		atomicAdd(&rho[idx + 1], (v.x) * q);

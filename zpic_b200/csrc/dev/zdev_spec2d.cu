@@ -40,6 +40,7 @@
 #include "zdev_common.cuh"
 #include "pic2d_core.cuh"
 #include "pic2d_packed.cuh"
+#include "zdev_tma.cuh"
 #include <vector>
 #include <cstring>
 
@@ -694,24 +695,6 @@ static size_t push_smem_bytes(int TX, int TY, int max_cap) {
 	return push_smem_front(TX, TY, max_cap) + perm + 6 * plane * 4;
 }
 
-// --- TMA bulk copy (global -> shared, completion on an mbarrier): the tile's key segment is fetched by
-//     one thread while the CTA stages the fields
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-	             :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-	asm volatile("{\n.reg .pred p;\nWAIT_%=:\n"
-	             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	             "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(bar)), "r"(phase) : "memory");
-}
-
 // One CTA per tile.  Dynamic shared memory: the tile's keys during the sort, afterwards the corner tile
 // (float4 x 6 planes) and the warps' queues in the same bytes; perm[max_cap] (16-bit slot indices); the raw
 // field planes.
@@ -769,12 +752,16 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	//      keys: at any moment the lanes of a warp are a stretch apart, i.e. in different cells, and the
 	//      atomics spread over the counters.  Stretches are an odd number of 32-bit words long, so the
 	//      lanes also read distinct banks.  Plain uniform loops: no votes, nothing divergent.
-	const int wpt = (((n + PUSH_THREADS - 1) / PUSH_THREADS + 1) >> 1) | 1;     // words (key pairs) per thread
-	const int k0 = threadIdx.x * wpt * 2;
-	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + threadIdx.x * wpt;
+	// Lane l owns the words [l*S, (l+1)*S) of the key array (S odd: the lanes of a warp read distinct banks
+	// and sit S*2 keys apart, i.e. in different cells as long as a cell holds fewer particles than that);
+	// the warps split every lane's stretch into WARPS consecutive pieces.
+	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	const int ws = (S + PUSH_WARPS - 1) / PUSH_WARPS;
+	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
+	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
 	#pragma unroll 4
-	for (int j = 0; j < wpt; j++) {
-		const int i = k0 + 2 * j;
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
 		if (i < n) {
 			const unsigned two = s_key2[j];
 			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
@@ -799,8 +786,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		__syncthreads();
 	}
 	#pragma unroll 4
-	for (int j = 0; j < wpt; j++) {
-		const int i = k0 + 2 * j;
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
 		if (i < n) {
 			const unsigned two = s_key2[j];
 			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
