@@ -44,6 +44,27 @@ def test_twostream_one_step_bit_exact(ours1, ref1):
     assert np.abs(sa["J"] - sb["J"]).max() < 1e-6 * 0.2
 
 
+@pytest.mark.parametrize("tile", [512, 32, 7])
+def test_tile_sizes_bit_exact_and_conserving(ours1, ref1, tile, monkeypatch):
+    """tiles of 512 / 32 / 7 cells (the size is normally picked from the particles per cell; 7 exercises a
+    partial last tile and many tile-to-tile migrations): one bit-exact step, then 20 more"""
+    monkeypatch.setenv("ZPIC_TILE_X1D", str(tile))
+    a, b = H1.twostream(ours1, ppc=64, n_sort=0), H1.twostream(ref1, ppc=64, n_sort=0)
+    a.iter(1)
+    b.iter(1)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert np.array_equal(sa["parts"][k].view(np.uint8), sb["parts"][k].view(np.uint8))
+    a.iter(20)
+    b.iter(20)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert sa["np"][k] == sb["np"][k]
+        assert (sa["parts"][k]["ix"] != sb["parts"][k]["ix"]).sum() <= 2
+        assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL
+    assert np.abs(sa["J"] - sb["J"]).max() < TOL * 0.2
+
+
 def test_twostream_shipped_deck_100_steps(ours1, ref1):
     """config 5 parity case: em1d/input/twostream.c as shipped (120 cells, 2 x 500 ppc)"""
     a, b = H1.twostream(ours1, n_sort=0), H1.twostream(ref1, n_sort=0)

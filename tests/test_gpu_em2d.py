@@ -138,6 +138,43 @@ def test_weibel_one_step_integer_state_bit_exact(ours, ref):
         assert abs(sa["energy"][k] - sb["energy"][k]) <= TOL_ENERGY * abs(sb["energy"][k])
 
 
+@pytest.mark.parametrize("tile", [(16, 16), (16, 8), (8, 8), (8, 4), (4, 4)])
+def test_every_tile_shape_is_bit_exact_and_conserves_particles(ours, ref, tile, monkeypatch):
+    """every instantiation of the push kernel (the tile shape is normally picked from the particles per
+    cell): bit-exact step 1 with cell crossings, then 10 more steps through tile borders and the
+    periodic wrap"""
+    monkeypatch.setenv("ZPIC_TILE_X", str(tile[0]))
+    monkeypatch.setenv("ZPIC_TILE_Y", str(tile[1]))
+    a = H.weibel(ours, n=40, ppc=(8, 8), n_sort=0)      # 40 is not a multiple of 16: partial edge tiles
+    b = H.weibel(ref, n=40, ppc=(8, 8), n_sort=0)
+    tx, ty = C.c_int(), C.c_int()
+    from zpic_b200._lib import spec_handle
+    ours.zdev_spec2d_tile_info(spec_handle(ours, C.byref(a.species[0])), C.byref(tx), C.byref(ty), None, None)
+    assert (tx.value, ty.value) == tile
+    a.iter(1)
+    b.iter(1)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert np.array_equal(sa["parts"][k].view(np.uint8), sb["parts"][k].view(np.uint8))
+    a.iter(10)
+    b.iter(10)
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert sa["np"][k] == sb["np"][k] == 40 * 40 * 64
+        same = (sa["parts"][k]["ix"] == sb["parts"][k]["ix"]) & (sa["parts"][k]["iy"] == sb["parts"][k]["iy"])
+        assert (~same).sum() <= 3
+        for q in ("ux", "uy", "uz"):
+            assert H.rel_l2(sa["parts"][k][q], sb["parts"][k][q]) < TOL_FIELD, q
+    # At 64 ppc the two counter-streaming species' currents (|Jz| ~ 0.6 each) cancel to noise level and the
+    # fields are still ~1e-3: measure the summation-order noise on the scale of ONE species' current
+    # (and of its time integral for E, B), not of the cancelled sum.
+    assert np.abs(sa["J"] - sb["J"]).max() < TOL_FIELD * 0.6
+    for q in ("E", "B"):
+        assert np.abs(sa[q] - sb[q]).max() < TOL_FIELD * 0.6 * 11 * 0.07, q
+    a.delete()
+    b.delete()
+
+
 def test_weibel_cells_cross_after_a_few_steps(ours, ref):
     """after 12 steps thousands of particles changed cell and wrapped around the box"""
     res = _compare_weibel(ours, ref, 64, (2, 2), 12, [12])
