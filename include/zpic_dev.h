@@ -54,6 +54,10 @@ void zdev_mem_info( size_t* free_b, size_t* total_b );
 void zdev_set_stream( void* stream );
 /* write `bytes` of scratch (>= L2 size) to evict the L2 between timed steps */
 void zdev_flush_l2( void );
+/* page-lock a host buffer that is transferred repeatedly (>= 1 MB; done once per buffer, silently skipped if it
+ * cannot be locked); the owner calls zdev_host_unpin before freeing it */
+void zdev_host_pin( const void* host_ptr, size_t bytes );
+void zdev_host_unpin( const void* host_ptr );
 
 /* ---------------------------------------------------------- em2d grids (E,B,J) */
 

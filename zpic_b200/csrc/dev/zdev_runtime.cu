@@ -77,3 +77,21 @@ extern "C" void zdev_flush_l2(void) {
 	}
 	ZDEV_CHECK(cudaMemsetAsync(zdev_flush_buf, 0, zdev_flush_bytes, zdev_strm));
 }
+
+// Host buffers that are copied to / from the device again and again (the E, B, J mirrors of a simulation) are
+// page-locked on first use: a pageable cudaMemcpy runs at ~6 GB/s on this box, a pinned one at PCIe speed.
+// The owner of the buffer calls zdev_host_unpin() before freeing it.
+struct zdev_pin { const void* ptr; size_t bytes; };
+static zdev_pin zdev_pins[32];
+extern "C" void zdev_host_pin(const void* ptr, size_t bytes) {
+	if (!ptr || bytes < ((size_t) 1 << 20)) return;
+	zdev_pin* slot = nullptr;
+	for (auto& p : zdev_pins) { if (p.ptr == ptr) return; if (!p.ptr && !slot) slot = &p; }
+	if (!slot) return;
+	if (cudaHostRegister((void*) ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return; }
+	slot->ptr = ptr; slot->bytes = bytes;
+}
+extern "C" void zdev_host_unpin(const void* ptr) {
+	if (!ptr) return;
+	for (auto& p : zdev_pins) if (p.ptr == ptr) { cudaHostUnregister((void*) ptr); p.ptr = nullptr; p.bytes = 0; }
+}

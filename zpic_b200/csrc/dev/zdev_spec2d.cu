@@ -1195,22 +1195,43 @@ extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* n
 
 // ------------------------------------------------------------------ charge deposit
 
-// reference spec_deposit_charge, em2d/particles.c:1289-1324 (node centred, linear)
+// reference spec_deposit_charge, em2d/particles.c:1289-1324 (node centred, linear).  The slots of a tile are
+// almost in cell order: the four weights of neighbouring slots in the same cell are combined with a segmented
+// warp scan and only the last lane of a run issues the four L2 reductions (one per particle and node is
+// ~30x slower: 64 particles of a cell serialise on the same four addresses).
 __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np,
                                  float* __restrict__ rho, int nrow, float q, int TX, int TY, int ntx) {
-	int t = blockIdx.x;
-	int n = tile_np[t];
-	int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
-	int64_t b = off[t];
-	for (int k = threadIdx.x; k < n; k += blockDim.x) {
-		if (p.key[b + k] == KEY_EMPTY) continue;
-		rec24 v = rec_load(p.rec, b + k);
-		int idx = (x0 + (v.cell & 0xffff)) + nrow * (y0 + (v.cell >> 16));
-		float w1 = v.x, w2 = v.y;
-		atomicAdd(&rho[idx], (1.0f - w1) * (1.0f - w2) * q);
-		atomicAdd(&rho[idx + 1], (w1) * (1.0f - w2) * q);
-		atomicAdd(&rho[idx + nrow], (1.0f - w1) * (w2) * q);
-		atomicAdd(&rho[idx + 1 + nrow], (w1) * (w2) * q);
+	const int t = blockIdx.x, lane = threadIdx.x & 31;
+	const int n = tile_np[t];
+	const int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
+	const int64_t b = off[t];
+	for (int k0 = (threadIdx.x >> 5) * 32; k0 < n; k0 += blockDim.x) {
+		const int k = k0 + lane;
+		const unsigned key = (k < n) ? p.key[b + k] : KEY_EMPTY;
+		float w[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+		int idx = 0;
+		if (key != KEY_EMPTY) {
+			const float* r = p.rec + rec_word(b + k);
+			const float w1 = r[0], w2 = r[32];
+			const int cell = __float_as_int(r[160]);
+			idx = (x0 + (cell & 0xffff)) + nrow * (y0 + (cell >> 16));
+			w[0] = (1.0f - w1) * (1.0f - w2) * q; w[1] = (w1) * (1.0f - w2) * q;
+			w[2] = (1.0f - w1) * (w2) * q;        w[3] = (w1) * (w2) * q;
+		}
+		const unsigned prev = __shfl_up_sync(0xffffffffu, key, 1);
+		const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+		const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+		#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const bool take = (lane - d) >= start;
+			#pragma unroll
+			for (int c = 0; c < 4; c++) { float u = __shfl_up_sync(0xffffffffu, w[c], d); if (take) w[c] += u; }
+		}
+		const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+		if (tail && key != KEY_EMPTY) {
+			atomicAdd(&rho[idx], w[0]); atomicAdd(&rho[idx + 1], w[1]);
+			atomicAdd(&rho[idx + nrow], w[2]); atomicAdd(&rho[idx + 1 + nrow], w[3]);
+		}
 	}
 }
 __global__ void k_charge_fold(float* __restrict__ rho, int nx, int ny, int mode) {
@@ -1220,18 +1241,32 @@ __global__ void k_charge_fold(float* __restrict__ rho, int nx, int ny, int mode)
 	else           { if (k <= nx) rho[k] += rho[k + (size_t) ny * nrow]; }                   // y fold
 }
 
+// scratch of the charge diagnostic, kept between calls: device grid + pinned host staging (a pageable 4 MB
+// copy each way and a cudaMalloc/cudaFree pair per call cost 10x the kernel)
+static float* g_rho_dev = nullptr;
+static float* g_rho_pin = nullptr;
+static size_t g_rho_cap = 0;
+
 extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_window, float* charge) {
 	size_t n = (size_t) (s->nx + 1) * (s->ny + 1);
-	float* d_rho; ZDEV_CHECK(cudaMalloc(&d_rho, n * sizeof(float)));
-	ZDEV_CHECK(cudaMemcpyAsync(d_rho, charge, n * sizeof(float), cudaMemcpyHostToDevice, zdev_strm));
+	if (n > g_rho_cap) {
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(g_rho_dev); cudaFreeHost(g_rho_pin);
+		ZDEV_CHECK(cudaMalloc(&g_rho_dev, n * sizeof(float)));
+		ZDEV_CHECK(cudaHostAlloc((void**) &g_rho_pin, n * sizeof(float), cudaHostAllocPortable));
+		g_rho_cap = n;
+	}
+	float* d_rho = g_rho_dev;
+	memcpy(g_rho_pin, charge, n * sizeof(float));
+	ZDEV_CHECK(cudaMemcpyAsync(d_rho, g_rho_pin, n * sizeof(float), cudaMemcpyHostToDevice, zdev_strm));
 	if (s->cap_total)
 		ZDEV_LAUNCH(k_deposit_charge, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_rho, s->nx + 1, q,
 		            s->TX, s->TY, s->ntx);
 	if (!moving_window) ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->ny + 1, 128), 128, 0, d_rho, s->nx, s->ny, 0);
 	ZDEV_LAUNCH(k_charge_fold, zdev_div_up(s->nx + 1, 128), 128, 0, d_rho, s->nx, s->ny, 1);
-	ZDEV_CHECK(cudaMemcpyAsync(charge, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaMemcpyAsync(g_rho_pin, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-	cudaFree(d_rho);
+	memcpy(charge, g_rho_pin, n * sizeof(float));
 }
 
 // ------------------------------------------------------------------ slab decomposition support

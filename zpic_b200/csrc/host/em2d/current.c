@@ -36,6 +36,7 @@ void current_new( t_current *current, int nx[], float box[], float dt )
 void current_delete( t_current *current )
 {
 	zb_grid_drop_cur(current);
+	if (zdev_ready()) zdev_host_unpin(current->J_buf);
 	free(current->J_buf);
 	current->J_buf = NULL;
 }

@@ -59,6 +59,7 @@ void emf_new( t_emf *emf, int nx[], float box[], const float dt )
 void emf_delete( t_emf *emf )
 {
 	zb_grid_drop_emf(emf);
+	if (zdev_ready()) { zdev_host_unpin(emf->E_buf); zdev_host_unpin(emf->B_buf); }
 	free(emf->E_buf); free(emf->B_buf);
 	emf->E_buf = emf->B_buf = NULL;
 	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.E_part_buf);

@@ -109,9 +109,17 @@ void zb_spec_drop( const t_species* spec ) {
 
 /* ---------------------------------------------------------------- coherence */
 
+/* the E, B mirrors are transferred again and again: page-lock them once (unpinned by emf_delete) */
+static void zb_pin_emf( const t_emf* emf ) {
+	const size_t bytes = (size_t) (emf->nx[0] + 3) * (emf->nx[1] + 3) * sizeof(float3);
+	zdev_host_pin(emf->E_buf, bytes);
+	zdev_host_pin(emf->B_buf, bytes);
+}
+
 void zb_emf_to_device( t_emf* emf ) {
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	if (e->eb_dev_stale) {
+		zb_pin_emf(emf);
 		zdev_grid2d_upload(zb_dev(e), ZDEV_E, (const float*) emf->E_buf);
 		zdev_grid2d_upload(zb_dev(e), ZDEV_B, (const float*) emf->B_buf);
 		e->eb_dev_stale = 0;
@@ -123,6 +131,7 @@ void zb_emf_to_host( const t_emf* emf ) {
 	zb_grid* e = zb_grid_of_emf(emf, 0);
 	if (!e) return;
 	if (e->eb_host_stale) {
+		zb_pin_emf(emf);
 		zdev_grid2d_download(zb_dev(e), ZDEV_E, (float*) emf->E_buf);
 		zdev_grid2d_download(zb_dev(e), ZDEV_B, (float*) emf->B_buf);
 		e->eb_host_stale = 0;
@@ -139,6 +148,7 @@ void zb_emf_to_host( const t_emf* emf ) {
 void zb_cur_to_host( const t_current* cur ) {
 	zb_grid* e = zb_grid_of_cur(cur, 0);
 	if (!e || !e->j_host_stale) return;
+	zdev_host_pin(cur->J_buf, (size_t) (cur->nx[0] + 3) * (cur->nx[1] + 3) * sizeof(float3));   /* unpinned by current_delete */
 	zdev_grid2d_download(zb_dev(e), ZDEV_J, (float*) cur->J_buf);
 	e->j_host_stale = 0;
 }
