@@ -186,6 +186,10 @@ void zdev_spec2d_fetch( zdev_spec2d* s, double* energy_sum, int64_t* np );
 /* spec_deposit_charge on the device (em2d/particles.c:1289-1324): charge is a host
  * (nx+1)*(ny+1) float array that is ADDED to, like the reference does */
 void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, float* charge );
+/* spec_deposit_pha on the device (em2d/particles.c:1569-1632): quant1/2 = the reference's
+ * X1 (1), X2 (2), U1 (4), U2 (5), U3 (6), pha_buf is a host pha_nx[0]*pha_nx[1] float array that is ADDED to */
+void zdev_spec2d_deposit_pha( zdev_spec2d* s, int quant1, int quant2, const int pha_nx[2], const float pha_range[2][2],
+                              float q, float dx, float dy, float* pha_buf );
 /* Slab decomposition along x (one process per GPU).  After zdev_spec2d_advance
  * with slab_left/right set, the particles that crossed a slab edge sit in two device lists of
  * 28-byte t_part records whose ix is already expressed in the neighbour's frame (all slabs

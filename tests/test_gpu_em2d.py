@@ -258,6 +258,32 @@ def test_charge_conservation_residual(ours, ref):
     b.delete()
 
 
+@pytest.mark.parametrize("quants,nx,rng", [
+    ((1, 6), (64, 32), ((0.0, 3.2), (-1.0, 1.0))),          # PHASESPACE(X1, U3) of the shipped Weibel deck: shared-memory path
+    ((4, 5), (256, 192), ((-0.5, 0.5), (-0.5, 0.5))),       # PHASESPACE(U1, U2), 49152 bins: straight to L2
+    ((2, 1), (40, 50), ((0.5, 2.5), (-1.0, 5.0))),          # PHASESPACE(X2, X1) with ranges cutting through the box
+])
+def test_phasespace_density_on_the_device(ours, ref, quants, nx, rng):
+    """spec_deposit_pha after a few steps (the device holds the population: no particle download)"""
+    a, b = H.weibel(ours, n=32, ppc=(4, 4), n_sort=0), H.weibel(ref, n=32, ppc=(4, 4), n_sort=0)
+    a.iter(5)
+    b.iter(5)
+    rep = quants[0] + 16 * quants[1] + 0x2000
+    pnx = (C.c_int * 2)(*nx)
+    prng = ((C.c_float * 2) * 2)((C.c_float * 2)(*rng[0]), (C.c_float * 2)(*rng[1]))
+    out = []
+    for d in (a, b):
+        buf = np.zeros((nx[1], nx[0]), dtype=np.float32)
+        d.lib.spec_deposit_pha(C.byref(d.species[1]), rep, pnx, prng, buf.ctypes.data_as(C.POINTER(C.c_float)))
+        out.append(buf)
+    assert np.abs(out[1]).sum() > 0
+    # same particles (momenta agree to ~1e-7 after 5 steps), different summation order
+    assert np.abs(out[0] - out[1]).max() <= 2e-5 * np.abs(out[1]).max()
+    assert abs(out[0].sum(dtype=np.float64) - out[1].sum(dtype=np.float64)) <= 1e-5 * abs(out[1].sum(dtype=np.float64))
+    a.delete()
+    b.delete()
+
+
 def test_lwfa_moving_window(ours, ref):
     """laser + moving window + absorbing x + compensated smoothing + window injection"""
     kw = dict(nx=(256, 64), box=(5.12, 12.8), dt=0.014, ppc=(2, 2), start=4.0, laser_start=3.5, a0=1.0, n_sort=0)

@@ -1269,6 +1269,86 @@ extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_w
 	memcpy(charge, g_rho_pin, n * sizeof(float));
 }
 
+// ------------------------------------------------------------------ phasespace density
+
+// reference spec_deposit_pha, em2d/particles.c:1569-1632: linear deposit of the charge on a 2-D grid over two of
+// {x1, x2, u1, u2, u3} (axis values as spec_pha_axis :1512-1538).  Grids of up to PHA_SMEM_BINS bins are
+// accumulated per CTA in shared memory and merged with one L2 reduction per touched bin; larger ones go
+// straight to L2.
+#define PHA_SMEM_BINS 8192
+struct pha_params { int q1, q2, n1, n2; float min1, min2, rd1, rd2, q, dx, dy; };
+
+__device__ __forceinline__ float pha_axis(int quant, float x, float y, float ux, float uy, float uz, int ix, int iy, float dx, float dy) {
+	switch (quant) {                      // the reference's X1, X2, U1, U2, U3 (em2d/particles.h:236-240)
+	case 1: return (x + ix) * dx;
+	case 2: return (y + iy) * dy;
+	case 4: return ux;
+	case 5: return uy;
+	default: return uz;
+	}
+}
+
+__global__ void k_deposit_pha(soa2d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np, int ntiles,
+                              float* __restrict__ buf, pha_params a, int TX, int TY, int ntx, int use_smem) {
+	extern __shared__ float s_pha[];
+	const int nbins = a.n1 * a.n2;
+	if (use_smem) {
+		for (int k = threadIdx.x; k < nbins; k += blockDim.x) s_pha[k] = 0.0f;
+		__syncthreads();
+	}
+	float* const dst = use_smem ? s_pha : buf;
+	for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+		const int n = tile_np[t];
+		const int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
+		const int64_t b = off[t];
+		for (int k = threadIdx.x; k < n; k += blockDim.x) {
+			if (p.key[b + k] == KEY_EMPTY) continue;
+			const rec24 v = rec_load(p.rec, b + k);
+			const int ix = x0 + (v.cell & 0xffff), iy = y0 + (v.cell >> 16);
+			const float nx1 = (pha_axis(a.q1, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min1) * a.rd1;
+			const float nx2 = (pha_axis(a.q2, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min2) * a.rd2;
+			const int i1 = (int) (nx1 + 0.5f), i2 = (int) (nx2 + 0.5f);
+			const float w1 = nx1 - i1 + 0.5f, w2 = nx2 - i2 + 0.5f;
+			const int idx = i1 + a.n1 * i2;
+			const bool in1a = (i1 >= 0 && i1 < a.n1), in1b = (i1 + 1 >= 0 && i1 + 1 < a.n1);
+			if (i2 >= 0 && i2 < a.n2) {
+				if (in1a) atomicAdd(&dst[idx], (1.0f - w1) * (1.0f - w2) * a.q);
+				if (in1b) atomicAdd(&dst[idx + 1], w1 * (1.0f - w2) * a.q);
+			}
+			if (i2 + 1 >= 0 && i2 + 1 < a.n2) {
+				if (in1a) atomicAdd(&dst[idx + a.n1], (1.0f - w1) * w2 * a.q);
+				if (in1b) atomicAdd(&dst[idx + a.n1 + 1], w1 * w2 * a.q);
+			}
+		}
+	}
+	if (use_smem) {
+		__syncthreads();
+		for (int k = threadIdx.x; k < nbins; k += blockDim.x) { const float v = s_pha[k]; if (v != 0.0f) atomicAdd(&buf[k], v); }
+	}
+}
+
+extern "C" void zdev_spec2d_deposit_pha(zdev_spec2d* s, int quant1, int quant2, const int pha_nx[2], const float pha_range[2][2],
+                                        float q, float dx, float dy, float* host_buf) {
+	const size_t n = (size_t) pha_nx[0] * pha_nx[1];
+	float* d_buf; ZDEV_CHECK(cudaMalloc(&d_buf, n * sizeof(float)));
+	ZDEV_CHECK(cudaMemcpyAsync(d_buf, host_buf, n * sizeof(float), cudaMemcpyHostToDevice, zdev_strm));
+	if (s->cap_total) {
+		pha_params a;
+		a.q1 = quant1; a.q2 = quant2; a.n1 = pha_nx[0]; a.n2 = pha_nx[1];
+		a.min1 = pha_range[0][0]; a.min2 = pha_range[1][0];
+		a.rd1 = pha_nx[0] / (pha_range[0][1] - pha_range[0][0]);       // float arithmetic as the reference (:1583-1584)
+		a.rd2 = pha_nx[1] / (pha_range[1][1] - pha_range[1][0]);
+		a.q = q; a.dx = dx; a.dy = dy;
+		const int use_smem = n <= PHA_SMEM_BINS;
+		const int grid = s->ntiles < 4 * zdev_num_sm ? s->ntiles : 4 * zdev_num_sm;
+		ZDEV_LAUNCH(k_deposit_pha, grid, 256, use_smem ? n * sizeof(float) : 0, s->p, s->tile_off, s->tile_np, s->ntiles,
+		            d_buf, a, s->TX, s->TY, s->ntx, use_smem);
+	}
+	ZDEV_CHECK(cudaMemcpyAsync(host_buf, d_buf, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	cudaFree(d_buf);
+}
+
 // ------------------------------------------------------------------ slab decomposition support
 
 extern "C" void zdev_spec2d_export_counts(zdev_spec2d* s, int64_t counts[2]) {

@@ -467,11 +467,20 @@ static inline float pha_value( const t_species* spec, const t_part* p, int quant
 	return 0;
 }
 
-/* linear deposit on a 2D phasespace grid (reference :1569-1632) */
+/* linear deposit on a 2D phasespace grid (reference :1569-1632).  When the device holds the current
+   population (any time after the first step) the deposit runs there - no 28 B/particle download; while the
+   host buffer is still the authoritative copy (iteration 0, Species.add) it is done here like the reference. */
 void spec_deposit_pha( const t_species *spec, const int rep_type,
                        const int pha_nx[], const float pha_range[][2], float* buf )
 {
-	zb_spec_to_host(spec);
+	{
+		zb_spec* e = zb_spec_of(spec, 0);
+		if (e && e->host_stale) {
+			zdev_spec2d_deposit_pha(zb_spec_dev(e), rep_type & 0x000F, (rep_type & 0x00F0) >> 4, pha_nx, pha_range,
+			                        spec->q, spec->dx[0], spec->dx[1], buf);
+			return;
+		}
+	}
 
 	const int nrow = pha_nx[0];
 	const int quant1 = rep_type & 0x000F;
