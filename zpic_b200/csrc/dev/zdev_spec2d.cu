@@ -609,7 +609,11 @@ struct push_geom {
 // compare-and-swap loops, 34 vs 50 Gpush/s; a tile of 32-bit coarse+fine fixed-point pairs with native
 // integer atomics 53 vs 56 Gpush/s.)
 struct jtile { float* v; };
+#ifdef ABL_NO_RED      // ablation builds (timing experiments only, results are wrong): ABL_NO_RED, ABL_NO_QUEUE, ABL_NO_DEPOSIT
+__device__ __forceinline__ void jt_add(const jtile& t, int idx, float w) { if (w == 12345.678f) atomicAdd(t.v + idx, w); }
+#else
 __device__ __forceinline__ void jt_add(const jtile& t, int idx, float w) { atomicAdd(t.v + idx, w); }
+#endif
 // the 8 contributions of one segment in cell c (index of its first component), W3 = 3 * row length
 __device__ __forceinline__ void jt_weights(const jtile& t, int c, int W3, const float w[8]) {
 	jt_add(t, c, w[0]);
