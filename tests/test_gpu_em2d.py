@@ -175,6 +175,31 @@ def test_every_tile_shape_is_bit_exact_and_conserves_particles(ours, ref, tile, 
     b.delete()
 
 
+def test_tiles_grow_when_the_plasma_piles_up(ours, ref, monkeypatch):
+    """tiles start with 64 spare slots (ZPIC_TILE_SLACK=1): the first density fluctuation fills one; the
+    particles that find it full are parked, the tile layout grows and they are re-appended before the next
+    push - nothing is lost or delayed"""
+    monkeypatch.setenv("ZPIC_TILE_SLACK", "1.0")
+    a, b = H.weibel(ours, n=64, ppc=(8, 8), n_sort=0), H.weibel(ref, n=64, ppc=(8, 8), n_sort=0)
+    from zpic_b200._lib import spec_handle
+    cap0 = C.c_int64()
+    ours.zdev_spec2d_tile_info(spec_handle(ours, C.byref(a.species[0])), None, None, None, C.byref(cap0))
+    a.iter(25)
+    b.iter(25)
+    cap1 = C.c_int64()
+    ours.zdev_spec2d_tile_info(spec_handle(ours, C.byref(a.species[0])), None, None, None, C.byref(cap1))
+    assert cap1.value > cap0.value, "the deck was meant to overflow a tile"
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert sa["np"][k] == sb["np"][k] == 64 * 64 * 64
+        same = (sa["parts"][k]["ix"] == sb["parts"][k]["ix"]) & (sa["parts"][k]["iy"] == sb["parts"][k]["iy"])
+        assert (~same).sum() <= 3
+        for q in ("ux", "uy", "uz"):
+            assert H.rel_l2(sa["parts"][k][q], sb["parts"][k][q]) < TOL_FIELD, q
+    a.delete()
+    b.delete()
+
+
 def test_weibel_cells_cross_after_a_few_steps(ours, ref):
     """after 12 steps thousands of particles changed cell and wrapped around the box"""
     res = _compare_weibel(ours, ref, 64, (2, 2), 12, [12])

@@ -92,8 +92,9 @@ __device__ __forceinline__ void rec_store(float* __restrict__ rec, int64_t slot,
 struct ctl2d {
 	double energy;                   // sum of utsq/(gamma+1)
 	unsigned long long np;           // live particles after the step
-	unsigned int pad0;
-	unsigned int flags;              // 1: tile capacity overflow, 2: a tile's migrants segment overflowed, 4: export list overflow
+	unsigned int n_ovf;              // entries in the overflow list
+	unsigned int flags;              // 1: some tile was full (particles parked in the overflow list), 2: a tile's migrants
+	                                 // segment overflowed, 4: export list overflow, 8: the overflow list overflowed
 	unsigned int n_exp[2];           // slab mode: particles handed to the left / right neighbour
 	unsigned int pad[2];
 };
@@ -111,6 +112,9 @@ struct zdev_spec2d {
 	int* tile_np_q;                  // device, ntiles: slots in use in q
 	mig2d mig;                       // per-tile migrants segments
 	int64_t mig_cap;                 // total entries allocated in mig.rec
+	part_aos* ovf; int* ovf_tag;     // particles that found their destination tile full (global cell indices):
+	unsigned int ovf_cap;            //   the host grows the tiles and re-appends them before the next push
+	int appended;                    // appends since the last overflow check
 	part_aos* stage; int64_t stage_cap;   // persistent staging for appended host particles
 	part_aos* exp_buf[2];            // slab mode: export lists (AoS, ix already in the neighbour's frame)
 	unsigned int exp_cap;
@@ -241,6 +245,7 @@ static void spec_free_particles(zdev_spec2d* s) {
 	s->exp_cap = 0;
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); }
 	mig_free(s);
+	cudaFree(s->ovf); cudaFree(s->ovf_tag); s->ovf = nullptr; s->ovf_tag = nullptr; s->ovf_cap = 0;
 	s->cap_total = 0;
 }
 
@@ -289,6 +294,9 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	s->cap_total = total;
 	s->max_cap = (int) max_cap;
 	mig_alloc(s, 8);
+	s->ovf_cap = (unsigned int) (total / 32 > (1 << 20) ? total / 32 : (1 << 20));
+	ZDEV_CHECK(cudaMalloc(&s->ovf, (size_t) s->ovf_cap * sizeof(part_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag, (size_t) s->ovf_cap * 4));
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t),
 	                           cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
@@ -303,26 +311,37 @@ __global__ void k_count_tiles(const part_aos* __restrict__ a, int64_t np, int TX
 	atomicAdd(&cnt[a[k].ix / TX + (a[k].iy / TY) * ntx], 1);
 }
 
-// append AoS records to their tiles; tag = tag0 + index when ids are tracked
+// a particle whose destination tile is full: park it (global cell indices) for the host to deal with
+__device__ __forceinline__ void ovf_push(ctl2d* ctl, part_aos* ovf, int* ovf_tag, unsigned int cap, const part_aos& r, int tag) {
+	atomicOr(&ctl->flags, 1u);
+	const unsigned int k = atomicAdd(&ctl->n_ovf, 1u);
+	if (k < cap) { ovf[k] = r; if (ovf_tag) ovf_tag[k] = tag; }
+	else atomicOr(&ctl->flags, 8u);
+}
+
+// append AoS records to their tiles; tag = tags[k] if given, else tag0 + index, when ids are tracked
 __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int TX, int TY, int ntx,
-                                soa2d p, const int64_t* __restrict__ off, int* tile_np, ctl2d* ctl, int tag0) {
+                                soa2d p, const int64_t* __restrict__ off, int* tile_np, ctl2d* ctl, int tag0,
+                                const int* __restrict__ tags, part_aos* ovf, int* ovf_tag, unsigned int ovf_cap) {
 	int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= np) return;
 	part_aos r = a[k];
+	const int tag = tags ? tags[k] : tag0 + (int) k;
 	int tx = r.ix / TX, ty = r.iy / TY, t = tx + ty * ntx;
 	int slot = atomicAdd(&tile_np[t], 1);
 	int64_t d = off[t] + slot;
-	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
+	if (d >= off[t + 1]) { atomicSub(&tile_np[t], 1); ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, tag); return; }
 	const int lx = r.ix - tx * TX, ly = r.iy - ty * TY;
 	rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
 	p.key[d] = (unsigned short) (lx + ly * TX);
-	if (p.tag) p.tag[d] = tag0 + (int) k;
+	if (p.tag) p.tag[d] = tag;
 }
 
+static void spec_resolve_overflow(zdev_spec2d* s);
 static void check_flags(zdev_spec2d* s, unsigned int flags) {
-	if (flags & 1u) {
-		fprintf(stderr, "(*error*) zpic-b200: particle tile capacity exceeded (tile %dx%d cells); "
-		        "raise ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->TX, s->TY, s->slack);
+	if (flags & 8u) {
+		fprintf(stderr, "(*error*) zpic-b200: more than %u particles found their tile full in one step (tile %dx%d cells); "
+		        "raise ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->ovf_cap, s->TX, s->TY, s->slack);
 		exit(-1);
 	}
 	if (flags & 2u) {
@@ -336,10 +355,11 @@ static void check_flags(zdev_spec2d* s, unsigned int flags) {
 	}
 }
 
-static void spec_append_dev(zdev_spec2d* s, const part_aos* d_aos, int64_t np, int tag0) {
+static void spec_append_dev(zdev_spec2d* s, const part_aos* d_aos, int64_t np, int tag0, const int* d_tags = nullptr) {
 	if (np <= 0) return;
 	ZDEV_LAUNCH(k_scatter_tiles, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->TY, s->ntx,
-	            s->p, s->tile_off, s->tile_np, s->ctl, tag0);
+	            s->p, s->tile_off, s->tile_np, s->ctl, tag0, d_tags, s->ovf, s->ovf_tag, s->ovf_cap);
+	s->appended = 1;
 }
 
 // Zero-copy option (ZPIC_ZERO_COPY_MIN=<bytes>): host buffers of at least that size are pinned + mapped once
@@ -515,6 +535,103 @@ extern "C" int64_t zdev_spec2d_np(zdev_spec2d* s) {
 	std::vector<int> cnt;
 	s->np_host = spec_live_counts(s, cnt);
 	return s->np_host;
+}
+
+// ------------------------------------------------------------------ growing tiles
+
+// copy every tile's slots (holes included) from one layout to another
+__global__ void k_relayout(soa2d src, const int64_t* __restrict__ off_src, soa2d dst, const int64_t* __restrict__ off_dst,
+                           const int* __restrict__ tile_np) {
+	const int t = blockIdx.x, n = tile_np[t];
+	const int64_t a = off_src[t], b = off_dst[t];
+	for (int k = threadIdx.x; k < n; k += blockDim.x) {
+		const unsigned short key = src.key[a + k];
+		dst.key[b + k] = key;
+		if (key != KEY_EMPTY) {
+			const rec24 v = rec_load(src.rec, a + k);
+			rec_store(dst.rec, b + k, v.x, v.y, v.ux, v.uy, v.uz, v.cell);
+			if (src.tag) dst.tag[b + k] = src.tag[a + k];
+		}
+	}
+}
+
+// Tiles are fixed-capacity segments; a plasma that piles up (the density spike behind a laser pulse is several
+// times the initial density) outgrows them.  Particles that find their tile full are parked in the overflow
+// list by the append / migrate kernels; here the tiles that need it get 1.5x the room they need now, the
+// population is copied to the new layout and the parked particles are appended.  Called (with one small
+// device -> host copy) after every advance, so nothing ever misses a push.
+static void spec_resolve_overflow(zdev_spec2d* s) {
+	s->appended = 0;
+	ctl2d h;
+	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	while (h.flags & 1u) {
+		check_flags(s, h.flags & (2u | 4u | 8u));
+		const int64_t n_ovf = h.n_ovf;
+		// what every tile holds and what is waiting for it
+		std::vector<int> np_t(s->ntiles), ovf_t(s->ntiles, 0);
+		int* d_cnt; ZDEV_CHECK(cudaMalloc(&d_cnt, (size_t) s->ntiles * sizeof(int)));
+		ZDEV_CHECK(cudaMemsetAsync(d_cnt, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+		ZDEV_LAUNCH(k_count_tiles, zdev_div_up(n_ovf, 256), 256, 0, s->ovf, n_ovf, s->TX, s->TY, s->ntx, d_cnt);
+		ZDEV_CHECK(cudaMemcpyAsync(ovf_t.data(), d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaMemcpyAsync(np_t.data(), s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_cnt);
+		// new layout
+		std::vector<int64_t> off_new(s->ntiles + 1, 0);
+		const std::vector<int64_t>& off = *s->h_off;
+		int64_t max_cap = 0;
+		for (int t = 0; t < s->ntiles; t++) {
+			int64_t cap = off[t + 1] - off[t];
+			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
+			if (ovf_t[t] > 0 || need > cap - cap / 8) {
+				int64_t grown = need + need / 2 + 64;
+				grown = (grown + 31) & ~(int64_t) 31;
+				if (grown > cap) cap = grown;
+			}
+			off_new[t + 1] = off_new[t] + cap;
+			if (cap > max_cap) max_cap = cap;
+		}
+		if (max_cap > 0xfff0) {
+			fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed the shared-memory index "
+			        "buffer; use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) max_cap, s->TX, s->TY);
+			exit(-1);
+		}
+		const int64_t total = off_new[s->ntiles];
+		// the parked particles move out of the way first (appending them may park others again)
+		part_aos* d_wait; int* d_wait_tag = nullptr;
+		ZDEV_CHECK(cudaMalloc(&d_wait, (size_t) n_ovf * sizeof(part_aos)));
+		ZDEV_CHECK(cudaMemcpyAsync(d_wait, s->ovf, (size_t) n_ovf * sizeof(part_aos), cudaMemcpyDeviceToDevice, zdev_strm));
+		if (s->ovf_tag) {
+			ZDEV_CHECK(cudaMalloc(&d_wait_tag, (size_t) n_ovf * 4));
+			ZDEV_CHECK(cudaMemcpyAsync(d_wait_tag, s->ovf_tag, (size_t) n_ovf * 4, cudaMemcpyDeviceToDevice, zdev_strm));
+		}
+		// population -> new layout (q is scratch between steps: release it first)
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		soa_free(s->q);
+		soa2d pn;
+		soa_alloc(pn, total, s->track_ids);
+		int64_t* d_off_new; ZDEV_CHECK(cudaMalloc(&d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
+		ZDEV_CHECK(cudaMemcpyAsync(d_off_new, off_new.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
+		ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, pn, d_off_new, s->tile_np);
+		ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_off_new);
+		soa_free(s->p);
+		s->p = pn;
+		soa_alloc(s->q, total, s->track_ids);
+		*s->h_off = off_new;
+		s->cap_total = total;
+		s->max_cap = (int) max_cap;
+		mig_alloc(s, s->mig.div);
+		// clear the overflow state (energy, counts and export counters of the step stay) and append
+		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->n_ovf, 0, 2 * sizeof(unsigned int), zdev_strm));    // n_ovf, flags
+		spec_append_dev(s, d_wait, n_ovf, 0, d_wait_tag);
+		s->appended = 0;
+		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_wait); cudaFree(d_wait_tag);
+	}
 }
 
 // ------------------------------------------------------------------ device-side uniform injection
@@ -1074,7 +1191,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig2d mig,
                             ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int ntiles, int nx, int ny,
                             int moving_window, int slab_left, int slab_right,
-                            part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap) {
+                            part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap,
+                            part_aos* __restrict__ ovf, int* __restrict__ ovf_tag, unsigned int ovf_cap) {
 	const int lane = threadIdx.x & 31;
 	const int nwarp = (gridDim.x * blockDim.x) >> 5;
 	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
@@ -1100,7 +1218,12 @@ __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* 
 			int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 			int slot = atomicAdd(&tile_np[t], 1);
 			int64_t d = tile_off[t] + slot;
-			if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
+			if (d >= tile_off[t + 1]) {
+				atomicSub(&tile_np[t], 1);
+				r.ix = ix; r.iy = iy;
+				ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, p.tag ? mig.tag[mb + k] : 0);
+				continue;
+			}
 			const int lx = ix - tx * TX, ly = iy - ty * TY;
 			rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
 			p.key[d] = (unsigned short) (lx + ly * TX);
@@ -1154,6 +1277,7 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	    zdev_grid2d_nx(gcur) != s->nx || zdev_grid2d_ny(gcur) != s->ny) {
 		fprintf(stderr, "(*error*) zdev_spec2d_advance: species / grid size mismatch\n"); exit(-1);
 	}
+	if (s->cap_total && s->appended) spec_resolve_overflow(s);      // appends since the last step may have hit a full tile
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
 	// a window shift sends a whole column of every tile through the migrants segments
@@ -1176,7 +1300,8 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	}
 	ZDEV_LAUNCH(k_migrate2d, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
 	            s->TX, s->TY, s->ntx, s->ntiles, s->nx, s->ny, prm->moving_window, prm->slab_left, prm->slab_right,
-	            s->exp_buf[0], s->exp_buf[1], s->exp_cap);
+	            s->exp_buf[0], s->exp_buf[1], s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap);
+	spec_resolve_overflow(s);
 	if (prm->moving_window || prm->slab_left || prm->slab_right) s->ids_valid = 0;
 }
 
