@@ -115,6 +115,8 @@ struct zdev_spec2d {
 	part_aos* ovf; int* ovf_tag;     // particles that found their destination tile full (global cell indices):
 	unsigned int ovf_cap;            //   the host grows the tiles and re-appends them before the next push
 	int appended;                    // appends since the last overflow check
+	int* tile_list;                  // device: ids of the ordinary tiles, then of the few that outgrew them
+	int n_small, cap_small;          // how many ordinary tiles, and their largest capacity
 	part_aos* stage; int64_t stage_cap;   // persistent staging for appended host particles
 	part_aos* exp_buf[2];            // slab mode: export lists (AoS, ix already in the neighbour's frame)
 	unsigned int exp_cap;
@@ -168,8 +170,9 @@ static void soa_free(soa2d& a) {
 	cudaFree(a.rec); cudaFree(a.key); cudaFree(a.tag);
 	memset(&a, 0, sizeof(a));
 }
-// migrants segments: 1/div of every tile's capacity.  A window shift empties a whole column of
-// every tile (1/TX of its particles) on top of the ordinary leavers, hence div = 4 there.
+// migrants segments: 1/div of every tile's capacity (8; ZPIC_MIG_DIV overrides).  Under a moving window a
+// shift empties a whole column of every tile on top of the ordinary leavers, and laser-driven plasma leaves a
+// tile at close to one cell per step along a whole edge: div = 2 there.
 static void mig_alloc(zdev_spec2d* s, int div);
 static void mig_free(zdev_spec2d* s);
 
@@ -231,6 +234,7 @@ static void mig_free(zdev_spec2d* s) {
 }
 static void mig_alloc(zdev_spec2d* s, int div) {
 	mig_free(s);
+	if (const char* e = getenv("ZPIC_MIG_DIV")) { const int v = atoi(e); if (v >= 1 && v < div) div = v; }
 	s->mig.div = div;
 	s->mig_cap = s->cap_total / div + 32;
 	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) s->mig_cap * sizeof(part_aos)));
@@ -253,7 +257,7 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	if (!s) return;
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
-	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl);
+	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl); cudaFree(s->tile_list);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -261,6 +265,28 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 
 extern "C" void zdev_spec2d_tile_info(zdev_spec2d* s, int* tx, int* ty, int* ntiles, int64_t* capacity) {
 	if (tx) *tx = s->TX; if (ty) *ty = s->TY; if (ntiles) *ntiles = s->ntiles; if (capacity) *capacity = s->cap_total;
+}
+
+// The shared memory of a push CTA is sized by the capacity of the tile it sorts.  A few tiles in a density
+// spike can grow to many times the ordinary capacity; sizing every CTA for them would halve the occupancy of
+// the whole launch.  The tiles are therefore split into the ordinary ones (capacity up to ~2x the nominal
+// fill) and the outgrown ones, pushed by a second small launch with its own shared-memory size.
+static void spec_build_tile_lists(zdev_spec2d* s) {
+	const std::vector<int64_t>& off = *s->h_off;
+	const int64_t limit = (int64_t) (2.2 * s->TX * s->TY * s->ppc_hint) + 128;
+	std::vector<int> small, big;
+	int cap_small = 32;
+	for (int t = 0; t < s->ntiles; t++) {
+		const int64_t cap = off[t + 1] - off[t];
+		if (cap <= limit) { small.push_back(t); if (cap > cap_small) cap_small = (int) cap; }
+		else big.push_back(t);
+	}
+	s->n_small = (int) small.size();
+	s->cap_small = cap_small;
+	small.insert(small.end(), big.begin(), big.end());
+	if (!s->tile_list) ZDEV_CHECK(cudaMalloc(&s->tile_list, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMemcpyAsync(s->tile_list, small.data(), (size_t) s->ntiles * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 }
 
 // Lay out tile segments for the given per-tile populations and (re)allocate the SoA
@@ -301,6 +327,7 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	                           cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	spec_build_tile_lists(s);
 }
 
 // ------------------------------------------------------------------ host <-> device
@@ -346,7 +373,7 @@ static void check_flags(zdev_spec2d* s, unsigned int flags) {
 	}
 	if (flags & 2u) {
 		fprintf(stderr, "(*error*) zpic-b200: a tile's migrants segment overflowed (1/%d of the tile capacity); "
-		        "raise ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->mig.div, s->slack);
+		        "set ZPIC_MIG_DIV=1 (or raise ZPIC_TILE_SLACK, current %.2f) and rerun, aborting.\n", s->mig.div, s->slack);
 		exit(-1);
 	}
 	if (flags & 4u) {
@@ -584,7 +611,7 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		for (int t = 0; t < s->ntiles; t++) {
 			int64_t cap = off[t + 1] - off[t];
 			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			if (ovf_t[t] > 0 || need > cap - cap / 8) {
+			if (ovf_t[t] > 0 || need > cap - cap / 5) {          // full, or above 80 %: it will be next
 				int64_t grown = need + need / 2 + 64;
 				grown = (grown + 31) & ~(int64_t) 31;
 				if (grown > cap) cap = grown;
@@ -598,6 +625,9 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 			exit(-1);
 		}
 		const int64_t total = off_new[s->ntiles];
+		if (getenv("ZPIC_VERBOSE"))
+			fprintf(stderr, "zpic-b200: %lld particles found their %dx%d tile full: slots %lld -> %lld\n",
+			        (long long) n_ovf, s->TX, s->TY, (long long) s->cap_total, (long long) total);
 		// the parked particles move out of the way first (appending them may park others again)
 		part_aos* d_wait; int* d_wait_tag = nullptr;
 		ZDEV_CHECK(cudaMalloc(&d_wait, (size_t) n_ovf * sizeof(part_aos)));
@@ -623,6 +653,7 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		*s->h_off = off_new;
 		s->cap_total = total;
 		s->max_cap = (int) max_cap;
+		spec_build_tile_lists(s);
 		mig_alloc(s, s->mig.div);
 		// clear the overflow state (energy, counts and export counters of the step stay) and append
 		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->n_ovf, 0, 2 * sizeof(unsigned int), zdev_strm));    // n_ovf, flags
@@ -824,7 +855,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, mig2d mig,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
-         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm) {
+         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm, const int* __restrict__ tile_list) {
 	constexpr int SROW = TX + 2;
 	constexpr int PLANE = SROW * (TY + 2);
 	constexpr int NC = TX * TY;
@@ -840,7 +871,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
-	const int t = blockIdx.x;
+	const int t = tile_list[blockIdx.x];
 	const int tx = t % g.ntx, ty = t / g.ntx;
 	const int x0 = tx * TX, y0 = ty * TY;
 	const int cx = min(TX, g.nx - x0), cy = min(TY, g.ny - y0);
@@ -1263,12 +1294,20 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
-	if (s->track_ids)
-		ZDEV_LAUNCH((k_push2d<TX, TY, true>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_front(TX, TY, s->max_cap), (unsigned) ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15)));
-	else
-		ZDEV_LAUNCH((k_push2d<TX, TY, false>), s->ntiles, PUSH_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-		            s->mig, s->ctl, E, B, J, g, prm, (unsigned) push_smem_front(TX, TY, s->max_cap), (unsigned) ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15)));
+	for (int grp = 0; grp < 2; grp++) {
+		const int ntl = grp ? s->ntiles - s->n_small : s->n_small;
+		if (ntl <= 0) continue;
+		const int cap = grp ? s->max_cap : s->cap_small;
+		const int* list = s->tile_list + (grp ? s->n_small : 0);
+		const size_t sm = push_smem_bytes(TX, TY, cap);
+		const unsigned front = (unsigned) push_smem_front(TX, TY, cap), permb = (unsigned) ((((size_t) cap * 2 + 15) & ~(size_t) 15));
+		if (s->track_ids)
+			ZDEV_LAUNCH((k_push2d<TX, TY, true>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
+		else
+			ZDEV_LAUNCH((k_push2d<TX, TY, false>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
+	}
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
 
@@ -1281,7 +1320,7 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
 	// a window shift sends a whole column of every tile through the migrants segments
-	if (prm->moving_window && s->mig.div > 4) mig_alloc(s, 4);
+	if (prm->moving_window && s->mig.div > 2) mig_alloc(s, 2);
 	push_geom g = { s->nx, s->ny, s->nx + 3, s->ntx };
 	const f3* E = zdev_grid2d_Epart(grid); const f3* B = zdev_grid2d_Bpart(grid); f3* J = zdev_grid2d_J(gcur);
 	if      (s->TX == 16 && s->TY == 16) launch_push<16, 16>(s, E, B, J, g, *prm);
