@@ -122,6 +122,8 @@ struct zdev_spec2d {
 	unsigned int exp_cap;
 	ctl2d* ctl;                      // device
 	int64_t np_host;                 // last known particle count
+	int np_known;                    // np_host is exact (no absorbing boundary / slab exchange since it was counted)
+	ctl2d last; int last_valid;      // control block of the last advance as read by the overflow check
 	int ids_valid;                   // tags are a permutation of [0,np)
 	std::vector<int64_t>* h_off;     // host copy of tile_off
 	// optional device timing of the push kernel alone (bench roofline): ring of event pairs
@@ -455,7 +457,7 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	}
 	if (d_stage) cudaFree(d_stage);
-	s->np_host = np;
+	s->np_host = np; s->np_known = 1;
 	s->ids_valid = s->track_ids;
 }
 
@@ -537,7 +539,7 @@ extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_
 	std::vector<int64_t> prefix(s->ntiles);
 	int64_t acc = 0;
 	for (int t = 0; t < s->ntiles; t++) { prefix[t] = acc; acc += cnt[t]; }
-	s->np_host = np;
+	s->np_host = np; s->np_known = 1;
 	if (np == 0) return 0;
 	if (np > max_np) {
 		fprintf(stderr, "(*error*) zpic-b200: host particle buffer too small (%lld > %lld)\n", (long long) np, (long long) max_np);
@@ -560,7 +562,7 @@ extern "C" int64_t zdev_spec2d_download(zdev_spec2d* s, void* part, int64_t max_
 extern "C" int64_t zdev_spec2d_np(zdev_spec2d* s) {
 	if (!s->cap_total) return 0;
 	std::vector<int> cnt;
-	s->np_host = spec_live_counts(s, cnt);
+	s->np_host = spec_live_counts(s, cnt); s->np_known = 1;
 	return s->np_host;
 }
 
@@ -663,6 +665,7 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 		cudaFree(d_wait); cudaFree(d_wait_tag);
 	}
+	s->last = h; s->last_valid = 1;
 }
 
 // ------------------------------------------------------------------ device-side uniform injection
@@ -740,7 +743,7 @@ extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, c
 	int64_t ncell = (int64_t) s->nx * s->ny;
 	ZDEV_LAUNCH(k_inject_uniform, zdev_div_up(ncell, 128), 128, 0, s->p, s->tile_off, s->tile_np,
 	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed);
-	s->np_host = np;
+	s->np_host = np; s->np_known = 1;
 	s->ids_valid = s->track_ids && np < 0x7fffffff;
 }
 
@@ -1317,6 +1320,8 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 		fprintf(stderr, "(*error*) zdev_spec2d_advance: species / grid size mismatch\n"); exit(-1);
 	}
 	if (s->cap_total && s->appended) spec_resolve_overflow(s);      // appends since the last step may have hit a full tile
+	s->last_valid = 0;
+	if (prm->moving_window || prm->slab_left || prm->slab_right) s->np_known = 0;
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
 	// a window shift sends a whole column of every tile through the migrants segments
@@ -1345,6 +1350,14 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 }
 
 extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* np) {
+	// the overflow check at the end of the advance has already brought the step's control block to the host;
+	// the particle count only changes through absorbing boundaries, slab exchange and appends
+	if (s->last_valid && (!np || s->np_known)) {
+		check_flags(s, s->last.flags);
+		if (np) *np = s->np_host;
+		if (energy_sum) *energy_sum = s->last.energy;
+		return;
+	}
 	ctl2d h;
 	memset(&h, 0, sizeof h);
 	if (s->cap_total && np)
@@ -1355,7 +1368,7 @@ extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* n
 	if (np) {
 		// the count is accumulated into ctl->np by k_count_total: reset so a second fetch does not double it
 		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->np, 0, sizeof(unsigned long long), zdev_strm));
-		s->np_host = (int64_t) h.np;
+		s->np_host = (int64_t) h.np; s->np_known = 1;
 		*np = (int64_t) h.np;
 	}
 	if (energy_sum) *energy_sum = h.energy;
