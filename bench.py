@@ -120,7 +120,7 @@ def fit_grid(lib, n, ppc_total):
     free_b, total_b = C.c_size_t(), C.c_size_t()
     lib.zdev_mem_info(C.byref(free_b), C.byref(total_b))
     while n > 256:
-        need = 2 * (n * n * ppc_total) * (2 * 26 * 1.25 + 28 / 8.0) + 5 * (n + 3) ** 2 * 12
+        need = 2 * (n * n * ppc_total) * 1.25 * (2 * 26 + 28 / 8.0 + 28 / 32.0) + 5 * (n + 3) ** 2 * 12      # A/B records + keys, migrants, overflow list; grids
         if need < 0.92 * free_b.value:
             break
         n //= 2

@@ -462,7 +462,7 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 }
 
 // Appends are on the per-step path of a moving window (one injected column per move): the staging
-// buffer is kept, nothing is synchronised, and a capacity overflow is reported by the next fetch.
+// buffer is kept; the only synchronisation is the overflow check (a 48-byte copy).
 extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np) {
 	if (np <= 0) return;
 	if (!s->cap_total) { zdev_spec2d_upload(s, part, np); return; }
@@ -475,6 +475,7 @@ extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np)
 	ZDEV_CHECK(cudaMemcpyAsync(s->stage, part, (size_t) np * sizeof(part_aos), cudaMemcpyHostToDevice, zdev_strm));
 	spec_append_dev(s, s->stage, np, (int) s->np_host);
 	s->np_host += np;
+	spec_resolve_overflow(s);          // a full tile: grow now, so that every consumer sees the whole population
 }
 
 // per tile: number of live slots (slots whose cell is not -1)
@@ -613,8 +614,8 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		for (int t = 0; t < s->ntiles; t++) {
 			int64_t cap = off[t + 1] - off[t];
 			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			if (ovf_t[t] > 0 || need > cap - cap / 5) {          // full, or above 80 %: it will be next
-				int64_t grown = need + need / 2 + 64;
+			if (ovf_t[t] > 0 || need > cap - cap / 5) {          // full (double it), or above 80 %: it will be next
+				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 64;
 				grown = (grown + 31) & ~(int64_t) 31;
 				if (grown > cap) cap = grown;
 			}
@@ -1550,4 +1551,5 @@ extern "C" void zdev_spec2d_append_device(zdev_spec2d* s, const void* dev_aos, i
 	spec_append_dev(s, (const part_aos*) dev_aos, np, 0);
 	s->np_host += np;
 	s->ids_valid = 0;
+	spec_resolve_overflow(s);
 }
