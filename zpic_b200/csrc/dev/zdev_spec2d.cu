@@ -43,6 +43,7 @@
 #include "zdev_tma.cuh"
 #include <vector>
 #include <cstring>
+#include <chrono>
 
 // accessors implemented in zdev_grid2d.cu
 f3* zdev_grid2d_Epart(zdev_grid2d* g);
@@ -596,6 +597,7 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	while (h.flags & 1u) {
+		const auto t_start = std::chrono::steady_clock::now();
 		check_flags(s, h.flags & (2u | 4u | 8u));
 		const int64_t n_ovf = h.n_ovf;
 		// what every tile holds and what is waiting for it
@@ -628,9 +630,7 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 			exit(-1);
 		}
 		const int64_t total = off_new[s->ntiles];
-		if (getenv("ZPIC_VERBOSE"))
-			fprintf(stderr, "zpic-b200: %lld particles found their %dx%d tile full: slots %lld -> %lld\n",
-			        (long long) n_ovf, s->TX, s->TY, (long long) s->cap_total, (long long) total);
+		const int64_t slots_before = s->cap_total;
 		// the parked particles move out of the way first (appending them may park others again)
 		part_aos* d_wait; int* d_wait_tag = nullptr;
 		ZDEV_CHECK(cudaMalloc(&d_wait, (size_t) n_ovf * sizeof(part_aos)));
@@ -665,6 +665,11 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 		cudaFree(d_wait); cudaFree(d_wait_tag);
+		if (getenv("ZPIC_VERBOSE"))
+			fprintf(stderr, "zpic-b200: %lld particles found their %dx%d tile full: slots %lld -> %lld, largest tile %d, "
+			        "%d outgrown tiles, %.1f ms\n", (long long) n_ovf, s->TX, s->TY, (long long) slots_before, (long long) total,
+			        s->max_cap, s->ntiles - s->n_small,
+			        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
 	}
 	s->last = h; s->last_valid = 1;
 }
