@@ -254,6 +254,8 @@ void zdev_spec1d_upload( zdev_spec1d* s, const void* part_aos, int64_t np );
 void zdev_spec1d_append( zdev_spec1d* s, const void* part_aos, int64_t np );
 int64_t zdev_spec1d_download( zdev_spec1d* s, void* part_aos, int64_t max_np );
 int64_t zdev_spec1d_np( zdev_spec1d* s );
+/* slots allocated per buffer (grows when tiles fill up) */
+int64_t zdev_spec1d_capacity( zdev_spec1d* s );
 void zdev_spec1d_inject_uniform( zdev_spec1d* s, int ppc, const float ufl[3], const float uth[3], uint64_t seed );
 /* spec_advance minus host bookkeeping (em1d/particles.c:936-1062): interpolate_fld (:864-886), Boris,
  * dep_current_zamb (:707-779), boundaries / window shift, per-step re-binning */

@@ -107,11 +107,11 @@ class Deck1D:
         self.lib.sim_delete(C.byref(self.sim))
 
 
-def twostream(lib, nx=120, ppc=500, n_sort=None):
+def twostream(lib, nx=120, ppc=500, n_sort=None, uth=(0.001, 0.001, 0.001)):
     """em1d/input/twostream.c as shipped (reference input/twostream.c:12-36)"""
     sp = []
     for name, u in (("right", 0.2), ("left", -0.2)):
-        s = dict(name=name, m_q=-1.0, ppc=ppc, ufl=(u, 0.0, 0.0), uth=(0.001, 0.001, 0.001))
+        s = dict(name=name, m_q=-1.0, ppc=ppc, ufl=(u, 0.0, 0.0), uth=uth)
         if n_sort is not None:
             s["n_sort"] = n_sort
         sp.append(s)

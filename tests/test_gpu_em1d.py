@@ -65,6 +65,28 @@ def test_tile_sizes_bit_exact_and_conserving(ours1, ref1, tile, monkeypatch):
     assert np.abs(sa["J"] - sb["J"]).max() < TOL * 0.2
 
 
+def test_tiles_grow_when_the_beams_bunch(ours1, ref1, monkeypatch):
+    """7-cell tiles with 64 spare slots (ZPIC_TILE_SLACK=1): the first fluctuation fills one; the particles that
+    find it full are parked, the layout grows and they are re-appended before the next push"""
+    monkeypatch.setenv("ZPIC_TILE_X1D", "7")
+    monkeypatch.setenv("ZPIC_TILE_SLACK", "1.0")
+    a = H1.twostream(ours1, ppc=500, n_sort=0, uth=(0.05, 0.05, 0.05))     # 3500 per tile: 64 slots are 1.8 % headroom
+    b = H1.twostream(ref1, ppc=500, n_sort=0, uth=(0.05, 0.05, 0.05))
+    a.iter(60)
+    b.iter(60)
+    ours1.zpic_b200_species_handle.restype = C.c_void_p
+    ours1.zdev_spec1d_capacity.restype = C.c_int64
+    ours1.zdev_spec1d_capacity.argtypes = [C.c_void_p]
+    h = ours1.zpic_b200_species_handle(C.byref(a.species[0]))
+    cap0 = 17 * 3584 + 576                  # 17 tiles of 7 cells + 1 cell, 500 ppc + 64 slots, rounded to 32
+    assert ours1.zdev_spec1d_capacity(h) > cap0, "the deck was meant to overflow a tile"
+    sa, sb = a.snapshot(), b.snapshot()
+    for k in range(2):
+        assert sa["np"][k] == sb["np"][k]
+        assert (sa["parts"][k]["ix"] != sb["parts"][k]["ix"]).sum() <= 2
+        assert H.rel_l2(sa["parts"][k]["ux"], sb["parts"][k]["ux"]) < TOL
+
+
 def test_twostream_shipped_deck_100_steps(ours1, ref1):
     """config 5 parity case: em1d/input/twostream.c as shipped (120 cells, 2 x 500 ppc)"""
     a, b = H1.twostream(ours1, n_sort=0), H1.twostream(ref1, n_sort=0)

@@ -54,8 +54,9 @@ __device__ __forceinline__ void rec1_store(float* __restrict__ rec, int64_t slot
 struct ctl1d {
 	double energy;
 	unsigned long long np;
-	unsigned int pad0;
-	unsigned int flags;      // 1 tile overflow, 2 a tile's migrants segment overflowed
+	unsigned int n_ovf;      // entries in the overflow list
+	unsigned int flags;      // 1: some tile was full (particles parked in the overflow list), 2: a tile's migrants
+	                         // segment overflowed, 8: the overflow list overflowed
 };
 
 struct zdev_spec1d {
@@ -67,6 +68,8 @@ struct zdev_spec1d {
 	int64_t* tile_off;
 	int *tile_np, *tile_np_q;
 	mig1d mig;                       // per-tile migrants segments
+	part1_aos* ovf; int* ovf_tag;    // particles that found their destination tile full (global cell index):
+	unsigned int ovf_cap;            //   the host grows the tiles and re-appends them before the next push
 	ctl1d* ctl;
 	int64_t np_host;
 	int ids_valid;
@@ -124,6 +127,7 @@ static void free_particles(zdev_spec1d* s) {
 	if (s->cap_total) { buf_free(s->p); buf_free(s->q); }
 	cudaFree(s->mig.rec); cudaFree(s->mig.tag); cudaFree(s->mig.np);
 	memset(&s->mig, 0, sizeof s->mig);
+	cudaFree(s->ovf); cudaFree(s->ovf_tag); s->ovf = nullptr; s->ovf_tag = nullptr; s->ovf_cap = 0;
 	s->cap_total = 0;
 }
 
@@ -135,6 +139,18 @@ extern "C" void zdev_spec1d_destroy(zdev_spec1d* s) {
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
+}
+
+// migrants segments: 1/4 of every tile (two-stream decks move ~10 % of a 32-cell tile per step, a window
+// shift a whole cell's worth on top)
+static void mig1_alloc(zdev_spec1d* s) {
+	cudaFree(s->mig.rec); cudaFree(s->mig.tag); cudaFree(s->mig.np);
+	memset(&s->mig, 0, sizeof s->mig);
+	s->mig.div = 4;
+	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) (s->cap_total / s->mig.div + 32) * sizeof(part1_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig.tag, (size_t) (s->cap_total / s->mig.div + 32) * 4));
+	ZDEV_CHECK(cudaMalloc(&s->mig.np, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMemsetAsync(s->mig.np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 }
 
 static void layout(zdev_spec1d* s, const std::vector<int>& cnt, int64_t np) {
@@ -162,13 +178,10 @@ static void layout(zdev_spec1d* s, const std::vector<int>& cnt, int64_t np) {
 	buf_alloc(s->p, total, s->track_ids);
 	buf_alloc(s->q, total, s->track_ids);
 	s->cap_total = total; s->max_cap = (int) max_cap;
-	// migrants segments: 1/4 of every tile (two-stream decks move ~10 % of a 32-cell tile per step, a window
-	// shift a whole cell's worth on top)
-	s->mig.div = 4;
-	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) (total / s->mig.div + 32) * sizeof(part1_aos)));
-	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig.tag, (size_t) (total / s->mig.div + 32) * 4));
-	ZDEV_CHECK(cudaMalloc(&s->mig.np, (size_t) s->ntiles * sizeof(int)));
-	ZDEV_CHECK(cudaMemsetAsync(s->mig.np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+	mig1_alloc(s);
+	s->ovf_cap = (unsigned int) (total / 32 > (1 << 20) ? total / 32 : (1 << 20));
+	ZDEV_CHECK(cudaMalloc(&s->ovf, (size_t) s->ovf_cap * sizeof(part1_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag, (size_t) s->ovf_cap * 4));
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -180,25 +193,36 @@ __global__ void k1_count_tiles(const part1_aos* __restrict__ a, int64_t np, int 
 	int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (k < np) atomicAdd(&cnt[a[k].ix / TX], 1);
 }
+// a particle whose destination tile is full: park it (global cell index) for the host to deal with
+__device__ __forceinline__ void ovf1_push(ctl1d* ctl, part1_aos* ovf, int* ovf_tag, unsigned int cap, const part1_aos& r, int tag) {
+	atomicOr(&ctl->flags, 1u);
+	const unsigned int k = atomicAdd(&ctl->n_ovf, 1u);
+	if (k < cap) { ovf[k] = r; if (ovf_tag) ovf_tag[k] = tag; }
+	else atomicOr(&ctl->flags, 8u);
+}
+
 __global__ void k1_scatter(const part1_aos* __restrict__ a, int64_t np, int TX, buf1d p, const int64_t* __restrict__ off,
-                           int* tile_np, ctl1d* ctl, int tag0) {
+                           int* tile_np, ctl1d* ctl, int tag0, const int* __restrict__ tags,
+                           part1_aos* ovf, int* ovf_tag, unsigned int ovf_cap) {
 	int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= np) return;
 	part1_aos r = a[k];
+	const int tag = tags ? tags[k] : tag0 + (int) k;
 	int t = r.ix / TX;
 	int slot = atomicAdd(&tile_np[t], 1);
 	int64_t d = off[t] + slot;
-	if (d >= off[t + 1]) { atomicOr(&ctl->flags, 1u); return; }
+	if (d >= off[t + 1]) { atomicSub(&tile_np[t], 1); ovf1_push(ctl, ovf, ovf_tag, ovf_cap, r, tag); return; }
 	rec20 v = { r.x, r.ux, r.uy, r.uz, r.ix - t * TX };
 	rec1_store(p.rec, d, v);
 	p.key[d] = (unsigned short) v.cell;
-	if (p.tag) p.tag[d] = tag0 + (int) k;
+	if (p.tag) p.tag[d] = tag;
 }
 
+static void spec1_resolve_overflow(zdev_spec1d* s);
 static void check_flags(zdev_spec1d* s, unsigned int flags) {
-	if (flags & 1u) {
-		fprintf(stderr, "(*error*) zpic-b200: particle tile capacity exceeded (%d-cell tiles); raise ZPIC_TILE_SLACK "
-		        "(current %.2f) and rerun, aborting.\n", s->TX, s->slack);
+	if (flags & 8u) {
+		fprintf(stderr, "(*error*) zpic-b200: more than %u particles found their tile full in one step (%d-cell tiles); raise "
+		        "ZPIC_TILE_SLACK (current %.2f) and rerun, aborting.\n", s->ovf_cap, s->TX, s->slack);
 		exit(-1);
 	}
 	if (flags & 2u) {
@@ -226,7 +250,8 @@ extern "C" void zdev_spec1d_upload(zdev_spec1d* s, const void* part, int64_t np)
 	if (fits) ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	else layout(s, cnt, np);
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl1d), zdev_strm));
-	if (np > 0) ZDEV_LAUNCH(k1_scatter, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->p, s->tile_off, s->tile_np, s->ctl, 0);
+	if (np > 0) ZDEV_LAUNCH(k1_scatter, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->p, s->tile_off, s->tile_np, s->ctl, 0,
+	                        (const int*) nullptr, s->ovf, s->ovf_tag, s->ovf_cap);
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	if (d_aos) cudaFree(d_aos);
 	s->np_host = np;
@@ -239,13 +264,12 @@ extern "C" void zdev_spec1d_append(zdev_spec1d* s, const void* part, int64_t np)
 	part1_aos* d_aos;
 	ZDEV_CHECK(cudaMalloc(&d_aos, (size_t) np * sizeof(part1_aos)));
 	ZDEV_CHECK(cudaMemcpyAsync(d_aos, part, (size_t) np * sizeof(part1_aos), cudaMemcpyHostToDevice, zdev_strm));
-	ZDEV_LAUNCH(k1_scatter, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->p, s->tile_off, s->tile_np, s->ctl, (int) s->np_host);
-	ctl1d h;
-	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_LAUNCH(k1_scatter, zdev_div_up(np, 256), 256, 0, d_aos, np, s->TX, s->p, s->tile_off, s->tile_np, s->ctl, (int) s->np_host,
+	            (const int*) nullptr, s->ovf, s->ovf_tag, s->ovf_cap);
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_aos);
-	check_flags(s, h.flags);
 	s->np_host += np;
+	spec1_resolve_overflow(s);
 }
 
 __global__ void k1_count_live(buf1d p, const int64_t* __restrict__ off, const int* __restrict__ tile_np, int* live) {
@@ -292,6 +316,8 @@ static int64_t live_counts(zdev_spec1d* s, std::vector<int>& cnt) {
 	return np;
 }
 
+extern "C" int64_t zdev_spec1d_capacity(zdev_spec1d* s) { return s->cap_total; }
+
 extern "C" int64_t zdev_spec1d_np(zdev_spec1d* s) {
 	if (!s->cap_total) return 0;
 	std::vector<int> cnt;
@@ -317,6 +343,94 @@ extern "C" int64_t zdev_spec1d_download(zdev_spec1d* s, void* part, int64_t max_
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	cudaFree(d_prefix); cudaFree(d_aos);
 	return np;
+}
+
+// ------------------------------------------------------------------ growing tiles (see zdev_spec2d.cu)
+
+__global__ void k1_relayout(buf1d src, const int64_t* __restrict__ off_src, buf1d dst, const int64_t* __restrict__ off_dst,
+                            const int* __restrict__ tile_np) {
+	const int t = blockIdx.x, n = tile_np[t];
+	const int64_t a = off_src[t], b = off_dst[t];
+	for (int k = threadIdx.x; k < n; k += blockDim.x) {
+		const unsigned short key = src.key[a + k];
+		dst.key[b + k] = key;
+		if (key != KEY1_EMPTY) {
+			rec1_store(dst.rec, b + k, rec1_load(src.rec, a + k));
+			if (src.tag) dst.tag[b + k] = src.tag[a + k];
+		}
+	}
+}
+
+// Particles that found their tile full were parked in the overflow list by the append / migrate kernels: give
+// the tiles that need it more room (full ones 2x, those above 80 % 1.5x what they hold), copy the population
+// to the new layout and append the parked particles.  Runs after every advance / append, so nothing ever
+// misses a push.
+static void spec1_resolve_overflow(zdev_spec1d* s) {
+	ctl1d h;
+	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	while (h.flags & 1u) {
+		check_flags(s, h.flags & (2u | 8u));
+		const int64_t n_ovf = h.n_ovf;
+		std::vector<int> np_t(s->ntiles), ovf_t(s->ntiles, 0);
+		int* d_cnt; ZDEV_CHECK(cudaMalloc(&d_cnt, (size_t) s->ntiles * sizeof(int)));
+		ZDEV_CHECK(cudaMemsetAsync(d_cnt, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+		ZDEV_LAUNCH(k1_count_tiles, zdev_div_up(n_ovf, 256), 256, 0, s->ovf, n_ovf, s->TX, d_cnt);
+		ZDEV_CHECK(cudaMemcpyAsync(ovf_t.data(), d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaMemcpyAsync(np_t.data(), s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_cnt);
+		std::vector<int64_t> off_new(s->ntiles + 1, 0);
+		const std::vector<int64_t>& off = *s->h_off;
+		int64_t max_cap = 0;
+		for (int t = 0; t < s->ntiles; t++) {
+			int64_t cap = off[t + 1] - off[t];
+			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
+			if (ovf_t[t] > 0 || need > cap - cap / 5) {
+				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 64;
+				grown = (grown + 31) & ~(int64_t) 31;
+				if (grown > cap) cap = grown;
+			}
+			off_new[t + 1] = off_new[t] + cap;
+			if (cap > max_cap) max_cap = cap;
+		}
+		if (max_cap > 0xfff0) {
+			fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %d-cell tile exceed the shared-memory index "
+			        "buffer; use smaller tiles (ZPIC_TILE_X1D)\n", (long long) max_cap, s->TX);
+			exit(-1);
+		}
+		const int64_t total = off_new[s->ntiles];
+		part1_aos* d_wait; int* d_wait_tag = nullptr;
+		ZDEV_CHECK(cudaMalloc(&d_wait, (size_t) n_ovf * sizeof(part1_aos)));
+		ZDEV_CHECK(cudaMemcpyAsync(d_wait, s->ovf, (size_t) n_ovf * sizeof(part1_aos), cudaMemcpyDeviceToDevice, zdev_strm));
+		if (s->ovf_tag) {
+			ZDEV_CHECK(cudaMalloc(&d_wait_tag, (size_t) n_ovf * 4));
+			ZDEV_CHECK(cudaMemcpyAsync(d_wait_tag, s->ovf_tag, (size_t) n_ovf * 4, cudaMemcpyDeviceToDevice, zdev_strm));
+		}
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		buf_free(s->q);                                   // scratch between steps
+		buf1d pn;
+		buf_alloc(pn, total, s->track_ids);
+		int64_t* d_off_new; ZDEV_CHECK(cudaMalloc(&d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
+		ZDEV_CHECK(cudaMemcpyAsync(d_off_new, off_new.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
+		ZDEV_LAUNCH(k1_relayout, s->ntiles, 256, 0, s->p, s->tile_off, pn, d_off_new, s->tile_np);
+		ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_off_new);
+		buf_free(s->p);
+		s->p = pn;
+		buf_alloc(s->q, total, s->track_ids);
+		*s->h_off = off_new;
+		s->cap_total = total;
+		s->max_cap = (int) max_cap;
+		mig1_alloc(s);
+		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->n_ovf, 0, 2 * sizeof(unsigned int), zdev_strm));    // n_ovf, flags
+		ZDEV_LAUNCH(k1_scatter, zdev_div_up(n_ovf, 256), 256, 0, d_wait, n_ovf, s->TX, s->p, s->tile_off, s->tile_np, s->ctl, 0,
+		            (const int*) d_wait_tag, s->ovf, s->ovf_tag, s->ovf_cap);
+		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(d_wait); cudaFree(d_wait_tag);
+	}
 }
 
 // ------------------------------------------------------------------ device-side uniform injection
@@ -789,7 +903,8 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 // Boundary conditions for the particles that left their tile (em1d/particles.c:1044-1060: absorbing under a
 // moving window or open boundaries, else periodic), then append them to their destination tiles.
 __global__ void k1_migrate(buf1d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig1d mig,
-                           ctl1d* __restrict__ ctl, int TX, int ntiles, int nx, int absorbing) {
+                           ctl1d* __restrict__ ctl, int TX, int ntiles, int nx, int absorbing,
+                           part1_aos* __restrict__ ovf, int* __restrict__ ovf_tag, unsigned int ovf_cap) {
 	const int lane = threadIdx.x & 31;
 	const int nwarp = (gridDim.x * blockDim.x) >> 5;
 	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
@@ -805,7 +920,12 @@ __global__ void k1_migrate(buf1d p, const int64_t* __restrict__ tile_off, int* _
 			int t = ix / TX;
 			int slot = atomicAdd(&tile_np[t], 1);
 			int64_t d = tile_off[t] + slot;
-			if (d >= tile_off[t + 1]) { atomicOr(&ctl->flags, 1u); continue; }
+			if (d >= tile_off[t + 1]) {
+				atomicSub(&tile_np[t], 1);
+				r.ix = ix;
+				ovf1_push(ctl, ovf, ovf_tag, ovf_cap, r, p.tag ? mig.tag[mb + k] : 0);
+				continue;
+			}
 			rec20 v = { r.x, r.ux, r.uy, r.uz, ix - t * TX };
 			rec1_store(p.rec, d, v);
 			p.key[d] = (unsigned short) v.cell;
@@ -872,7 +992,9 @@ extern "C" void zdev_spec1d_advance(zdev_spec1d* s, zdev_grid1d* grid, zdev_grid
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 	{ buf1d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
-	ZDEV_LAUNCH(k1_migrate, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl, s->TX, s->ntiles, s->nx, prm->absorbing);
+	ZDEV_LAUNCH(k1_migrate, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl, s->TX, s->ntiles, s->nx, prm->absorbing,
+	            s->ovf, s->ovf_tag, s->ovf_cap);
+	spec1_resolve_overflow(s);
 	if (prm->absorbing) s->ids_valid = 0;
 }
 
