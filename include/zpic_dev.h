@@ -173,6 +173,9 @@ int64_t zdev_spec2d_np( zdev_spec2d* s );
  * throughput configurations whose host mirrors would not fit (hard part 5). */
 void zdev_spec2d_inject_uniform( zdev_spec2d* s, int ppcx, int ppcy,
                                  const float ufl[3], const float uth[3], uint64_t seed );
+/* the same in the rows iy0 <= iy < iy1 only (half-box species of a shear-flow deck) */
+void zdev_spec2d_inject_band( zdev_spec2d* s, int ppcx, int ppcy,
+                              const float ufl[3], const float uth[3], uint64_t seed, int iy0, int iy1 );
 
 /* spec_advance minus the host bookkeeping (em2d/particles.c:1125-1259):
  * interpolate_fld (:1029-1071) + Boris push (:1146-1207) + dep_current_zamb

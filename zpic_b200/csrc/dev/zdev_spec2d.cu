@@ -42,6 +42,7 @@
 #include "pic2d_packed.cuh"
 #include "zdev_tma.cuh"
 #include <vector>
+#include <algorithm>
 #include <cstring>
 #include <chrono>
 
@@ -702,15 +703,18 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t gid, float& a, f
 // 335-347), momenta as spec_set_u (thermal, minus the cell mean, plus fluid; :96-142)
 __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* tile_np,
                                  int nx, int ny, int TX, int TY, int ntx, int ppcx, int ppcy,
-                                 f3 ufl, f3 uth, uint64_t seed) {
+                                 f3 ufl, f3 uth, uint64_t seed, int iy0, int iy1) {
 	int64_t cell = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (cell >= (int64_t) nx * ny) return;
 	int iy = (int) (cell / nx), ix = (int) (cell - (int64_t) iy * nx);
+	if (iy < iy0 || iy >= iy1) return;                       // outside the band: no particles
 	int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 	int cx = (tx + 1) * TX <= nx ? TX : nx - tx * TX;
 	int lx = ix - tx * TX, ly = iy - ty * TY;
 	int npc = ppcx * ppcy;
-	int64_t base = off[t] + (int64_t) (lx + ly * cx) * npc;
+	// rows of the tile inside the band are packed from the tile's first slot
+	const int ly0 = max(iy0 - ty * TY, 0);
+	int64_t base = off[t] + (int64_t) (lx + (ly - ly0) * cx) * npc;
 	uint64_t gid0 = (uint64_t) cell * npc;
 	float sx = 0, sy = 0, sz = 0;
 	for (int k = 0; k < npc; k++) {
@@ -729,28 +733,46 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = (int) (gid0 + k);
 	}
-	if (lx == 0 && ly == 0) {
+	if (lx == 0 && ly == ly0) {
 		int cy = (ty + 1) * TY <= ny ? TY : ny - ty * TY;
-		tile_np[t] = cx * cy * npc;
+		const int rows = min(ty * TY + cy, iy1) - max(ty * TY, iy0);
+		tile_np[t] = cx * rows * npc;
 	}
 }
 
-extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed) {
+// uniform plasma in the rows iy0 <= iy < iy1 only (e.g. the two half-box species of a shear-flow deck); tiles
+// outside the band get the minimum capacity (they grow on demand when particles arrive)
+extern "C" void zdev_spec2d_inject_band(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
+                                        int iy0, int iy1) {
 	int npc = ppcx * ppcy;
+	if (iy0 < 0) iy0 = 0;
+	if (iy1 > s->ny) iy1 = s->ny;
 	std::vector<int> cnt(s->ntiles);
 	int64_t np = 0;
 	for (int ty = 0; ty < s->nty; ty++) for (int tx = 0; tx < s->ntx; tx++) {
 		int cx = (tx + 1) * s->TX <= s->nx ? s->TX : s->nx - tx * s->TX;
 		int cy = (ty + 1) * s->TY <= s->ny ? s->TY : s->ny - ty * s->TY;
-		cnt[tx + ty * s->ntx] = cx * cy * npc; np += (int64_t) cx * cy * npc;
+		int rows = std::min(ty * s->TY + cy, iy1) - std::max(ty * s->TY, iy0);
+		if (rows < 0) rows = 0;
+		cnt[tx + ty * s->ntx] = cx * rows * npc; np += (int64_t) cx * rows * npc;
 	}
+	const bool band = iy0 > 0 || iy1 < s->ny;
+	const int hint = s->ppc_hint;
+	if (band) s->ppc_hint = 0;                  // capacities from the actual populations, not the nominal fill
 	spec_layout(s, cnt, np);
+	s->ppc_hint = hint;
+	if (band) spec_build_tile_lists(s);
 	f3 fl = {ufl[0], ufl[1], ufl[2]}, th = {uth[0], uth[1], uth[2]};
 	int64_t ncell = (int64_t) s->nx * s->ny;
+	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_LAUNCH(k_inject_uniform, zdev_div_up(ncell, 128), 128, 0, s->p, s->tile_off, s->tile_np,
-	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed);
+	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed, iy0, iy1);
 	s->np_host = np; s->np_known = 1;
 	s->ids_valid = s->track_ids && np < 0x7fffffff;
+}
+
+extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed) {
+	zdev_spec2d_inject_band(s, ppcx, ppcy, ufl, uth, seed, 0, s->ny);
 }
 
 // ------------------------------------------------------------------ the push

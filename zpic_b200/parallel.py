@@ -143,6 +143,10 @@ class CudaSlab:
         self.lib.zdev_spec2d_inject_uniform(self.species[k]["handle"], ppc[0], ppc[1], (C.c_float * 3)(*ufl),
                                             (C.c_float * 3)(*uth), seed)
 
+    def inject_band(self, k, ppc, ufl, uth, seed, iy0, iy1):
+        self.lib.zdev_spec2d_inject_band(self.species[k]["handle"], ppc[0], ppc[1], (C.c_float * 3)(*ufl),
+                                         (C.c_float * 3)(*uth), seed, iy0, iy1)
+
     def push(self, k, shift):
         sp, g = self.species[k], self.g
         q, m_q = np.float32(sp["q"]), np.float32(sp["m_q"])
