@@ -449,3 +449,27 @@ def test_parity_read_from_zdf_output(ours, ref, tmp_path):
             top = str(f).split(os.sep)[0]
             scale = {"EMF": 0.6 * 30 * 0.07, "CURRENT": 0.6, "CHARGE": 1.0}[top]
             assert np.abs(a - b).max() <= TOL_FIELD * max(scale, np.abs(b).max()), (f, np.abs(a - b).max())
+
+
+def test_band_injection_on_the_device(ours):
+    """zdev_spec2d_inject_band (config 4: half-box species): exactly ppc particles in every cell of the band,
+    none outside, positions on the reference's sub-cell lattice, momenta = fluid + thermal with zero cell mean"""
+    nx, ny, ppc = 48, 40, (4, 2)
+    s = ours.zdev_spec2d_create(nx, ny, ppc[0] * ppc[1], 0)
+    ufl, uth = (C.c_float * 3)(0.2, 0.0, 0.0), (C.c_float * 3)(0.01, 0.02, 0.03)
+    ours.zdev_spec2d_inject_band(s, ppc[0], ppc[1], ufl, uth, 99, 10, 25)
+    n = (25 - 10) * nx * ppc[0] * ppc[1]
+    assert ours.zdev_spec2d_np(s) == n
+    parts = np.zeros(n, dtype=A.PART_DTYPE)
+    assert ours.zdev_spec2d_download(s, parts.ctypes.data, n) == n
+    assert parts["iy"].min() == 10 and parts["iy"].max() == 24
+    cell = parts["ix"].astype(np.int64) + nx * parts["iy"]
+    assert np.array_equal(np.bincount(cell, minlength=nx * ny).reshape(ny, nx)[10:25], np.full((15, nx), 8))
+    assert np.array_equal(np.unique(parts["x"]), np.array([0.125, 0.375, 0.625, 0.875], dtype=np.float32))
+    assert np.array_equal(np.unique(parts["y"]), np.array([0.25, 0.75], dtype=np.float32))
+    order = np.argsort(cell, kind="stable")
+    for q, fl, th in (("ux", 0.2, 0.01), ("uy", 0.0, 0.02), ("uz", 0.0, 0.03)):
+        per_cell = parts[q][order].reshape(-1, 8)
+        assert np.abs(per_cell.mean(axis=1) - fl).max() < 1e-6          # the cell mean of the thermal part is removed
+        assert 0.7 * th < (per_cell - fl).std() < 1.1 * th
+    ours.zdev_spec2d_destroy(s)
