@@ -29,6 +29,18 @@ int zdev_grid1d_nx(zdev_grid1d* g);
 struct part1_aos { int ix; float x, ux, uy, uz; };           // host record (em1d/particles.h:29-35)
 struct rec20 { float x, ux, uy, uz; int cell; };             // one particle as a value; cell = tile-local index
 #define KEY1_EMPTY 0xffffu
+// The sort key is the cell AND the quarter of the cell the particle sits in (SUB1 bins): inside a cell the
+// particles are then ordered by position, so the ones about to cross a face (a contiguous slice at one end
+// when the species drifts, 19 % per step in the two-stream deck) leave and arrive as a block and the gathers
+// of the next step read runs of consecutive slots instead of isolated ones.
+#ifndef SUB1
+#define SUB1 4
+#endif
+__host__ __device__ __forceinline__ unsigned short key1_of(int cell, float x) {
+	int b = (int) (x * SUB1);
+	b = b < 0 ? 0 : (b > SUB1 - 1 ? SUB1 - 1 : b);
+	return (unsigned short) (cell * SUB1 + b);
+}
 #define REC1_CHUNK_WORDS 160          // 5 rows x 32 slots
 
 struct buf1d {
@@ -214,7 +226,7 @@ __global__ void k1_scatter(const part1_aos* __restrict__ a, int64_t np, int TX, 
 	if (d >= off[t + 1]) { atomicSub(&tile_np[t], 1); ovf1_push(ctl, ovf, ovf_tag, ovf_cap, r, tag); return; }
 	rec20 v = { r.x, r.ux, r.uy, r.uz, r.ix - t * TX };
 	rec1_store(p.rec, d, v);
-	p.key[d] = (unsigned short) v.cell;
+	p.key[d] = key1_of(v.cell, v.x);
 	if (p.tag) p.tag[d] = tag;
 }
 
@@ -467,7 +479,7 @@ __global__ void k1_inject_uniform(buf1d p, const int64_t* __restrict__ off, int*
 	for (int k = lane; k < ppc; k += 32) {
 		float a, b, c; normal3_1d(seed, gid0 + k, a, b, c);
 		rec20 v = { (float) ((k + 0.5) / ppc), uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz), lc };
-		rec1_store(p.rec, base + k, v); p.key[base + k] = (unsigned short) lc;
+		rec1_store(p.rec, base + k, v); p.key[base + k] = key1_of(lc, v.x);
 		if (p.tag) p.tag[base + k] = (int) (gid0 + k);
 	}
 	if (lc == 0 && lane == 0) { int cx = (t + 1) * TX <= nx ? TX : nx - t * TX; tile_np[t] = cx * ppc; }
@@ -595,7 +607,8 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
 	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
 	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
-	__shared__ int s_cnt[512], s_cur[512];
+	__shared__ int s_cnt[512 * SUB1], s_cur[512 * SUB1];
+	const int NK = TX * SUB1;                            // sort keys of the tile
 	__shared__ int s_wsum[P1_WARPS];
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
@@ -615,7 +628,7 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_raw[k] = e.x; s_raw[k + PL] = e.y; s_raw[k + 2 * PL] = e.z;
 		s_raw[k + 3 * PL] = b.x; s_raw[k + 4 * PL] = b.y; s_raw[k + 5 * PL] = b.z;
 	}
-	for (int k = threadIdx.x; k < TX; k += P1_THREADS) s_cnt[k] = 0;
+	for (int k = threadIdx.x; k < NK; k += P1_THREADS) s_cnt[k] = 0;
 	__syncthreads();
 	if (n > 0) mbar_wait(&s_bar, 0);
 
@@ -641,19 +654,22 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	}
 	__syncthreads();
 	int nlive;
-	{	// exclusive scan over TX <= 512 counters, two per thread
-		const int i0 = 2 * threadIdx.x;
-		int a = (i0 < TX) ? s_cnt[i0] : 0, b = (i0 + 1 < TX) ? s_cnt[i0 + 1] : 0;
-		int v = a + b, incl = v;
+	{	// exclusive scan over the NK <= 2048 counters, 2 * SUB1 consecutive ones per thread
+		constexpr int PER = 2 * SUB1;
+		const int i0 = PER * threadIdx.x;
+		int c[PER], v = 0;
+		#pragma unroll
+		for (int k = 0; k < PER; k++) { c[k] = (i0 + k < NK) ? s_cnt[i0 + k] : 0; v += c[k]; }
+		int incl = v;
 		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
 		if (lane == 31) s_wsum[warp] = incl;
 		__syncthreads();
 		int woff = 0, tot = 0;
 		#pragma unroll
-		for (int w = 0; w < P1_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
-		const int ex = woff + incl - v;
-		if (i0 < TX) s_cur[i0] = ex;
-		if (i0 + 1 < TX) s_cur[i0 + 1] = ex + a;
+		for (int w = 0; w < P1_WARPS; w++) { int cw = s_wsum[w]; woff += (w < warp) ? cw : 0; tot += cw; }
+		int run = woff + incl - v;
+		#pragma unroll
+		for (int k = 0; k < PER; k++) { if (i0 + k < NK) s_cur[i0 + k] = run; run += c[k]; }
 		nlive = tot;
 		__syncthreads();
 	}
@@ -848,13 +864,13 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (actA) {
 			float* qd = Brec + (pa >> 5) * REC1_CHUNK_WORDS + (pa & 31);
 			qd[0] = xn.x; qd[32] = ux.x; qd[64] = uy.x; qd[96] = uz.x; qd[128] = __int_as_float(nlxa);
-			Bo.key[base + pa] = sta ? (unsigned short) nlxa : (unsigned short) KEY1_EMPTY;
+			Bo.key[base + pa] = sta ? key1_of(nlxa, xn.x) : (unsigned short) KEY1_EMPTY;
 			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
 		if (actB) {
 			float* qd = Brec + (pb >> 5) * REC1_CHUNK_WORDS + (pb & 31);
 			qd[0] = xn.y; qd[32] = ux.y; qd[64] = uy.y; qd[96] = uz.y; qd[128] = __int_as_float(nlxb);
-			Bo.key[base + pb] = stb ? (unsigned short) nlxb : (unsigned short) KEY1_EMPTY;
+			Bo.key[base + pb] = stb ? key1_of(nlxb, xn.y) : (unsigned short) KEY1_EMPTY;
 			if (TAGS) Bo.tag[base + pb] = v.tb;
 		}
 		{
@@ -928,7 +944,7 @@ __global__ void k1_migrate(buf1d p, const int64_t* __restrict__ tile_off, int* _
 			}
 			rec20 v = { r.x, r.ux, r.uy, r.uz, ix - t * TX };
 			rec1_store(p.rec, d, v);
-			p.key[d] = (unsigned short) v.cell;
+			p.key[d] = key1_of(v.cell, v.x);
 			if (p.tag) p.tag[d] = mig.tag[mb + k];
 		}
 	}
