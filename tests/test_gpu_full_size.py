@@ -1,0 +1,68 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (tests/full_size.py).
+
+2^31 particles cannot be compared one by one with the CPU reference; what can be checked at any size is
+what a correct step preserves (particle counts, total charge, the Gauss-law residual of the charge-conserving
+deposit) and what is intensive (energy per cell after K steps equals the reference's at equal ppc, whatever
+the grid).  The intensive numbers of the reference are committed in tests/golden/full_size_<code>_ref.json:
+
+    python -m tests.full_size em2d 256 8 5 --lib ref > tests/golden/full_size_em2d_ref.json
+    python -m tests.full_size em1d 14 256 5 --lib ref > tests/golden/full_size_em1d_ref.json
+
+(the reference itself gives the same per-cell energies at 128^2 and 256^2 to 4e-5; its Gauss residual is
+1.4e-6 .. 2.1e-6 of the species density and its deposited charge sums to q*np within 2e-9).
+Each case runs in its own process: the big ones take 120 - 150 GB of HBM.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TOL_CHARGE_SUM = 1e-6      # |sum(rho) - q np| / |q np|
+TOL_GAUSS = 1e-5           # max |div E - rho - (div E - rho)(0)| / species density
+TOL_ENERGY_CELL = 1e-3     # energy per cell against the reference run at equal ppc (other random stream)
+TOL_FIELD_CELL = 1e-2      # field energy per cell, em2d (uniform Jz of the counter-streaming species drives Ez)
+TOL_DRIFT_1D = 1e-6        # em1d two-stream, first steps: energy is conserved to rounding (reference: 3e-10)
+
+CASES = [
+    # code, n, ppc, device-side initialisation
+    ("em2d", 256, 8, False),        # the golden size, species built on the host with the reference stream
+    ("em2d", 4096, 8, True),        # BASELINE configs[1]: 4096^2 cells, 2 species x 64 ppc = 2^31 particles
+    ("em1d", 14, 256, False),
+    ("em1d", 22, 256, True),        # BASELINE configs[4]: 2^22 cells x 256 ppc (x 2 beams) = 2^31 particles
+]
+
+
+def _golden(code):
+    with open(os.path.join(REPO, "tests", "golden", "full_size_%s_ref.json" % code)) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("code,n,ppc,device_init", CASES)
+def test_properties_hold_at_any_size(code, n, ppc, device_init):
+    g = _golden(code)
+    cmd = [sys.executable, "-m", "tests.full_size", code, str(n), str(ppc), str(g["steps"])]
+    if device_init:
+        cmd.append("--device-init")
+    r = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = json.loads(r.stdout.strip().splitlines()[-1])
+    cells = n * n if code == "em2d" else 1 << n
+    assert m["cells"] == cells and m["ppc"] == g["ppc"]
+    assert m["np0"] == [cells * m["ppc"]] * 2
+    assert m["npK"] == m["np0"]                                        # periodic box: nothing lost, nothing doubled
+    assert max(m["charge_sum_rel"]) < TOL_CHARGE_SUM, m
+    assert m["gauss_max"] < TOL_GAUSS, m
+    for key in ("energy_1", "energy_K"):
+        ours, ref = m[key] / m["cells"], g[key] / g["cells"]
+        assert abs(ours - ref) < TOL_ENERGY_CELL * abs(ref), (key, ours, ref)
+    if code == "em2d":
+        ours, ref = m["field_energy_K"] / m["cells"], g["field_energy_K"] / g["cells"]
+        assert abs(ours - ref) < TOL_FIELD_CELL * abs(ref), (ours, ref)
+    else:
+        assert m["energy_rel_drift"] < TOL_DRIFT_1D, m
