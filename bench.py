@@ -15,6 +15,7 @@ re-binned every step; per-GPU work is kept fixed for N>1 (weak scaling: the box 
 Extra keys (see the task contract): `roofline` for the dominant kernel (k_push2d) from CUDA
 events recorded around its launches on the library stream; `cpu_baseline` = the unmodified
 reference (oracle/_ref, -Ofast as shipped) timed on one host core over a bounded sample;
+`cells` = cell-updates/s of the grid half of the step (current_update + emf_advance) timed alone;
 `e2e` = the same metric through the public C API (sim_new / sim_iter) with HOST buffers, i.e.
 host->device upload of particles+fields and device->host download inside every timed step.
 """
@@ -35,6 +36,7 @@ sys.path.insert(0, REPO)
 METRIC = "particle-pushes/sec (push+deposit)"
 UNIT = "pushes/s"
 BYTES_PER_PUSH = 56.0          # algorithmic: 28 B read + 28 B write per particle
+BYTES_PER_CELL = 72.0          # algorithmic, grid half of a step: E,B read + write (48 B), J zeroed and read (24 B)
 CELL = 0.1                     # dx of the shipped Weibel deck (em2d/input/weibel.c:17-18)
 DT = 0.07
 
@@ -125,6 +127,34 @@ def fit_grid(lib, n, ppc_total):
             break
         n //= 2
     return n, free_b.value
+
+
+def time_grid_term(lib, sim, n, reps=20):
+    """cell-updates/s of the grid half of a step alone - current_zero, current_update (guard fold; the Weibel
+    deck does not smooth) and emf_advance (yee_b, yee_e, yee_b, guard refresh) through the public C API
+    (em2d/current.c:98-183, em2d/emf.c:688-716), CUDA events on the library stream.  The grids (3 x 202 MB
+    at 4096^2) exceed the L2, so consecutive repetitions do not feed each other from cache."""
+    def grid_half():
+        lib.current_zero(C.byref(sim.current))
+        lib.current_update(C.byref(sim.current))
+        lib.emf_advance(C.byref(sim.emf), C.byref(sim.current))
+    for _ in range(3):
+        grid_half()
+    e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
+    lib.zdev_sync()
+    n0 = lib.zdev_launch_count()
+    lib.zdev_event_record(e0)
+    for _ in range(reps):
+        grid_half()
+    lib.zdev_event_record(e1)
+    ms = lib.zdev_event_elapsed_ms(e0, e1) / reps
+    peak, peak_src = peaks()
+    gbs = BYTES_PER_CELL * n * n / (ms * 1e-3) / 1e9
+    return {"value": n * n / (ms * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms,
+            "kernels_per_step": int((lib.zdev_launch_count() - n0) // reps),
+            "algorithmic_bytes_per_cell": BYTES_PER_CELL, "achieved": gbs, "peak": peak, "frac": gbs / peak,
+            "what": "current_zero + current_update + emf_advance alone on the %dx%d grid (the grid term of the "
+                    "step; with the particles it is %s of a step)" % (n, n, "%.1f %%")}
 
 
 def run_slabs(args, lib, rank, world, local):
@@ -245,6 +275,8 @@ def run_ours(args):
         lib.zdev_spec2d_fetch(handles[0], C.byref(en), C.byref(cnt))
         assert cnt.value == n * n * args.ppc * args.ppc, "particles were lost: %d" % cnt.value
         value = np_total * K / (ms * 1e-3)
+        cells = time_grid_term(lib, sim, n)
+        cells["what"] = cells["what"] % (100.0 * cells["ms_per_step"] / (ms / K))
         lib.sim_delete(C.byref(sim))
 
     out = None
@@ -278,6 +310,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1:
+            out["cells"] = cells
             out["e2e"] = run_e2e(lib, A, args, n)
             out["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds, threads=1)
         else:
