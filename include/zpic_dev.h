@@ -106,6 +106,9 @@ void zdev_emf_set_ext_grid( zdev_grid2d* g, const float* host_ext_e, const float
  * shift_window with the reference's float test (emf.c:650). */
 void zdev_emf_advance( zdev_grid2d* g, zdev_grid2d* g_cur, float dt, float dx, float dy,
                        int moving_window, int shift_window );
+/* The three stencils of emf_advance run as ONE kernel by default (60 B instead of 132 B of traffic per cell,
+ * bit-identical results); 0 selects the three separate kernels below ($ZPIC_FUSED_YEE=0 does the same). */
+void zdev_yee_set_fused( int on );
 /* pieces, for kernel-level parity tests */
 void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c:500-522 */
 void zdev_yee_e( zdev_grid2d* g, zdev_grid2d* g_cur, float dt_dx, float dt_dy, float dt );  /* emf.c:531-562 */

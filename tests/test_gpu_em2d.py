@@ -36,11 +36,16 @@ def _fill_random(deck, rng, amp=1.0):
     return vals
 
 
-def test_field_solver_bit_exact(ours, ref):
-    """yee_b/yee_e/yee_b + guard refresh on random E, B, J: every cell, guards included"""
+@pytest.mark.parametrize("mw,fused", [(0, 1), (1, 1), (0, 0)])
+def test_field_solver_bit_exact(ours, ref, mw, fused, monkeypatch):
+    """yee_b/yee_e/yee_b + guard refresh on random E, B, J: every cell, guards included.  mw = 1: the x guards
+    are NOT refreshed (moving window, em2d/emf.c:581), so the raw stencil results in the guard columns are
+    compared too (1 step: the window does not shift yet).  fused = 0: the three separate stencil kernels
+    (the one-pass kernel is the default; the switch is read once per process, hence the seam call below)."""
     rng = np.random.default_rng(1)
     a = H.Deck(ours, (70, 45), (7.0, 9.0), 0.05)
     b = H.Deck(ref, (70, 45), (7.0, 9.0), 0.05)
+    b.sim.emf.moving_window = mw
     e, bb, j = _fill_random(a, rng)
     for d in (a, b):
         d.E()[...] = e
@@ -54,9 +59,12 @@ def test_field_solver_bit_exact(ours, ref):
     lib.zdev_grid2d_upload(g, 0, e.ctypes.data)
     lib.zdev_grid2d_upload(g, 1, bb.ctypes.data)
     lib.zdev_grid2d_upload(g, 2, j.ctypes.data)
-    for it in range(3):
-        lib.zdev_emf_advance(g, g, 0.05, float(np.float32(7.0) / np.float32(70)), float(np.float32(9.0) / np.float32(45)), 0, 0)
+    lib.zdev_yee_set_fused(fused)
+    for it in range(3 - 2 * mw):
+        lib.zdev_emf_advance(g, g, 0.05, float(np.float32(7.0) / np.float32(70)), float(np.float32(9.0) / np.float32(45)), mw, 0)
         ref.emf_advance(C.byref(b.sim.emf), C.byref(b.sim.current))
+    lib.zdev_yee_set_fused(1)
+    assert b.sim.emf.n_move == 0
     eo = np.empty_like(e)
     bo = np.empty_like(e)
     lib.zdev_grid2d_download(g, 0, eo.ctypes.data)

@@ -67,6 +67,7 @@ def _declare_dev(lib):
         "zdev_emf_set_ext_uniform": (None, [vp, i, fp, i, fp]),
         "zdev_emf_set_ext_grid": (None, [vp, vp, vp]),
         "zdev_emf_advance": (None, [vp, vp, f, f, f, i, i]),
+        "zdev_yee_set_fused": (None, [i]),
         "zdev_yee_b": (None, [vp, f, f]), "zdev_yee_e": (None, [vp, vp, f, f, f]),
         "zdev_emf_update_gc": (None, [vp, i]), "zdev_emf_move_window": (None, [vp]),
         "zdev_emf_energy": (None, [vp, C.POINTER(C.c_double)]),

@@ -13,7 +13,8 @@ struct zdev_grid2d {
 	int nx, ny, nrow, nrows;
 	size_t ncell;            // (nx+3)*(ny+3)
 	f3 *E, *B, *J;           // point at buffer start, i.e. cell (-1,-1)
-	f3 *tmp;                 // scratch of the same size (smoothing ping-pong, window shift)
+	f3 *tmp;                 // scratch of the same size (smoothing ping-pong, window shift, fused field advance)
+	f3 *tmp2;                // second scratch, only for the fused field advance (E and B both move out of place)
 	f3 *Epart, *Bpart;       // fields seen by particles; alias E/B unless external fields are on
 	f3 *Eext, *Bext;         // cached custom external fields (or null)
 	int e_ext, b_ext;        // 0 none, 1 uniform, 2 grid
@@ -48,6 +49,7 @@ static void need_EB(zdev_grid2d* g) {
 }
 static void need_J(zdev_grid2d* g) { if (!g->J) g->J = grid_alloc_zero(g); }
 static void need_tmp(zdev_grid2d* g) { if (!g->tmp) g->tmp = grid_alloc_zero(g); }
+static void need_tmp2(zdev_grid2d* g) { if (!g->tmp2) g->tmp2 = grid_alloc_zero(g); }
 
 extern "C" void zdev_grid2d_destroy(zdev_grid2d* g) {
 	if (!g) return;
@@ -55,7 +57,7 @@ extern "C" void zdev_grid2d_destroy(zdev_grid2d* g) {
 	if (g->e_ext) cudaFree(g->Epart);
 	if (g->b_ext) cudaFree(g->Bpart);
 	cudaFree(g->Eext); cudaFree(g->Bext);
-	cudaFree(g->E); cudaFree(g->B); cudaFree(g->J); cudaFree(g->tmp); cudaFree(g->d_sums);
+	cudaFree(g->E); cudaFree(g->B); cudaFree(g->J); cudaFree(g->tmp); cudaFree(g->tmp2); cudaFree(g->d_sums);
 	free(g);
 }
 
@@ -128,6 +130,162 @@ extern "C" void zdev_yee_e(zdev_grid2d* g, zdev_grid2d* gj, float dt_dx, float d
 	need_EB(g); need_J(gj); check_same_shape(g, gj);
 	dim3 blk(64, 4), grd(zdev_div_up(g->nx + 2, 64), zdev_div_up(g->ny + 2, 4));
 	ZDEV_LAUNCH(k_yee_e, grd, blk, 0, g->E, g->B, gj->J, g->nx, g->ny, g->nrow, dt_dx, dt_dy, dt);
+}
+
+// ---- yee_b(dt/2), yee_e(dt), yee_b(dt/2) in ONE pass over the grids (reference em2d/emf.c:694-698).
+// The three stencils separately move 132 B per cell (E is read twice and rewritten once, B is rewritten
+// twice and read a third time); fused they move 60: every CTA stages the E and B neighbourhood of its tile
+// in shared memory, applies the three updates there with the reference's own loop bounds as masks, and
+// writes the tile of the new E and B OUT OF PLACE (a neighbouring CTA may still be reading the old halo).
+//   new B on the tile T needs new E on T + its upper neighbours, new E there needs the half-step B on one
+//   more lower layer, and that needs old E on one more upper layer:
+//   sE = old E on [A-1, A+W+1] x [R-1, R+H+1],  sB = old B on [A-1, A+W] x [R-1, R+H]  (buffer indices).
+// The halo results are computed redundantly with exactly the arithmetic of their owner CTA, so every cell
+// (guards included) is bit-identical to the three separate kernels.
+#ifndef YF_H_N
+#define YF_H_N 16
+#endif
+#ifndef YF_TY_N
+#define YF_TY_N 4
+#endif
+constexpr int YF_W = 64, YF_H = YF_H_N, YF_TY = YF_TY_N, YF_THREADS = YF_W * YF_TY;
+constexpr int YF_EW = YF_W + 3, YF_EH = YF_H + 3, YF_BW = YF_W + 2, YF_BH = YF_H + 2, YF_JW = YF_W + 1, YF_JH = YF_H + 1;
+
+// 4-byte asynchronous copy global -> shared (LDGSTS): no register, no wait; ok = false writes a zero
+__device__ __forceinline__ void yf_cp4(float* sdst, const float* gsrc, bool ok) {
+	const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(sa), "l"(gsrc), "r"(ok ? 4 : 0) : "memory");
+}
+// yee_b on one cell: e = E here, ex = E at i+1, ey = E at j+1 (reference em2d/emf.c:514-520)
+__device__ __forceinline__ void yf_b(f3& b, const f3 e, const f3 ex, const f3 ey, float dt_dx, float dt_dy) {
+	b.x += ( - dt_dy * ( ey.z - e.z ) );
+	b.y += (   dt_dx * ( ex.z - e.z ) );
+	b.z += ( - dt_dx * ( ex.y - e.y ) + dt_dy * ( ey.x - e.x ) );
+}
+
+// The neighbourhoods arrive as flat runs of floats per buffer row through asynchronous 4-byte copies (rows
+// of the reference layout are only 4-byte aligned, so no bulk copies): every thread issues all its copies
+// back to back and waits once, instead of one DRAM round trip per row.  In the stencil phases thread (tx, ty)
+// of the 64 x YF_TY CTA walks rows ty, ty+YF_TY, ... at column tx; the one or two extra halo columns of a
+// region are taken by the first threads of each row.  12-byte cells in shared memory are conflict free
+// (stride 3 words).
+__global__ void __launch_bounds__(YF_THREADS)
+k_yee_fused(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__ E, const f3* __restrict__ B,
+            const f3* __restrict__ J, int nrow, int nrows, float hdt_dx, float hdt_dy, float dt_dx, float dt_dy, float dt) {
+	__shared__ f3 sE[YF_EH * YF_EW];
+	__shared__ f3 sB[YF_BH * YF_BW];
+	__shared__ f3 sJ[YF_JH * YF_JW];
+	const int A = blockIdx.x * YF_W, R = blockIdx.y * YF_H;       // buffer column / row of the tile origin
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	{	// ---- old E on [A-1, A+W+1] x [R-1, R+H+1], old B on [A-1, A+W] x [R-1, R+H], J on [A, A+W] x [R, R+H]
+		const int tid = ty * YF_W + tx;
+		const long rowf = (long) nrow * 3;                          // floats per buffer row
+		const float* gE = reinterpret_cast<const float*>(E);
+		const float* gB = reinterpret_cast<const float*>(B);
+		const float* gJ = reinterpret_cast<const float*>(J);
+		float* fE = reinterpret_cast<float*>(sE);
+		float* fB = reinterpret_cast<float*>(sB);
+		float* fJ = reinterpret_cast<float*>(sJ);
+		#pragma unroll 1
+		for (int r = 0; r < YF_EH; r++) {
+			const int bj = R - 1 + r;
+			const bool rok = bj >= 0 && bj < nrows;
+			for (int f = tid; f < YF_EW * 3; f += YF_THREADS) {
+				const long fo = (long) (A - 1) * 3 + f;             // float offset inside the buffer row
+				const bool ok = rok && fo >= 0 && fo < rowf;
+				const long go = ok ? (long) bj * rowf + fo : 0;
+				yf_cp4(fE + r * (YF_EW * 3) + f, gE + go, ok);
+				if (r < YF_BH && f < YF_BW * 3) yf_cp4(fB + r * (YF_BW * 3) + f, gB + go, ok);
+			}
+		}
+		#pragma unroll 1
+		for (int r = 0; r < YF_JH; r++) {
+			const int bj = R + r;
+			for (int f = tid; f < YF_JW * 3; f += YF_THREADS) {
+				const long fo = (long) A * 3 + f;
+				const bool ok = bj < nrows && fo < rowf;
+				yf_cp4(fJ + r * (YF_JW * 3) + f, gJ + (ok ? (long) bj * rowf + fo : 0), ok);
+			}
+		}
+		asm volatile("cp.async.wait_all;" ::: "memory");
+	}
+	__syncthreads();
+	// ---- yee_b(dt/2) on the whole sB region: cells i in [-1,nx], j in [-1,ny] = buffer [0,nrow-2] x [0,nrows-2]
+	#pragma unroll
+	for (int r = ty; r < YF_BH; r += YF_TY) {
+		const int bj = R - 1 + r;
+		const bool rok = bj >= 0 && bj <= nrows - 2;
+		#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int c = h ? YF_W + tx : tx;
+			if (h && tx >= 2) break;
+			const int bi = A - 1 + c;
+			if (rok && bi >= 0 && bi <= nrow - 2) {
+				f3 b = sB[r * YF_BW + c];
+				yf_b(b, sE[r * YF_EW + c], sE[r * YF_EW + c + 1], sE[(r + 1) * YF_EW + c], hdt_dx, hdt_dy);
+				sB[r * YF_BW + c] = b;
+			}
+		}
+	}
+	__syncthreads();
+	// ---- yee_e(dt) on the tile and its upper neighbours: cells i in [0,nx+1], j in [0,ny+1] = buffer [1,nrow-1] x [1,nrows-1]
+	#pragma unroll
+	for (int rr = ty; rr < YF_JH; rr += YF_TY) {
+		const int bj = R + rr;
+		const bool rok = bj >= 1 && bj <= nrows - 1;
+		#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const int cc = h ? YF_W : tx;
+			if (h && tx >= 1) break;
+			const int bi = A + cc;
+			if (rok && bi >= 1 && bi <= nrow - 1) {
+				const int r = rr + 1, c = cc + 1;                   // position in sE / sB
+				const f3 b = sB[r * YF_BW + c], bx = sB[r * YF_BW + c - 1], by = sB[(r - 1) * YF_BW + c];
+				const f3 jc = sJ[rr * YF_JW + cc];
+				f3 e = sE[r * YF_EW + c];
+				e.x += ( + dt_dy * ( b.z - by.z ) ) - dt * jc.x;
+				e.y += ( - dt_dx * ( b.z - bx.z ) ) - dt * jc.y;
+				e.z += ( + dt_dx * ( b.y - bx.y ) - dt_dy * ( b.x - by.x ) ) - dt * jc.z;
+				sE[r * YF_EW + c] = e;
+			}
+		}
+	}
+	__syncthreads();
+	// ---- yee_b(dt/2) on the tile from the new E; both grids leave from registers
+	#pragma unroll
+	for (int rr = ty; rr < YF_H; rr += YF_TY) {
+		const int bi = A + tx, bj = R + rr;
+		if (bi < nrow && bj < nrows) {
+			const int r = rr + 1, c = tx + 1;
+			const f3 e = sE[r * YF_EW + c];
+			f3 b = sB[r * YF_BW + c];
+			if (bi <= nrow - 2 && bj <= nrows - 2)
+				yf_b(b, e, sE[r * YF_EW + c + 1], sE[(r + 1) * YF_EW + c], hdt_dx, hdt_dy);
+			const long o = (long) bj * nrow + bi;
+			Eout[o] = e;
+			Bout[o] = b;
+		}
+	}
+}
+
+// ZPIC_FUSED_YEE=0 (or zdev_yee_set_fused(0)) keeps the three separate stencil kernels
+static int fused_yee = -1;
+static int fused_yee_on() {
+	if (fused_yee < 0) { const char* e = getenv("ZPIC_FUSED_YEE"); fused_yee = (e && e[0] == '0') ? 0 : 1; }
+	return fused_yee;
+}
+extern "C" void zdev_yee_set_fused(int on) { fused_yee = on ? 1 : 0; }
+static void yee_fused(zdev_grid2d* g, zdev_grid2d* gj, float dt, float dx, float dy) {
+	need_EB(g); need_J(gj); check_same_shape(g, gj); need_tmp(g); need_tmp2(g);
+	const float dtb = dt / 2.0f;
+	const int alias_e = (g->Epart == g->E), alias_b = (g->Bpart == g->B);
+	dim3 grd(zdev_div_up(g->nrow, YF_W), zdev_div_up(g->nrows, YF_H));
+	ZDEV_LAUNCH(k_yee_fused, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
+	            dtb / dx, dtb / dy, dt / dx, dt / dy, dt);
+	{ f3* t = g->E; g->E = g->tmp; g->tmp = t; }
+	{ f3* t = g->B; g->B = g->tmp2; g->tmp2 = t; }
+	if (alias_e) g->Epart = g->E;
+	if (alias_b) g->Bpart = g->B;
 }
 
 // ------------------------------------------------------------------ guard cells
@@ -399,10 +557,14 @@ extern "C" void zdev_emf_set_ext_grid(zdev_grid2d* g, const float* he, const flo
 
 extern "C" void zdev_emf_advance(zdev_grid2d* g, zdev_grid2d* gj, float dt, float dx, float dy, int moving_window, int shift_window) {
 	// reference em2d/emf.c:694-698, scalars formed exactly as in yee_b/yee_e (:509-510, :537-538)
-	float dtb = dt / 2.0f;
-	zdev_yee_b(g, dtb / dx, dtb / dy);
-	zdev_yee_e(g, gj, dt / dx, dt / dy, dt);
-	zdev_yee_b(g, dtb / dx, dtb / dy);
+	if (fused_yee_on()) {
+		yee_fused(g, gj, dt, dx, dy);
+	} else {
+		float dtb = dt / 2.0f;
+		zdev_yee_b(g, dtb / dx, dtb / dy);
+		zdev_yee_e(g, gj, dt / dx, dt / dy, dt);
+		zdev_yee_b(g, dtb / dx, dtb / dy);
+	}
 	zdev_emf_update_gc(g, moving_window);
 	update_part_fld(g);
 	if (shift_window) {
