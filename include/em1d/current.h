@@ -27,11 +27,15 @@ typedef struct Current {
 	enum current_boundary bc_type;
 } t_current;
 
+/* replaces em1d/current.c:31-73 */
 void current_new( t_current *current, int nx, float box, float dt );
+/* replaces em1d/current.c:80-86 */
 void current_delete( t_current *current );
+/* replaces em1d/current.c:93-101 */
 void current_zero( t_current *current );
 /* device: periodic guard fold + binomial / compensated filter (reference em1d/current.c:112-155, 265-333) */
 void current_update( t_current *current );
+/* replaces em1d/current.c:167-230 */
 void current_report( const t_current *current, const int jc );
 
 #endif

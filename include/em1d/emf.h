@@ -53,15 +53,23 @@ typedef struct EMF_Laser {
 	float a0, omega0, polarization;
 } t_emf_laser;
 
+/* replaces em1d/emf.c:590-609 */
 void emf_get_energy( const t_emf *emf, double energy[] );
+/* replaces em1d/emf.c:56-114 */
 void emf_new( t_emf *emf, int nx, float box, const float dt );
+/* replaces em1d/emf.c:124-142 */
 void emf_delete( t_emf *emf );
+/* replaces em1d/emf.c:278-365 */
 void emf_report( const t_emf *emf, const char field, const int fc );
+/* replaces em1d/emf.c:191-260 */
 void emf_add_laser( t_emf* const emf, t_emf_laser* laser );
+/* replaces em1d/emf.c:764-811 */
 void emf_init_fld( t_emf* const emf, t_emf_init_fld* init_fld );
+/* replaces em1d/emf.c:623-686 */
 void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld );
 /* device: yee_b, yee_e, Mur boundary, yee_b, guards, ext. fields, window shift (reference em1d/emf.c:548-590) */
 void emf_advance( t_emf *emf, const t_current *current );
+/* replaces em1d/emf.c:34-37 */
 double emf_time( void );
 
 #endif

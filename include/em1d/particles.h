@@ -57,16 +57,23 @@ typedef struct Species {
 	int n_sort;
 } t_species;
 
+/* replaces em1d/particles.c:511-584 */
 void spec_new( t_species* spec, char name[], const float m_q, const int ppc,
                const float ufl[], const float uth[],
                const int nx, float box, const float dt, t_density* density );
+/* replaces em1d/particles.c:621-625 */
 void spec_delete( t_species* spec );
+/* replaces em1d/particles.c:460-466 */
 void spec_grow_buffer( t_species* spec, const int size );
 /* device: interpolate + Boris + split-segment deposit + boundaries (reference em1d/particles.c:919-1074) */
 void spec_advance( t_species* spec, t_emf* emf, t_current* current );
+/* replaces em1d/particles.c:594-614 */
 void spec_move_window( t_species *spec );
+/* replaces em1d/particles.c:48-51 */
 uint64_t spec_npush( void );
+/* replaces em1d/particles.c:38-41 */
 double spec_time( void );
+/* replaces em1d/particles.c:58-61 */
 double spec_perf( void );
 
 #define CHARGE      0x1000
@@ -78,10 +85,13 @@ double spec_perf( void );
 #define U3          0x0006
 #define PHASESPACE(a,b) ((a) + (b)*16 + PHA)
 
+/* replaces em1d/particles.c:1323-1386 */
 void spec_deposit_pha( const t_species *spec, const int rep_type,
                        const int pha_nx[], const float pha_range[][2], float* buf );
+/* replaces em1d/particles.c:1477-1493 */
 void spec_report( const t_species *spec, const int rep_type,
                   const int pha_nx[], const float pha_range[][2] );
+/* replaces em1d/particles.c:1093-1112 */
 void spec_deposit_charge( const t_species* spec, float* charge );
 
 #endif

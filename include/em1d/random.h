@@ -6,6 +6,8 @@
 #include <stdint.h>
 /* NB the reference definition assigns the FIRST argument to m_w (random.c:25-29) */
 void set_rand_seed( uint32_t m_z_, uint32_t m_w_ );
+/* replaces em1d/random.c:48-53 */
 uint32_t rand_uint32( void );
+/* replaces em1d/random.c:67-101 */
 double rand_norm( void );
 #endif

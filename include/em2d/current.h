@@ -30,7 +30,9 @@ typedef struct Current {
 	int moving_window;
 } t_current;
 
+/* replaces em2d/current.c:30-79 */
 void current_new( t_current *current, int nx[], float box[], float dt );
+/* replaces em2d/current.c:86-91 */
 void current_delete( t_current *current );
 /* device: cudaMemsetAsync of the whole J buffer (reference current.c:98-107) */
 void current_zero( t_current *current );

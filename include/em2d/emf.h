@@ -57,15 +57,21 @@ typedef struct EMF_Laser {
 
 /* device reduction, 6 doubles (reference emf.c:729-750) */
 void emf_get_energy( const t_emf *emf, double energy[] );
+/* replaces em2d/emf.c:56-113 */
 void emf_new( t_emf *emf, int nx[], float box[], const float dt );
+/* replaces em2d/emf.c:123-142 */
 void emf_delete( t_emf *emf );
+/* replaces em2d/emf.c:368-485 */
 void emf_report( const t_emf *emf, const char field, const int fc );
 /* host double-precision launch, then device refresh (reference emf.c:242-350) */
 void emf_add_laser( t_emf* const emf, t_emf_laser* laser );
+/* replaces em2d/emf.c:922-980 */
 void emf_init_fld( t_emf* const emf, t_emf_init_fld* init_fld );
+/* replaces em2d/emf.c:764-831 */
 void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld );
 /* device: yee_b, yee_e, yee_b, guard refresh, ext. fields, window shift (reference emf.c:688-716) */
 void emf_advance( t_emf *emf, const t_current *current );
+/* replaces em2d/emf.c:34-37 */
 double emf_time( void );
 
 #endif

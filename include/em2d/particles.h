@@ -56,17 +56,24 @@ typedef struct Species {
 	int n_sort;
 } t_species;
 
+/* replaces em2d/particles.c:535-609 */
 void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
                const float ufl[], const float uth[],
                const int nx[], float box[], const float dt, t_density* density );
+/* replaces em2d/particles.c:647-651 */
 void spec_delete( t_species* spec );
+/* replaces em2d/particles.c:460-466 */
 void spec_grow_buffer( t_species* spec, const int size );
 /* device: fused interpolate + Boris + split-segment deposit, boundaries, window,
  * tile re-binning (reference particles.c:1104-1269) */
 void spec_advance( t_species* spec, t_emf* emf, t_current* current );
+/* replaces em2d/particles.c:619-640 */
 void spec_move_window( t_species *spec );
+/* replaces em2d/particles.c:46-49 */
 uint64_t spec_npush( void );
+/* replaces em2d/particles.c:36-39 */
 double spec_time( void );
+/* replaces em2d/particles.c:56-59 */
 double spec_perf( void );
 
 /* diagnostics selectors (reference particles.h:230-246) */
@@ -80,10 +87,13 @@ double spec_perf( void );
 #define U3          0x0006
 #define PHASESPACE(a,b) ((a) + (b)*16 + PHA)
 
+/* replaces em2d/particles.c:1569-1632 */
 void spec_deposit_pha( const t_species *spec, const int rep_type,
                        const int pha_nx[], const float pha_range[][2], float* buf );
+/* replaces em2d/particles.c:1725-1741 */
 void spec_report( const t_species *spec, const int rep_type,
                   const int pha_nx[], const float pha_range[][2] );
+/* replaces em2d/particles.c:1289-1324 */
 void spec_deposit_charge( const t_species* spec, float* charge );
 
 #endif

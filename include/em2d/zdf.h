@@ -69,22 +69,36 @@ typedef struct ZDF_PartInfo {
 	char** qunits;
 } t_zdf_part_info;
 
+/* replaces em2d/zdf.c:135-155 */
 size_t zdf_sizeof( enum zdf_data_type data_type );
+/* replaces em2d/zdf.c:183-270 */
 int zdf_open_file( t_zdf_file* zdf, const char* filename, enum zdf_file_access_mode mode );
+/* replaces em2d/zdf.c:166-174 */
 int zdf_close_file( t_zdf_file* zdf );
+/* replaces em2d/zdf.c:893-909 */
 size_t zdf_add_string( t_zdf_file* zdf, const char* name, const char* str );
+/* replaces em2d/zdf.c:918-934 */
 size_t zdf_add_int32( t_zdf_file* zdf, const char* name, const int32_t value );
+/* replaces em2d/zdf.c:943-956 */
 size_t zdf_add_double( t_zdf_file* zdf, const char* name, const double value );
+/* replaces em2d/zdf.c:969-987 */
 size_t zdf_add_iteration( t_zdf_file* zdf, const t_zdf_iteration* iter );
+/* replaces em2d/zdf.c:1021-1056 */
 size_t zdf_add_grid_info( t_zdf_file* zdf, const t_zdf_grid_info* grid );
+/* replaces em2d/zdf.c:1083-1109 */
 size_t zdf_add_part_info( t_zdf_file* zdf, const t_zdf_part_info* part );
+/* replaces em2d/zdf.c:1241-1268 */
 size_t zdf_add_dataset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+/* replaces em2d/zdf.c:1500-1528 */
 int zdf_open_grid_file( t_zdf_file *file, const t_zdf_grid_info *info,
                         const t_zdf_iteration *iteration, char const path[] );
+/* replaces em2d/zdf.c:1540-1562 */
 int zdf_save_grid( const void* data, enum zdf_data_type data_type, const t_zdf_grid_info *info,
                    const t_zdf_iteration *iteration, char const path[] );
+/* replaces em2d/zdf.c:1572-1600 */
 int zdf_open_part_file( t_zdf_file *file, t_zdf_part_info *info,
                         const t_zdf_iteration *iteration, char const path[] );
+/* replaces em2d/zdf.c:1610-1624 */
 int zdf_add_quant_part_file( t_zdf_file *zdf, const char *name, const float* data, const uint64_t np );
 
 #endif
