@@ -33,6 +33,15 @@ typedef struct ZDF_Dataset {
 	uint64_t offset;
 } t_zdf_dataset;
 
+/* one piece of a chunked dataset (reference zdf.h:117-122): `count` elements per direction placed at `start`
+ * with `stride` inside the dataset; data is contiguous */
+typedef struct ZDF_Chunk {
+	uint64_t count[zdf_max_dims];
+	uint64_t start[zdf_max_dims];
+	uint64_t stride[zdf_max_dims];
+	void* data;
+} t_zdf_chunk;
+
 enum zdf_axis_type { zdf_linear, zdf_log10, zdf_log2 };
 
 typedef struct ZDF_GridAxis {
@@ -69,6 +78,19 @@ typedef struct ZDF_PartInfo {
 	char** qunits;
 } t_zdf_part_info;
 
+/* particle tracks metadata (reference zdf.h:192-203) */
+typedef struct ZDF_TrackInfo {
+	char* name;
+	char* label;
+	uint32_t ntracks;
+	uint32_t ndump;
+	uint32_t niter;
+	uint32_t nquants;
+	char** quants;
+	char** qlabels;
+	char** qunits;
+} t_zdf_track_info;
+
 /* replaces em2d/zdf.c:135-155 */
 size_t zdf_sizeof( enum zdf_data_type data_type );
 /* replaces em2d/zdf.c:183-270 */
@@ -89,6 +111,30 @@ size_t zdf_add_grid_info( t_zdf_file* zdf, const t_zdf_grid_info* grid );
 size_t zdf_add_part_info( t_zdf_file* zdf, const t_zdf_part_info* part );
 /* replaces em2d/zdf.c:1241-1268 */
 size_t zdf_add_dataset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+/* raw vector of `len` elements: 8-bit data is zero-padded to a multiple of 4 bytes, wider types are not;
+ * returns the bytes written, 0 on error or when len is 0 (replaces em2d/zdf.c:735-756) */
+size_t zdf_vector_write( t_zdf_file* zdf, const void* data, enum zdf_data_type data_type, size_t len );
+/* replaces em2d/zdf.c:1135-1161 */
+size_t zdf_add_track_info( t_zdf_file* zdf, const t_zdf_track_info* tracks );
+/* Chunked datasets: a start record with the dataset header, any number of chunk records
+ * ("<id>-chunk": dataset id, count, start, stride, data), an end record ("<id>-end").
+ * replaces em2d/zdf.c:1277-1296 */
+size_t zdf_start_cdset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+/* replaces em2d/zdf.c:1303-1307 */
+size_t size_zdf_chunk_header( const t_zdf_dataset* dataset );
+/* replaces em2d/zdf.c:1316-1359 */
+size_t zdf_write_chunk_header( t_zdf_file* zdf, t_zdf_dataset* dataset, t_zdf_chunk* chunk );
+/* replaces em2d/zdf.c:1369-1385 */
+size_t zdf_write_cdset( t_zdf_file* zdf, t_zdf_dataset* dataset, t_zdf_chunk* chunk );
+/* replaces em2d/zdf.c:1393-1409 */
+size_t zdf_end_cdset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+/* find a (chunked) dataset by name in a file opened with ZDF_READ / ZDF_UPDATE and load its header; the file
+ * position ends up at the end of the file. 1 on success; 0 on read errors, which includes running off the
+ * end of the file when there is no such dataset (replaces em2d/zdf.c:1412-1457) */
+size_t zdf_open_dataset( t_zdf_file* zdf, t_zdf_dataset* dataset );
+/* grow the dimensions recorded in the dataset header in place; 1 on success, -1 if a dimension would
+ * shrink (replaces em2d/zdf.c:1470-1488) */
+int zdf_extend_dataset( t_zdf_file* zdf, t_zdf_dataset* dataset, uint64_t* new_count );
 /* replaces em2d/zdf.c:1500-1528 */
 int zdf_open_grid_file( t_zdf_file *file, const t_zdf_grid_info *info,
                         const t_zdf_iteration *iteration, char const path[] );

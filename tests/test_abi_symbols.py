@@ -63,3 +63,20 @@ def test_library_exports_every_declared_symbol(code):
     # sim_init / sim_report are IMPORTED from the deck, like in the reference (em2d/main.c:32-36)
     missing = [n for n in missing if n not in ("sim_init", "sim_report")]
     assert not missing, missing
+
+
+@pytest.mark.parametrize("code", ["em2d", "em1d"])
+def test_headers_declare_the_whole_reference_api(code):
+    """every function a reference header of the code directory declares is declared by our header of the same
+    name (and therefore exported, by the test above); runs where the reference tree is present"""
+    ref_dir = os.path.join(os.environ.get("ZPIC_REFERENCE", "/root/reference"), code)
+    if not os.path.isdir(ref_dir):
+        pytest.skip("reference tree not present")
+    checked = 0
+    for h in headers(code):
+        ref_h = os.path.join(ref_dir, os.path.basename(h))
+        assert os.path.exists(ref_h), ref_h
+        missing = declared(ref_h) - declared(h)
+        assert not missing, (os.path.basename(h), sorted(missing))
+        checked += len(declared(ref_h))
+    assert checked > 60
