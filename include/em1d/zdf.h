@@ -10,6 +10,9 @@
 #include <stdio.h>
 
 #define zdf_max_dims 3
+/* strings and 8-bit vectors are padded to this many bytes; length of the "ZDF1" magic (reference zdf.h) */
+#define BYTES_PER_ZDF_UNIT 4
+#define ZDF_MAGIC_LENGTH 4
 
 enum zdf_data_type {
 	zdf_null, zdf_int8, zdf_uint8, zdf_int16, zdf_uint16, zdf_int32, zdf_uint32,
