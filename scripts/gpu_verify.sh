@@ -12,3 +12,5 @@ PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_push2d -s 2 -c 1 -o gpurun_out/push_final -f python scripts/quick_push_probe.py 1024 8 2 > gpurun_out/ncu_final.log 2>&1
 python scripts/lwfa_probe.py 4096 1024 200 | tail -1
 python scripts/quick_push_probe1d.py 22 256 5 | tail -1
+python scripts/gpu_decks.py em2d | cut -c1-400
+python scripts/gpu_decks.py em1d | cut -c1-400
