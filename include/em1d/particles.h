@@ -20,13 +20,11 @@ enum density_type { UNIFORM, EMPTY, STEP, SLAB, RAMP, CUSTOM };
 
 /* reference em1d/particles.h:52-70 */
 typedef struct Density {
-	float n;
+	float n;                                  /* reference density (0 is read as 1) */
 	enum density_type type;
-	float start, end;
-	float ramp[2];
-	float (*custom)(float, void*);
-	void *custom_data;
-	unsigned long total_np_inj;
+	float start, end, ramp[2];                /* STEP / SLAB / RAMP limits and the two ramp densities */
+	float (*custom)(float, void*);  void *custom_data;        /* CUSTOM: n(x) = n * custom(x) */
+	unsigned long total_np_inj;               /* injector bookkeeping for the moving window */
 	double custom_q_inj;
 } t_density;
 
@@ -36,24 +34,18 @@ enum part_boundary { PART_BC_NONE, PART_BC_PERIODIC, PART_BC_OPEN };
 /* reference em1d/particles.h:86-135 */
 typedef struct Species {
 	char name[MAX_SPNAME_LEN+1];
-	t_part *part;
-	int np;
-	int np_max;
-	float m_q;
-	double energy;
-	float q;
+	t_part *part;                 /* host mirror of the population (the device copy is authoritative while stepping) */
+	int np, np_max;               /* particles in use / allocated in the mirror */
+	float m_q;                    /* mass over charge */
+	double energy;                /* kinetic energy of the last advance */
+	float q;                      /* charge of one simulation particle */
 	int ppc;
 	t_density density;
-	float ufl[3];
-	float uth[3];
+	float ufl[3], uth[3];         /* fluid / thermal momenta */
 	int nx;
-	float dx;
-	float box;
-	float dt;
-	int iter;
-	int moving_window;
-	int n_move;
-	enum part_boundary bc_type;
+	float dx, box, dt;
+	int iter, moving_window, n_move;
+	enum part_boundary bc_type;   /* re-read every step (decks poke it) */
 	int n_sort;
 } t_species;
 

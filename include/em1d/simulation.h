@@ -8,11 +8,9 @@
 #include "current.h"
 
 typedef struct Simulation {
-	float dt;
-	float tmax;
-	int ndump;
-	int n_species;
-	t_species* species;
+	float dt, tmax;              /* time step, end of the run */
+	int ndump, n_species;        /* report period (0: never); length of species[] */
+	t_species* species;          /* malloc'ed by the caller, freed by sim_delete */
 	t_emf emf;
 	t_current current;
 	int moving_window;

@@ -22,38 +22,29 @@ enum density_type { UNIFORM, EMPTY, STEP, SLAB, CUSTOM };
 
 /* injection profile (reference particles.h:55-78) */
 typedef struct Density {
-	float n;
+	float n;                                  /* reference density (0 is read as 1) */
 	enum density_type type;
-	float start, end;
-	float (*custom_x)(float, void*);
-	void *custom_data_x;
-	float (*custom_y)(float, void*);
-	void *custom_data_y;
-	unsigned long custom_x_total_part;
+	float start, end;                         /* STEP / SLAB limits along x */
+	float (*custom_x)(float, void*);  void *custom_data_x;     /* CUSTOM: n(x,y) = n * custom_x(x) * custom_y(y) */
+	float (*custom_y)(float, void*);  void *custom_data_y;
+	unsigned long custom_x_total_part;        /* injector bookkeeping for the moving window */
 	double custom_x_total_q;
 } t_density;
 
 /* species container (reference particles.h:85-132) */
 typedef struct Species {
 	char name[MAX_SPNAME_LEN+1];
-	t_part *part;
-	int np;
-	int np_max;
-	float m_q;
-	double energy;
-	float q;
+	t_part *part;                 /* host mirror of the population (the device copy is authoritative while stepping) */
+	int np, np_max;               /* particles in use / allocated in the mirror */
+	float m_q;                    /* mass over charge */
+	double energy;                /* kinetic energy of the last advance */
+	float q;                      /* charge of one simulation particle */
 	int ppc[2];
 	t_density density;
-	float ufl[3];
-	float uth[3];
+	float ufl[3], uth[3];         /* fluid / thermal momenta */
 	int nx[2];
-	float dx[2];
-	float box[2];
-	float dt;
-	int iter;
-	int moving_window;
-	int n_move;
-	int n_sort;
+	float dx[2], box[2], dt;
+	int iter, moving_window, n_move, n_sort;
 } t_species;
 
 /* replaces em2d/particles.c:535-609 */
