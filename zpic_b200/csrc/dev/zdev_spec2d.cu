@@ -132,6 +132,10 @@ struct zdev_spec2d {
 	std::vector<cudaEvent_t>* ev;    // 2*EV_RING events, created on first use
 	int ev_next, ev_pending;
 	double push_ms; int64_t push_launches, push_particles;
+	// PUSH_PRESORTED build variant: the per-step index sort runs as its own kernel and hands the push kernel
+	// perm[] (16-bit slot indices in cell order, per tile segment) and the live count of every tile
+	unsigned short* gperm; int64_t gperm_cap;
+	int* tile_nlive;
 };
 static const int EV_RING = 64;
 
@@ -262,6 +266,7 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl); cudaFree(s->tile_list);
+	cudaFree(s->gperm); cudaFree(s->tile_nlive);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -866,6 +871,86 @@ struct pair_rec { f2 x, y, ux, uy, uz; int ca, cb, ta, tb; };
 #endif
 static const int XQ_CAP = XQ_CAP_N;
 
+#ifdef PUSH_PRESORTED
+// ---- PUSH_PRESORTED build variant (unmeasured; A/B against the default with ZPIC_LIB_SUFFIX): the per-step
+// index sort of k_push2d's phase A as a kernel of its own.  It needs 33 KB of shared memory and 40 registers,
+// so 6 CTAs share an SM and hide each other's barriers and dependent shared-memory atomics - in the fused
+// kernel the two resident CTAs sit in that phase together, 20 % of the warp time for 10 % of the instructions.
+// Price: perm[] goes through global memory (2 B written + 2 B read per particle; the tile's 16 KB stay in L2).
+// Same algorithm as phase A below (lane-strided counting sort, see there), same result: perm[] = live slots of
+// the tile in cell order, nlive = their number.
+template <int TX, int TY>
+__global__ void __launch_bounds__(PUSH_THREADS)
+k_sort2d(soa2d A, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
+         unsigned short* __restrict__ gperm, int* __restrict__ tile_nlive, unsigned smem_keys, const int* __restrict__ tile_list) {
+	constexpr int NC = TX * TY;
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
+	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_keys);
+	__shared__ int s_cnt[NC], s_cur[NC];
+	__shared__ int s_wsum[PUSH_WARPS];
+	__shared__ __align__(8) unsigned long long s_bar;
+	const int t = tile_list[blockIdx.x];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int n = tile_np[t];
+	const int64_t base = tile_off[t];
+	if (threadIdx.x == 0) {
+		mbar_init(&s_bar, 1);
+		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
+	}
+	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
+	__syncthreads();
+	if (n > 0) mbar_wait(&s_bar, 0);
+	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	const int ws = (S + PUSH_WARPS - 1) / PUSH_WARPS;
+	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
+	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
+			if (c0 != KEY_EMPTY) atomicAdd(&s_cnt[c0], 1);
+			if (c1 != KEY_EMPTY) atomicAdd(&s_cnt[c1], 1);
+		}
+	}
+	__syncthreads();
+	int nlive;
+	{
+		int v = (threadIdx.x < NC) ? s_cnt[threadIdx.x] : 0;
+		int incl = v;
+		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+		if (lane == 31) s_wsum[warp] = incl;
+		__syncthreads();
+		int woff = 0, tot = 0;
+		#pragma unroll
+		for (int w = 0; w < PUSH_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
+		if (threadIdx.x < NC) s_cur[threadIdx.x] = woff + incl - v;
+		nlive = tot;
+		__syncthreads();
+	}
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
+			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
+			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
+		}
+	}
+	__syncthreads();
+	// perm[] leaves as 32-bit words (the tile segment starts on a 64-byte boundary; the odd last entry is padding)
+	{
+		const unsigned* src = reinterpret_cast<const unsigned*>(s_perm);
+		unsigned* dst = reinterpret_cast<unsigned*>(gperm + base);
+		for (int k = threadIdx.x; k < (nlive + 1) / 2; k += PUSH_THREADS) dst[k] = src[k];
+	}
+	if (threadIdx.x == 0) tile_nlive[t] = nlive;
+}
+#endif
+
 // dynamic shared memory of k_push2d: [keys during the sort | corner tile + queues afterwards][perm][raw planes]
 static size_t push_smem_front(int TX, int TY, int max_cap) {
 	size_t plane = (size_t) (TX + 2) * (TY + 2);
@@ -886,7 +971,11 @@ __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, mig2d mig,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
-         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm, const int* __restrict__ tile_list) {
+         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm, const int* __restrict__ tile_list
+#ifdef PUSH_PRESORTED
+         , const unsigned short* __restrict__ gperm, const int* __restrict__ tile_nlive
+#endif
+         ) {
 	constexpr int SROW = TX + 2;
 	constexpr int PLANE = SROW * (TY + 2);
 	constexpr int NC = TX * TY;
@@ -910,6 +999,25 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
 
+#ifdef PUSH_PRESORTED
+	// ---- perm[] was built by k_sort2d: one bulk copy into its place, in flight while the fields are staged
+	const int nlive = tile_nlive[t];
+	if (threadIdx.x == 0) {
+		s_nmig = 0; s_done = 0;
+		mbar_init(&s_bar, 1);
+		if (nlive > 0) bulk_load(s_perm, gperm + base, (unsigned) ((nlive * 2 + 15) & ~15), &s_bar);
+	}
+	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += PUSH_THREADS) {
+		int r = k / (cx + 2), c = k - r * (cx + 2);
+		int gi = (x0 + c) + (y0 + r) * g.nrow;        // buffer index of cell (x0-1+c, y0-1+r)
+		f3 e = E[gi], b = B[gi];
+		int o = c + r * SROW;
+		s_raw[o] = e.x; s_raw[o + PLANE] = e.y; s_raw[o + 2 * PLANE] = e.z;
+		s_raw[o + 3 * PLANE] = b.x; s_raw[o + 4 * PLANE] = b.y; s_raw[o + 5 * PLANE] = b.z;
+	}
+	__syncthreads();
+	(void) s_key; (void) s_cnt; (void) s_cur; (void) n;
+#else
 	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
 	if (threadIdx.x == 0) {
 		s_nmig = 0; s_done = 0;
@@ -979,6 +1087,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		}
 	}
 	__syncthreads();                                    // the keys are dead: their bytes become corner tile + queues
+#endif
 	// ---- the fields as the four corners of every cell (entries of the last row / column are never read)
 	for (int k = threadIdx.x; k < 6 * PLANE; k += PUSH_THREADS) {
 		const int pl = k / PLANE, o = k - pl * PLANE;
@@ -989,6 +1098,9 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_f4[k] = make_float4(P[o], P[o2], P[o1], P[o3]);
 	}
 	__syncthreads();
+#ifdef PUSH_PRESORTED
+	if (nlive > 0) mbar_wait(&s_bar, 0);
+#endif
 
 	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
 	//      owns the particles l and l+32 of the iteration's block); no block barriers from here on
@@ -1325,6 +1437,23 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
+#ifdef PUSH_PRESORTED
+	if (s->gperm_cap < s->cap_total) {
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(s->gperm);
+		ZDEV_CHECK(cudaMalloc(&s->gperm, (size_t) s->cap_total * 2 + 64));
+		s->gperm_cap = s->cap_total;
+	}
+	if (!s->tile_nlive) ZDEV_CHECK(cudaMalloc(&s->tile_nlive, (size_t) s->ntiles * sizeof(int)));
+	{
+		static size_t sort_configured = 0;
+		const size_t need = 2 * ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15));
+		if (need > sort_configured) {
+			ZDEV_CHECK(cudaFuncSetAttribute(k_sort2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) need));
+			sort_configured = need;
+		}
+	}
+#endif
 	for (int grp = 0; grp < 2; grp++) {
 		const int ntl = grp ? s->ntiles - s->n_small : s->n_small;
 		if (ntl <= 0) continue;
@@ -1332,12 +1461,22 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		const int* list = s->tile_list + (grp ? s->n_small : 0);
 		const size_t sm = push_smem_bytes(TX, TY, cap);
 		const unsigned front = (unsigned) push_smem_front(TX, TY, cap), permb = (unsigned) ((((size_t) cap * 2 + 15) & ~(size_t) 15));
+#ifdef PUSH_PRESORTED
+		ZDEV_LAUNCH((k_sort2d<TX, TY>), ntl, PUSH_THREADS, 2 * (size_t) permb, s->p, s->tile_off, s->tile_np, s->gperm, s->tile_nlive, permb, list);
+		if (s->track_ids)
+			ZDEV_LAUNCH((k_push2d<TX, TY, true>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list, s->gperm, s->tile_nlive);
+		else
+			ZDEV_LAUNCH((k_push2d<TX, TY, false>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
+			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list, s->gperm, s->tile_nlive);
+#else
 		if (s->track_ids)
 			ZDEV_LAUNCH((k_push2d<TX, TY, true>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
 			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
 		else
 			ZDEV_LAUNCH((k_push2d<TX, TY, false>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
 			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
+#endif
 	}
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
