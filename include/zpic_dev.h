@@ -107,7 +107,8 @@ void zdev_emf_set_ext_grid( zdev_grid2d* g, const float* host_ext_e, const float
 void zdev_emf_advance( zdev_grid2d* g, zdev_grid2d* g_cur, float dt, float dx, float dy,
                        int moving_window, int shift_window );
 /* The three stencils of emf_advance run as ONE kernel by default (60 B instead of 132 B of traffic per cell,
- * bit-identical results); 0 selects the three separate kernels below ($ZPIC_FUSED_YEE=0 does the same). */
+ * bit-identical results); 0 selects the three separate kernels below, 2 an experimental form of the one-pass
+ * kernel that classifies its tiles as interior / rim once ($ZPIC_FUSED_YEE=0 / 2 do the same). */
 void zdev_yee_set_fused( int on );
 /* pieces, for kernel-level parity tests */
 void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c:500-522 */
