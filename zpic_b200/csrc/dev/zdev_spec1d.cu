@@ -87,6 +87,9 @@ struct zdev_spec1d {
 	int ids_valid;
 	std::vector<int64_t>* h_off;
 	std::vector<cudaEvent_t>* ev; int ev_next, ev_pending; double push_ms; int64_t push_launches;
+	// PUSH1_PRESORTED build variant: perm[] and the live counts come from k_sort1d (see there)
+	unsigned short* gperm; int64_t gperm_cap;
+	int* tile_nlive;
 };
 
 static const int P1_THREADS = 256;
@@ -148,6 +151,7 @@ extern "C" void zdev_spec1d_destroy(zdev_spec1d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl);
+	cudaFree(s->gperm); cudaFree(s->tile_nlive);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -584,6 +588,87 @@ __device__ __forceinline__ void flush_cell1(const float acc[5], int cell, int la
 
 struct pair1_rec { f2 x, ux, uy, uz; int ca, cb, ta, tb; };
 
+#ifdef PUSH1_PRESORTED
+// ---- PUSH1_PRESORTED build variant (unmeasured; the em1d twin of PUSH_PRESORTED in zdev_spec2d.cu): phase A of
+// k_push1d as a kernel of its own - its 16 KB of counters and its barriers leave the push kernel, more CTAs of
+// the light sort kernel share an SM - handing perm[] (16-bit slot indices in key order) and the live count of
+// every tile to the push kernel through global memory.
+__global__ void __launch_bounds__(P1_THREADS)
+k_sort1d(buf1d A, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
+         unsigned short* __restrict__ gperm, int* __restrict__ tile_nlive, int TX, unsigned smem_keys) {
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
+	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_keys);
+	__shared__ int s_cnt[512 * SUB1], s_cur[512 * SUB1];
+	__shared__ int s_wsum[P1_WARPS];
+	__shared__ __align__(8) unsigned long long s_bar;
+	const int NK = TX * SUB1;
+	const int t = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int n = tile_np[t];
+	const int64_t base = tile_off[t];
+	if (threadIdx.x == 0) {
+		mbar_init(&s_bar, 1);
+		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
+	}
+	for (int k = threadIdx.x; k < NK; k += P1_THREADS) s_cnt[k] = 0;
+	__syncthreads();
+	if (n > 0) mbar_wait(&s_bar, 0);
+	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	const int ws = (S + P1_WARPS - 1) / P1_WARPS;
+	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
+	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
+			if (c0 != KEY1_EMPTY) atomicAdd(&s_cnt[c0], 1);
+			if (c1 != KEY1_EMPTY) atomicAdd(&s_cnt[c1], 1);
+		}
+	}
+	__syncthreads();
+	int nlive;
+	{
+		constexpr int PER = 2 * SUB1;
+		const int i0 = PER * threadIdx.x;
+		int c[PER], v = 0;
+		#pragma unroll
+		for (int k = 0; k < PER; k++) { c[k] = (i0 + k < NK) ? s_cnt[i0 + k] : 0; v += c[k]; }
+		int incl = v;
+		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
+		if (lane == 31) s_wsum[warp] = incl;
+		__syncthreads();
+		int woff = 0, tot = 0;
+		#pragma unroll
+		for (int w = 0; w < P1_WARPS; w++) { int cw = s_wsum[w]; woff += (w < warp) ? cw : 0; tot += cw; }
+		int run = woff + incl - v;
+		#pragma unroll
+		for (int k = 0; k < PER; k++) { if (i0 + k < NK) s_cur[i0 + k] = run; run += c[k]; }
+		nlive = tot;
+		__syncthreads();
+	}
+	#pragma unroll 4
+	for (int j = 0; j < wn; j++) {
+		const int i = 2 * (w0 + j);
+		if (i < n) {
+			const unsigned two = s_key2[j];
+			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
+			if (c0 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
+			if (c1 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
+		}
+	}
+	__syncthreads();
+	{
+		const unsigned* src = reinterpret_cast<const unsigned*>(s_perm);
+		unsigned* dst = reinterpret_cast<unsigned*>(gperm + base);
+		for (int k = threadIdx.x; k < (nlive + 1) / 2; k += P1_THREADS) dst[k] = src[k];
+	}
+	if (threadIdx.x == 0) tile_nlive[t] = nlive;
+}
+#endif
+
 // dynamic shared memory of k_push1d: [keys during the sort | field pairs + queues afterwards][perm][raw planes]
 static size_t push1_smem_front(int TX, int max_cap) {
 	size_t late = (size_t) 6 * (TX + 2) * 8 + (size_t) P1_WARPS * XQ1_CAP * sizeof(xq1_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
@@ -599,7 +684,11 @@ __global__ void __launch_bounds__(P1_THREADS, 2)
 k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np, int* __restrict__ tile_np_out,
          mig1d mig, ctl1d* __restrict__ ctl,
          const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J, int nx, int TX,
-         zdev_push1d_params prm, unsigned smem_front, unsigned smem_perm) {
+         zdev_push1d_params prm, unsigned smem_front, unsigned smem_perm
+#ifdef PUSH1_PRESORTED
+         , const unsigned short* __restrict__ gperm, const int* __restrict__ tile_nlive
+#endif
+         ) {
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	const int PL = TX + 2;
 	f2* const s_f2 = reinterpret_cast<f2*>(s_dyn);                     // 6 planes of (F[k], F[k+1])
@@ -607,9 +696,11 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
 	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
 	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
+#ifndef PUSH1_PRESORTED
 	__shared__ int s_cnt[512 * SUB1], s_cur[512 * SUB1];
 	const int NK = TX * SUB1;                            // sort keys of the tile
 	__shared__ int s_wsum[P1_WARPS];
+#endif
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
@@ -618,6 +709,22 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
 
+#ifdef PUSH1_PRESORTED
+	// ---- perm[] was built by k_sort1d: one bulk copy into its place, in flight while the fields are staged
+	const int nlive = tile_nlive[t];
+	if (threadIdx.x == 0) {
+		s_nmig = 0; s_done = 0;
+		mbar_init(&s_bar, 1);
+		if (nlive > 0) bulk_load(s_perm, gperm + base, (unsigned) ((nlive * 2 + 15) & ~15), &s_bar);
+	}
+	for (int k = threadIdx.x; k < cx + 2; k += P1_THREADS) {        // cells x0-1 .. x0+cx
+		f3 e = E[x0 + k], b = B[x0 + k];
+		s_raw[k] = e.x; s_raw[k + PL] = e.y; s_raw[k + 2 * PL] = e.z;
+		s_raw[k + 3 * PL] = b.x; s_raw[k + 4 * PL] = b.y; s_raw[k + 5 * PL] = b.z;
+	}
+	__syncthreads();
+	(void) s_key; (void) n; (void) warp;
+#else
 	if (threadIdx.x == 0) {
 		s_nmig = 0; s_done = 0;
 		mbar_init(&s_bar, 1);
@@ -684,6 +791,7 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		}
 	}
 	__syncthreads();                                    // the keys are dead: their bytes become field pairs + queues
+#endif
 	// ---- the fields as (F[k], F[k+1]) pairs: one LDS.64 per component and particle
 	for (int k = threadIdx.x; k < 6 * PL; k += P1_THREADS) {
 		const int pl = k / PL, o = k - pl * PL;
@@ -691,6 +799,9 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_f2[k] = mk2(s_raw[k], s_raw[o1]);
 	}
 	__syncthreads();
+#ifdef PUSH1_PRESORTED
+	if (nlive > 0) mbar_wait(&s_bar, 0);
+#endif
 
 	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
 	//      owns the particles l and l+32 of the block); no block barriers from here on
@@ -999,12 +1110,36 @@ extern "C" void zdev_spec1d_advance(zdev_spec1d* s, zdev_grid1d* grid, zdev_grid
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
 	const unsigned front = (unsigned) push1_smem_front(s->TX, s->max_cap), permb = (unsigned) (((size_t) s->max_cap * 2 + 15) & ~(size_t) 15);
+#ifdef PUSH1_PRESORTED
+	if (s->gperm_cap < s->cap_total) {
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		cudaFree(s->gperm);
+		ZDEV_CHECK(cudaMalloc(&s->gperm, (size_t) s->cap_total * 2 + 64));
+		s->gperm_cap = s->cap_total;
+	}
+	if (!s->tile_nlive) ZDEV_CHECK(cudaMalloc(&s->tile_nlive, (size_t) s->ntiles * sizeof(int)));
+	{
+		static size_t sort_configured = 0;
+		if (2 * (size_t) permb > sort_configured) {
+			ZDEV_CHECK(cudaFuncSetAttribute(k_sort1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (2 * (size_t) permb)));
+			sort_configured = 2 * (size_t) permb;
+		}
+	}
+	ZDEV_LAUNCH(k_sort1d, s->ntiles, P1_THREADS, 2 * (size_t) permb, s->p, s->tile_off, s->tile_np, s->gperm, s->tile_nlive, s->TX, permb);
+	if (s->track_ids)
+		ZDEV_LAUNCH(k_push1d<true>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
+		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb, s->gperm, s->tile_nlive);
+	else
+		ZDEV_LAUNCH(k_push1d<false>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
+		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb, s->gperm, s->tile_nlive);
+#else
 	if (s->track_ids)
 		ZDEV_LAUNCH(k_push1d<true>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
 		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
 	else
 		ZDEV_LAUNCH(k_push1d<false>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
 		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
+#endif
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 	{ buf1d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
