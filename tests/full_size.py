@@ -115,6 +115,16 @@ def main(argv=None):
         lib = load(a.code)
         if lib.zdev_init(-1) != 0:
             raise SystemExit("full_size: no CUDA device - the CUDA path is the only path")
+        # a population that does not fit the free device memory is reported as such (exit code 77: the test skips)
+        # instead of ending in the allocator's fatal error
+        free_b, total_b = C.c_size_t(), C.c_size_t()
+        lib.zdev_mem_info(C.byref(free_b), C.byref(total_b))
+        cells = n * n if a.code == "em2d" else n
+        per_particle = (2 * 26 * 1.25 + 4.4) if a.code == "em2d" else (2 * 22 * 1.25 + 3.6)     # A/B records + keys, migrants, overflow list
+        need = 2.0 * cells * (a.ppc * a.ppc if a.code == "em2d" else a.ppc) * per_particle + 6 * 12.0 * cells
+        if need > 0.97 * free_b.value:
+            sys.stderr.write("full_size: %.1f GB needed, %.1f GB free\n" % (need / 1e9, free_b.value / 1e9))
+            return 77
         lib.zpic_b200_set_option(b"device_init", int(a.device_init))
         lib.zpic_b200_set_option(b"lazy", 0)
         lib.zpic_b200_set_option(b"coherent", 0)

@@ -50,6 +50,8 @@ def test_properties_hold_at_any_size(code, n, ppc, device_init):
     if device_init:
         cmd.append("--device-init")
     r = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    if r.returncode == 77:
+        pytest.skip("not enough free device memory for this size: " + r.stderr.strip()[-200:])
     assert r.returncode == 0, r.stderr[-2000:]
     m = json.loads(r.stdout.strip().splitlines()[-1])
     cells = n * n if code == "em2d" else 1 << n
