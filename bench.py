@@ -324,6 +324,77 @@ def run_ours(args):
     return out
 
 
+def run_em1d(args, lib=None):
+    """--workload em1d: BASELINE configs[4], the em1d two-stream deck scaled to 2^22 cells x 256 ppc x 2 beams
+    (2^31 particles, 118 GB), driven through the device seam like scripts/quick_push_probe1d.py; one JSON line with
+    the same keys.  A secondary line: the driver's default run is the em2d configuration above."""
+    from zpic_b200._lib import PushParams1D
+    if lib is None:
+        from zpic_b200 import load
+        lib = load("em1d")
+    if lib.zdev_init(-1) != 0:
+        raise SystemExit("bench.py: no CUDA device - the CUDA path is the only path")
+    K, W = args.steps, max(args.warmup, 3)
+    n, ppc = 1 << args.log2_cells, args.ppc1d
+    dx = np.float32(4 * np.pi / 120)                # em1d/input/twostream.c:15-20
+    dt = np.float32(0.1)
+    g = lib.zdev_grid1d_create(n)
+    specs = []
+    for k, sign in enumerate((1.0, -1.0)):
+        sp = lib.zdev_spec1d_create(n, ppc, 0)
+        ufl = (C.c_float * 3)(0.2 * sign, 0, 0)
+        uth = (C.c_float * 3)(0.001, 0.001, 0.001)
+        lib.zdev_spec1d_inject_uniform(sp, ppc, ufl, uth, 4321 + k)
+        q = np.float32(-1.0) / np.float32(ppc)
+        prm = PushParams1D(float(np.float32(0.5 * float(dt) / -1.0)), float(dt / dx), float(q * dx / dt), float(q), 0, 0)
+        specs.append((sp, prm))
+    lib.zdev_sync()
+    npart = 2 * n * ppc
+
+    def step():
+        lib.zdev_current1d_zero(g)
+        for sp, prm in specs:
+            lib.zdev_spec1d_advance(sp, g, g, C.byref(prm))
+        lib.zdev_current1d_update(g, 1, 0, 0)
+        lib.zdev_emf1d_advance(g, g, float(dt), float(dx), 0, 0)
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(0)
+    e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
+    lib.zdev_sync()
+    launches0 = lib.zdev_launch_count()
+    sampler.start()
+    lib.zdev_event_record(e0)
+    for _ in range(K):
+        step()
+    lib.zdev_event_record(e1)
+    ms = lib.zdev_event_elapsed_ms(e0, e1)
+    clocks = sampler.finish()
+    launches = lib.zdev_launch_count() - launches0
+    en, cnt = C.c_double(), C.c_int64()
+    lib.zdev_spec1d_fetch(specs[0][0], C.byref(en), C.byref(cnt))
+    assert cnt.value == n * ppc, "particles were lost: %d" % cnt.value
+    peak, peak_src = peaks()
+    value = npart * K / (ms * 1e-3)
+    gbs = 40.0 * value / 1e9
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "em1d two-stream 2^%d cells x %d ppc x 2 beams, periodic (BASELINE configs[4])" % (args.log2_cells, ppc),
+                      "particles_per_gpu": npart, "dt": float(dt), "dx": float(dx),
+                      "init": "device-side counter-based thermal+fluid distribution",
+                      "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (npart * 44 / 1e9)},
+           "roofline": {"bound": "hbm", "kernel": "k_push1d", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": 40.0,
+                        "note": "from the whole step (the grid kernels are below 1 % of it), not from per-launch events"},
+           "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "cpu_baseline": None}
+    for sp, _ in specs:
+        lib.zdev_spec1d_destroy(sp)
+    lib.zdev_grid1d_destroy(g)
+    print(json.dumps(out))
+    return out
+
+
 def run_e2e(lib, A, args, n_full):
     """The metric through the public C API as a caller uses it (reference em2d/main.c:53-59 and the
     Weibel deck's sim_report, input/weibel.c:44-57): the species are created on the HOST by spec_new
@@ -483,9 +554,15 @@ def main():
     ap.add_argument("--ppc", type=int, default=8, help="particles per cell per direction (8 -> 64 ppc)")
     ap.add_argument("--e2e-grid", type=int, default=1024, dest="e2e_n")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
+    ap.add_argument("--workload", default="em2d", choices=["em2d", "em1d"],
+                    help="em2d = BASELINE configs[1] (the default, what the driver runs); em1d = configs[4], one GPU")
+    ap.add_argument("--log2-cells", type=int, default=22, dest="log2_cells", help="em1d: log2 of the cell count")
+    ap.add_argument("--ppc1d", type=int, default=256, help="em1d: particles per cell per beam")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "em1d":
+        run_em1d(args)
     else:
         run_ours(args)
 
