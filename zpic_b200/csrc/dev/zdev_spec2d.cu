@@ -2,20 +2,19 @@
 //
 // Data layout in HBM.  The grid is cut into tiles of TX x TY cells; every tile owns a
 // fixed-capacity segment [tile_off[t], tile_off[t+1]) of slots (a multiple of 32) in
-//     rec[]  chunks of 32 slots, each chunk six 128-byte rows  x[32] y[32] ux[32] uy[32] uz[32]
-//            cell[32]  (cell = lx | ly<<16, tile local): a warp reading 32 neighbouring slots
-//            touches one line per field, and two neighbouring slots of one field form an
-//            aligned 8-byte pair - the operand format of the packed fp32 pipe (FMUL2/FADD2/FFMA2);
-//     key[]  16-bit cell number lx + ly*TX (0xffff = empty slot), the only thing the
-//            index sort has to read;
+//     rec[]  chunks of 32 slots, each chunk five 128-byte rows  x[32] y[32] ux[32] uy[32] uz[32]:
+//            a warp reading 32 neighbouring slots touches one line per field;
+//     key[]  16-bit tile-local cell number lx + ly*TX (0xffff = empty slot): the only thing the
+//            index sort has to read, and the only place the cell is stored (TX is a power of two:
+//            lx = key & (TX-1), ly = key / TX) - 22 bytes per particle in all;
 //     tag[]  optional injection index (parity runs),
 // of which the first tile_np[t] slots are in use.  There are two such buffers, A and B,
 // and every step streams A -> B.
 //
 // One CTA advances one tile (k_push2d), every thread two particles at a time:
 //   phase A  an index-only counting sort of the tile's particles by cell, done in shared
-//            memory with native integer atomics: perm[] lists the live slots in cell
-//            order (empty slots drop out here, so compaction is free);
+//            memory with native integer atomics: perm[] lists (cell << 16 | slot) of the live
+//            slots in cell order (empty slots drop out here, so compaction is free);
 //   phase B  each warp walks a contiguous range of perm[], 64 particles per iteration, lane l
 //            owning the sorted neighbours 2l and 2l+1.  The two particles travel through the
 //            Boris push as the two halves of packed fp32 registers: one FMUL2/FADD2/FFMA2 per
@@ -31,7 +30,7 @@
 //            cell indices) and leave an empty slot behind.
 // k_migrate2d then applies the boundary conditions to the migrants and appends them to their
 // destination tiles in B (or to the slab export lists).
-// Per step a particle is read once and written once (2 x 26 B; 56 B with the reference's
+// Per step a particle is read once and written once (2 x 22 B; 56 B with the reference's
 // 28-byte record), plus the few percent that migrate.
 //
 // Replaces reference em2d/particles.c:1104-1269 (spec_advance incl. boundaries and
@@ -45,6 +44,7 @@
 #include <algorithm>
 #include <cstring>
 #include <chrono>
+#include <type_traits>
 
 // accessors implemented in zdev_grid2d.cu
 f3* zdev_grid2d_Epart(zdev_grid2d* g);
@@ -57,14 +57,14 @@ int zdev_grid2d_ny(zdev_grid2d* g);
 struct part_aos { int ix, iy; float x, y, ux, uy, uz; };
 
 // one particle as a value (registers); in memory its six words live in a 32-slot chunk, see above
-struct rec24 { float x, y, ux, uy, uz; int cell; };
+struct rec20 { float x, y, ux, uy, uz; };
 #define KEY_EMPTY 0xffffu
-#define REC_CHUNK_WORDS 192          // 6 rows x 32 slots
+#define REC_CHUNK_WORDS 160          // 5 rows x 32 slots
 
 // buffer view handed to kernels by value
 struct soa2d {
-	float* rec;          // chunked records, cell = lx | ly<<16
-	unsigned short* key;
+	float* rec;          // chunked records
+	unsigned short* key; // lx + ly*TX, KEY_EMPTY for a hole
 	int *tag;            // null unless ids are tracked
 };
 // migrants: one fixed segment per tile, [tile_off[t]/div, tile_off[t+1]/div), of reference-format records
@@ -80,14 +80,14 @@ struct mig2d {
 __device__ __forceinline__ size_t rec_word(int64_t slot) {
 	return (size_t) (slot >> 5) * REC_CHUNK_WORDS + (size_t) (slot & 31);
 }
-__device__ __forceinline__ rec24 rec_load(const float* __restrict__ rec, int64_t slot) {
+__device__ __forceinline__ rec20 rec_load(const float* __restrict__ rec, int64_t slot) {
 	const float* q = rec + rec_word(slot);
-	rec24 r; r.x = q[0]; r.y = q[32]; r.ux = q[64]; r.uy = q[96]; r.uz = q[128]; r.cell = __float_as_int(q[160]);
+	rec20 r; r.x = q[0]; r.y = q[32]; r.ux = q[64]; r.uy = q[96]; r.uz = q[128];
 	return r;
 }
-__device__ __forceinline__ void rec_store(float* __restrict__ rec, int64_t slot, float x, float y, float ux, float uy, float uz, int cell) {
+__device__ __forceinline__ void rec_store(float* __restrict__ rec, int64_t slot, float x, float y, float ux, float uy, float uz) {
 	float* q = rec + rec_word(slot);
-	q[0] = x; q[32] = y; q[64] = ux; q[96] = uy; q[128] = uz; q[160] = __int_as_float(cell);
+	q[0] = x; q[32] = y; q[64] = ux; q[96] = uy; q[128] = uz;
 }
 
 // control block in device memory, zeroed at the start of every advance
@@ -132,10 +132,6 @@ struct zdev_spec2d {
 	std::vector<cudaEvent_t>* ev;    // 2*EV_RING events, created on first use
 	int ev_next, ev_pending;
 	double push_ms; int64_t push_launches, push_particles;
-	// PUSH_PRESORTED build variant: the per-step index sort runs as its own kernel and hands the push kernel
-	// perm[] (16-bit slot indices in cell order, per tile segment) and the live count of every tile
-	unsigned short* gperm; int64_t gperm_cap;
-	int* tile_nlive;
 };
 static const int EV_RING = 64;
 
@@ -170,7 +166,7 @@ static const int PUSH_WARPS = PUSH_THREADS / 32;
 static void soa_alloc(soa2d& a, int64_t n, int with_tag) {
 	size_t nn = (size_t) (n > 0 ? n : 32);           // n is a multiple of 32 (whole chunks)
 	memset(&a, 0, sizeof(a));
-	ZDEV_CHECK(cudaMalloc(&a.rec, nn * 24));
+	ZDEV_CHECK(cudaMalloc(&a.rec, nn * 20));
 	ZDEV_CHECK(cudaMalloc(&a.key, nn * 2));
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&a.tag, nn * 4));
 }
@@ -266,7 +262,6 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl); cudaFree(s->tile_list);
-	cudaFree(s->gperm); cudaFree(s->tile_nlive);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -368,7 +363,7 @@ __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int 
 	int64_t d = off[t] + slot;
 	if (d >= off[t + 1]) { atomicSub(&tile_np[t], 1); ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, tag); return; }
 	const int lx = r.ix - tx * TX, ly = r.iy - ty * TY;
-	rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
+	rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz);
 	p.key[d] = (unsigned short) (lx + ly * TX);
 	if (p.tag) p.tag[d] = tag;
 }
@@ -511,15 +506,16 @@ __global__ void k_gather_aos(soa2d p, const int64_t* __restrict__ off, const int
 	__syncthreads();
 	for (int k0 = 0; k0 < n; k0 += blockDim.x) {
 		int k = k0 + threadIdx.x;
-		bool live = (k < n) && p.key[b + k] != KEY_EMPTY;
+		const unsigned key = (k < n) ? p.key[b + k] : KEY_EMPTY;
+		bool live = key != KEY_EMPTY;
 		unsigned m = __ballot_sync(0xffffffffu, live);
 		int wbase = 0;
 		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
 		wbase = __shfl_sync(0xffffffffu, wbase, 0);
 		if (live) {
-			rec24 v = rec_load(p.rec, b + k);
+			rec20 v = rec_load(p.rec, b + k);
 			part_aos r;
-			r.ix = x0 + (v.cell & 0xffff); r.iy = y0 + (v.cell >> 16);
+			r.ix = x0 + (int) (key % TX); r.iy = y0 + (int) (key / TX);
 			r.x = v.x; r.y = v.y; r.ux = v.ux; r.uy = v.uy; r.uz = v.uz;
 			int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
 			out[d] = r;
@@ -585,8 +581,8 @@ __global__ void k_relayout(soa2d src, const int64_t* __restrict__ off_src, soa2d
 		const unsigned short key = src.key[a + k];
 		dst.key[b + k] = key;
 		if (key != KEY_EMPTY) {
-			const rec24 v = rec_load(src.rec, a + k);
-			rec_store(dst.rec, b + k, v.x, v.y, v.ux, v.uy, v.uz, v.cell);
+			const rec20 v = rec_load(src.rec, a + k);
+			rec_store(dst.rec, b + k, v.x, v.y, v.ux, v.uy, v.uz);
 			if (src.tag) dst.tag[b + k] = src.tag[a + k];
 		}
 	}
@@ -734,7 +730,7 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		int kx = k % ppcx, ky = k / ppcx;
 		int64_t d = base + k;
 		rec_store(p.rec, d, (float) (dpcx * (kx + 0.5)), (float) (dpcy * (ky + 0.5)),
-		          uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz), lx | (ly << 16));
+		          uth.x * a + (ufl.x - sx), uth.y * b + (ufl.y - sy), uth.z * c + (ufl.z - sz));
 		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = (int) (gid0 + k);
 	}
@@ -816,8 +812,9 @@ __device__ __forceinline__ void deposit_seg(const jtile& t, int W3, const seg2d&
 }
 
 // one queued move (warp-private shared-memory queue): what is left of a move after its first cell face;
-// ix, iy tile local, dij: the face it still has to cross, if any
-struct __align__(16) xq_entry { int ix, iy, dij; float x0, y0, dx, dy, qvz; };
+// cij = (ix+1) | (iy+1) << 8 | dij << 16 with ix, iy tile local (-1 .. TX) and dij = the face it still has to
+// cross, if any: (di+1) | (dj+1) << 2
+struct __align__(8) xq_entry { int cij; float x0, y0, dx, dy, qvz; };
 
 // split + deposit up to 32 queued moves, one per lane
 __device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, const jtile& t, int W3,
@@ -825,7 +822,8 @@ __device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, 
 	if (lane < n) {
 		xq_entry e = q[lane];
 		seg2d vp[2];
-		int vnp = split_once(e.ix, e.iy, (e.dij & 3) - 1, ((e.dij >> 2) & 3) - 1, e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
+		int vnp = split_once((e.cij & 0xff) - 1, ((e.cij >> 8) & 0xff) - 1, ((e.cij >> 16) & 3) - 1, ((e.cij >> 18) & 3) - 1,
+		                     e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
 		deposit_seg(t, W3, vp[0], qnx, qny);
 		if (vnp > 1) deposit_seg(t, W3, vp[1], qnx, qny);
 	}
@@ -864,118 +862,37 @@ __device__ __forceinline__ void flush_cell(const float acc[8], int cell, int lan
 }
 
 // the six words of the sorted neighbours (pa, pa+1), as loaded from their source slots
-struct pair_rec { f2 x, y, ux, uy, uz; int ca, cb, ta, tb; };
+struct pair_rec { f2 x, y, ux, uy, uz; int ca, cb, ta, tb; };      // ca, cb: cell numbers (keys)
 
 #ifndef XQ_CAP_N
 #define XQ_CAP_N 96                  // 31 left over + 64 new entries at most
 #endif
 static const int XQ_CAP = XQ_CAP_N;
 
-#ifdef PUSH_PRESORTED
-// ---- PUSH_PRESORTED build variant (unmeasured; A/B against the default with ZPIC_LIB_SUFFIX): the per-step
-// index sort of k_push2d's phase A as a kernel of its own.  It needs 33 KB of shared memory and 40 registers,
-// so 6 CTAs share an SM and hide each other's barriers and dependent shared-memory atomics - in the fused
-// kernel the two resident CTAs sit in that phase together, 20 % of the warp time for 10 % of the instructions.
-// Price: perm[] goes through global memory (2 B written + 2 B read per particle; the tile's 16 KB stay in L2).
-// Same algorithm as phase A below (lane-strided counting sort, see there), same result: perm[] = live slots of
-// the tile in cell order, nlive = their number.
-template <int TX, int TY>
-__global__ void __launch_bounds__(PUSH_THREADS)
-k_sort2d(soa2d A, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
-         unsigned short* __restrict__ gperm, int* __restrict__ tile_nlive, unsigned smem_keys, const int* __restrict__ tile_list) {
-	constexpr int NC = TX * TY;
-	extern __shared__ __align__(16) unsigned char s_dyn[];
-	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
-	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_keys);
-	__shared__ int s_cnt[NC], s_cur[NC];
-	__shared__ int s_wsum[PUSH_WARPS];
-	__shared__ __align__(8) unsigned long long s_bar;
-	const int t = tile_list[blockIdx.x];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int n = tile_np[t];
-	const int64_t base = tile_off[t];
-	if (threadIdx.x == 0) {
-		mbar_init(&s_bar, 1);
-		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
-	}
-	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
-	__syncthreads();
-	if (n > 0) mbar_wait(&s_bar, 0);
-	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
-	const int ws = (S + PUSH_WARPS - 1) / PUSH_WARPS;
-	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
-	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
-	#pragma unroll 4
-	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) atomicAdd(&s_cnt[c0], 1);
-			if (c1 != KEY_EMPTY) atomicAdd(&s_cnt[c1], 1);
-		}
-	}
-	__syncthreads();
-	int nlive;
-	{
-		int v = (threadIdx.x < NC) ? s_cnt[threadIdx.x] : 0;
-		int incl = v;
-		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
-		if (lane == 31) s_wsum[warp] = incl;
-		__syncthreads();
-		int woff = 0, tot = 0;
-		#pragma unroll
-		for (int w = 0; w < PUSH_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
-		if (threadIdx.x < NC) s_cur[threadIdx.x] = woff + incl - v;
-		nlive = tot;
-		__syncthreads();
-	}
-	#pragma unroll 4
-	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
-			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
-		}
-	}
-	__syncthreads();
-	// perm[] leaves as 32-bit words (the tile segment starts on a 64-byte boundary; the odd last entry is padding)
-	{
-		const unsigned* src = reinterpret_cast<const unsigned*>(s_perm);
-		unsigned* dst = reinterpret_cast<unsigned*>(gperm + base);
-		for (int k = threadIdx.x; k < (nlive + 1) / 2; k += PUSH_THREADS) dst[k] = src[k];
-	}
-	if (threadIdx.x == 0) tile_nlive[t] = nlive;
-}
-#endif
-
-// dynamic shared memory of k_push2d: [keys during the sort | corner tile + queues afterwards][perm][raw planes]
-static size_t push_smem_front(int TX, int TY, int max_cap) {
-	size_t plane = (size_t) (TX + 2) * (TY + 2);
-	size_t late = 6 * plane * 16 + (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
-	return late > keys ? late : keys;
-}
-static size_t push_smem_bytes(int TX, int TY, int max_cap) {
-	size_t plane = (size_t) (TX + 2) * (TY + 2);
-	size_t perm = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
-	return push_smem_front(TX, TY, max_cap) + perm + 6 * plane * 4;
+// dynamic shared memory of k_push2d: [front][perm], front = the tile's keys during the sort, afterwards the
+// corner tile + the warps' queues in the same bytes; the raw field planes (staged before the sort, dead once the
+// corner tile is built, i.e. before the first queue entry is written) sit in the tail of the queue area, behind
+// the keys; perm[] = 32-bit (cell << 16 | slot) entries.
+struct push_smem { size_t front, raw, total; };
+static push_smem push_smem_layout(int TX, int TY, int max_cap) {
+	const size_t plane = (size_t) (TX + 2) * (TY + 2);
+	const size_t corner = 6 * plane * 16, queues = (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry);
+	const size_t keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	push_smem L;
+	L.raw = keys > corner ? keys : corner;
+	L.front = corner + queues > L.raw + 6 * plane * 4 ? corner + queues : L.raw + 6 * plane * 4;
+	L.front = (L.front + 15) & ~(size_t) 15;
+	L.total = L.front + (size_t) max_cap * 4;
+	return L;
 }
 
-// One CTA per tile.  Dynamic shared memory: the tile's keys during the sort, afterwards the corner tile
-// (float4 x 6 planes) and the warps' queues in the same bytes; perm[max_cap] (16-bit slot indices); the raw
-// field planes.
+// One CTA per tile.
 template <int TX, int TY, bool TAGS>
 __global__ void __launch_bounds__(PUSH_THREADS, PUSH_MIN_BLOCKS)
 k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
          int* __restrict__ tile_np_out, mig2d mig,
          ctl2d* __restrict__ ctl, const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J,
-         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_perm, const int* __restrict__ tile_list
-#ifdef PUSH_PRESORTED
-         , const unsigned short* __restrict__ gperm, const int* __restrict__ tile_nlive
-#endif
-         ) {
+         push_geom g, zdev_push2d_params prm, unsigned smem_front, unsigned smem_raw, const int* __restrict__ tile_list) {
 	constexpr int SROW = TX + 2;
 	constexpr int PLANE = SROW * (TY + 2);
 	constexpr int NC = TX * TY;
@@ -984,8 +901,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	float4* const s_f4 = reinterpret_cast<float4*>(s_dyn);
 	xq_entry* const s_xq = reinterpret_cast<xq_entry*>(s_dyn + 6 * PLANE * 16);
 	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
-	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
-	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
+	unsigned* const s_perm = reinterpret_cast<unsigned*>(s_dyn + smem_front);
+	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_raw);
 	const int JW3 = 3 * g.nrow;
 	__shared__ int s_cnt[NC], s_cur[NC];
 	__shared__ int s_nmig, s_done;
@@ -999,25 +916,6 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
 
-#ifdef PUSH_PRESORTED
-	// ---- perm[] was built by k_sort2d: one bulk copy into its place, in flight while the fields are staged
-	const int nlive = tile_nlive[t];
-	if (threadIdx.x == 0) {
-		s_nmig = 0; s_done = 0;
-		mbar_init(&s_bar, 1);
-		if (nlive > 0) bulk_load(s_perm, gperm + base, (unsigned) ((nlive * 2 + 15) & ~15), &s_bar);
-	}
-	for (int k = threadIdx.x; k < (cx + 2) * (cy + 2); k += PUSH_THREADS) {
-		int r = k / (cx + 2), c = k - r * (cx + 2);
-		int gi = (x0 + c) + (y0 + r) * g.nrow;        // buffer index of cell (x0-1+c, y0-1+r)
-		f3 e = E[gi], b = B[gi];
-		int o = c + r * SROW;
-		s_raw[o] = e.x; s_raw[o + PLANE] = e.y; s_raw[o + 2 * PLANE] = e.z;
-		s_raw[o + 3 * PLANE] = b.x; s_raw[o + 4 * PLANE] = b.y; s_raw[o + 5 * PLANE] = b.z;
-	}
-	__syncthreads();
-	(void) s_key; (void) s_cnt; (void) s_cur; (void) n;
-#else
 	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
 	if (threadIdx.x == 0) {
 		s_nmig = 0; s_done = 0;
@@ -1082,12 +980,11 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (i < n) {
 			const unsigned two = s_key2[j];
 			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
-			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
+			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (c0 << 16) | (unsigned) i;
+			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (c1 << 16) | (unsigned) (i + 1);
 		}
 	}
 	__syncthreads();                                    // the keys are dead: their bytes become corner tile + queues
-#endif
 	// ---- the fields as the four corners of every cell (entries of the last row / column are never read)
 	for (int k = threadIdx.x; k < 6 * PLANE; k += PUSH_THREADS) {
 		const int pl = k / PLANE, o = k - pl * PLANE;
@@ -1098,9 +995,6 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_f4[k] = make_float4(P[o], P[o2], P[o1], P[o3]);
 	}
 	__syncthreads();
-#ifdef PUSH_PRESORTED
-	if (nlive > 0) mbar_wait(&s_bar, 0);
-#endif
 
 	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
 	//      owns the particles l and l+32 of the iteration's block); no block barriers from here on
@@ -1172,12 +1066,13 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 
 	// source slots of the particles (pa, pa+32); lanes past the end of the range read the range's first particle
 	auto load_pair = [&](int pa, pair_rec& r) {
-		const int ia = s_perm[pa < pend ? pa : pbeg], ib = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const unsigned va = s_perm[pa < pend ? pa : pbeg], vb = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const int ia = va & 0xffffu, ib = vb & 0xffffu;
 		const float* qa = Arec + (ia >> 5) * REC_CHUNK_WORDS + (ia & 31);
 		const float* qb = Arec + (ib >> 5) * REC_CHUNK_WORDS + (ib & 31);
 		r.x = mk2(qa[0], qb[0]); r.y = mk2(qa[32], qb[32]);
 		r.ux = mk2(qa[64], qb[64]); r.uy = mk2(qa[96], qb[96]); r.uz = mk2(qa[128], qb[128]);
-		r.ca = __float_as_int(qa[160]); r.cb = __float_as_int(qb[160]);
+		r.ca = (int) (va >> 16); r.cb = (int) (vb >> 16);
 		r.ta = r.tb = 0;
 		if (TAGS) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
 	};
@@ -1188,14 +1083,18 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	pair_rec nv;
 	if (PUSH_PREFETCH && pbeg < pend) load_pair(pbeg + lane, nv);
 
-	for (int p0 = pbeg; p0 < pend; p0 += 64) {
+	// one iteration = 64 particles; FULL: all 64 exist (every iteration but the last of a warp's range), so the
+	// activity masks are compile-time true and the predicates, selects and store guards they feed disappear
+	auto advance64 = [&](const int p0, auto full_tag) {
+		constexpr bool FULL = decltype(full_tag)::value;
 		const int pa = p0 + lane, pb = pa + 32;
-		const bool actA = pa < pend, actB = pb < pend;
+		const bool actA = FULL || pa < pend, actB = FULL || pb < pend;
 		if (!PUSH_PREFETCH) load_pair(pa, nv);
 		const pair_rec v = nv;
 		if (PUSH_PREFETCH && p0 + 64 < pend) load_pair(pa + 64, nv);
 
-		const int lxa = v.ca & 0xffff, lya = v.ca >> 16, lxb = v.cb & 0xffff, lyb = v.cb >> 16;
+		constexpr int LOG_TX = (TX == 16) ? 4 : ((TX == 8) ? 3 : 2);
+		const int lxa = v.ca & (TX - 1), lya = v.ca >> LOG_TX, lxb = v.cb & (TX - 1), lyb = v.cb >> LOG_TX;
 		f2 x = v.x, y = v.y, ux = v.ux, uy = v.uy, uz = v.uz;
 		f2 dx, dy, qvz;
 		{
@@ -1241,10 +1140,10 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			#pragma unroll
 			for (int q = 0; q < 8; q++) w[q] = w2[q].x;
 #ifndef ABL_NO_DEPOSIT
-			deposit32(actA ? lxa + lya * TX : 0x7fffffff, w, actA, lxa, lya);
+			deposit32(actA ? v.ca : 0x7fffffff, w, actA, lxa, lya);
 			#pragma unroll
 			for (int q = 0; q < 8; q++) w[q] = w2[q].y;
-			deposit32(actB ? lxb + lyb * TX : 0x7fffffff, w, actB, lxb, lyb);
+			deposit32(actB ? v.cb : 0x7fffffff, w, actB, lxb, lyb);
 #else
 			acc[0] += w[0] + w[1] + w[2] + w[3] + w[4] + w[5] + w[6] + w[7];
 			#pragma unroll
@@ -1264,8 +1163,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				// what is left of the two moves, in the frame of the cell behind the face
 				if (xa) {
 					xq_entry e;
-					e.ix = lxa + (xfa ? dia : 0); e.iy = lya + (yfa ? dja : 0);
-					e.dij = ((xfa ? 0 : dia) + 1) | (((yfa ? 0 : dja) + 1) << 2);
+					e.cij = (lxa + (xfa ? dia : 0) + 1) | ((lya + (yfa ? dja : 0) + 1) << 8) |
+					        (((xfa ? 0 : dia) + 1) << 16) | (((yfa ? 0 : dja) + 1) << 18);
 					{ const float r1 = 1.0f - t1.x;
 					e.x0 = xfa ? 1.0f - fx.x : xe.x; e.y0 = yfa ? 1.0f - fy.x : ye.x;
 					e.dx = dx.x * r1; e.dy = dy.x * r1; e.qvz = qvz.x * r1; }
@@ -1274,8 +1173,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				nxq += __popc(ma);
 				if (xb) {
 					xq_entry e;
-					e.ix = lxb + (xfb ? dib : 0); e.iy = lyb + (yfb ? djb : 0);
-					e.dij = ((xfb ? 0 : dib) + 1) | (((yfb ? 0 : djb) + 1) << 2);
+					e.cij = (lxb + (xfb ? dib : 0) + 1) | ((lyb + (yfb ? djb : 0) + 1) << 8) |
+					        (((xfb ? 0 : dib) + 1) << 16) | (((yfb ? 0 : djb) + 1) << 18);
 					{ const float r1 = 1.0f - t1.y;
 					e.x0 = xfb ? 1.0f - fx.y : xe.y; e.y0 = yfb ? 1.0f - fy.y : ye.y;
 					e.dx = dx.y * r1; e.dy = dy.y * r1; e.qvz = qvz.y * r1; }
@@ -1301,14 +1200,12 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (actA) {
 			float* qd = Brec + (pa >> 5) * REC_CHUNK_WORDS + (pa & 31);
 			qd[0] = xn.x; qd[32] = yn.x; qd[64] = ux.x; qd[96] = uy.x; qd[128] = uz.x;
-			qd[160] = __int_as_float(nlxa | (nlya << 16));
 			Bo.key[base + pa] = sta ? (unsigned short) (nlxa + nlya * TX) : (unsigned short) KEY_EMPTY;
 			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
 		if (actB) {
 			float* qd = Brec + (pb >> 5) * REC_CHUNK_WORDS + (pb & 31);
 			qd[0] = xn.y; qd[32] = yn.y; qd[64] = ux.y; qd[96] = uy.y; qd[128] = uz.y;
-			qd[160] = __int_as_float(nlxb | (nlyb << 16));
 			Bo.key[base + pb] = stb ? (unsigned short) (nlxb + nlyb * TX) : (unsigned short) KEY_EMPTY;
 			if (TAGS) Bo.tag[base + pb] = v.tb;
 		}
@@ -1339,6 +1236,11 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				}
 			}
 		}
+	};
+	{
+		int p0 = pbeg;
+		for (; p0 + 64 <= pend; p0 += 64) advance64(p0, std::true_type());
+		if (p0 < pend) advance64(p0, std::false_type());
 	}
 	if (cur >= 0) flush_cell<TX>(acc, cur, lane, jt, JW3);
 	if (nxq) drain_queue(xq, nxq, lane, jt, JW3, prm.qnx, prm.qny);
@@ -1399,7 +1301,7 @@ __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* 
 				continue;
 			}
 			const int lx = ix - tx * TX, ly = iy - ty * TY;
-			rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz, lx | (ly << 16));
+			rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz);
 			p.key[d] = (unsigned short) (lx + ly * TX);
 			if (p.tag) p.tag[d] = mig.tag[mb + k];
 		}
@@ -1420,7 +1322,7 @@ __global__ void k_count_total(soa2d p, const int64_t* __restrict__ off, const in
 
 template <int TX, int TY>
 static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const push_geom& g, const zdev_push2d_params& prm) {
-	size_t smem = push_smem_bytes(TX, TY, s->max_cap);
+	size_t smem = push_smem_layout(TX, TY, s->max_cap).total;
 	static size_t configured = 0;
 	if (smem > configured) {
 		ZDEV_CHECK(cudaFuncSetAttribute(k_push2d<TX, TY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1437,46 +1339,20 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
-#ifdef PUSH_PRESORTED
-	if (s->gperm_cap < s->cap_total) {
-		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(s->gperm);
-		ZDEV_CHECK(cudaMalloc(&s->gperm, (size_t) s->cap_total * 2 + 64));
-		s->gperm_cap = s->cap_total;
-	}
-	if (!s->tile_nlive) ZDEV_CHECK(cudaMalloc(&s->tile_nlive, (size_t) s->ntiles * sizeof(int)));
-	{
-		static size_t sort_configured = 0;
-		const size_t need = 2 * ((((size_t) s->max_cap * 2 + 15) & ~(size_t) 15));
-		if (need > sort_configured) {
-			ZDEV_CHECK(cudaFuncSetAttribute(k_sort2d<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) need));
-			sort_configured = need;
-		}
-	}
-#endif
 	for (int grp = 0; grp < 2; grp++) {
 		const int ntl = grp ? s->ntiles - s->n_small : s->n_small;
 		if (ntl <= 0) continue;
 		const int cap = grp ? s->max_cap : s->cap_small;
 		const int* list = s->tile_list + (grp ? s->n_small : 0);
-		const size_t sm = push_smem_bytes(TX, TY, cap);
-		const unsigned front = (unsigned) push_smem_front(TX, TY, cap), permb = (unsigned) ((((size_t) cap * 2 + 15) & ~(size_t) 15));
-#ifdef PUSH_PRESORTED
-		ZDEV_LAUNCH((k_sort2d<TX, TY>), ntl, PUSH_THREADS, 2 * (size_t) permb, s->p, s->tile_off, s->tile_np, s->gperm, s->tile_nlive, permb, list);
-		if (s->track_ids)
-			ZDEV_LAUNCH((k_push2d<TX, TY, true>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list, s->gperm, s->tile_nlive);
-		else
-			ZDEV_LAUNCH((k_push2d<TX, TY, false>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
-			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list, s->gperm, s->tile_nlive);
-#else
+		const push_smem L = push_smem_layout(TX, TY, cap);
+		const size_t sm = L.total;
+		const unsigned front = (unsigned) L.front, permb = (unsigned) L.raw;
 		if (s->track_ids)
 			ZDEV_LAUNCH((k_push2d<TX, TY, true>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
 			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
 		else
 			ZDEV_LAUNCH((k_push2d<TX, TY, false>), ntl, PUSH_THREADS, sm, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q,
 			            s->mig, s->ctl, E, B, J, g, prm, front, permb, list);
-#endif
 	}
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 }
@@ -1561,8 +1437,7 @@ __global__ void k_deposit_charge(soa2d p, const int64_t* __restrict__ off, const
 		if (key != KEY_EMPTY) {
 			const float* r = p.rec + rec_word(b + k);
 			const float w1 = r[0], w2 = r[32];
-			const int cell = __float_as_int(r[160]);
-			idx = (x0 + (cell & 0xffff)) + nrow * (y0 + (cell >> 16));
+			idx = (x0 + (int) (key % TX)) + nrow * (y0 + (int) (key / TX));
 			w[0] = (1.0f - w1) * (1.0f - w2) * q; w[1] = (w1) * (1.0f - w2) * q;
 			w[2] = (1.0f - w1) * (w2) * q;        w[3] = (w1) * (w2) * q;
 		}
@@ -1650,9 +1525,10 @@ __global__ void k_deposit_pha(soa2d p, const int64_t* __restrict__ off, const in
 		const int x0 = (t % ntx) * TX, y0 = (t / ntx) * TY;
 		const int64_t b = off[t];
 		for (int k = threadIdx.x; k < n; k += blockDim.x) {
-			if (p.key[b + k] == KEY_EMPTY) continue;
-			const rec24 v = rec_load(p.rec, b + k);
-			const int ix = x0 + (v.cell & 0xffff), iy = y0 + (v.cell >> 16);
+			const unsigned key = p.key[b + k];
+			if (key == KEY_EMPTY) continue;
+			const rec20 v = rec_load(p.rec, b + k);
+			const int ix = x0 + (int) (key % TX), iy = y0 + (int) (key / TX);
 			const float nx1 = (pha_axis(a.q1, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min1) * a.rd1;
 			const float nx2 = (pha_axis(a.q2, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min2) * a.rd2;
 			const int i1 = (int) (nx1 + 0.5f), i2 = (int) (nx2 + 0.5f);
