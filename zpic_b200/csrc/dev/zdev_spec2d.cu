@@ -297,7 +297,9 @@ static void spec_build_tile_lists(zdev_spec2d* s) {
 // buffers.  Capacity per tile = slack * max(population, nominal fill), rounded to 32.
 static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np) {
 	double slack = s->slack;
-	if (slack <= 0.0) slack = (np > (int64_t) 200000000) ? 1.25 : 2.0;
+	// perm[] costs 4 bytes of shared memory per slot of capacity: tiles whose nominal fill is large keep 25 % of
+	// room (two push CTAs + 92 KB of L1 per SM), small ones 100 %; full tiles grow on demand either way
+	if (slack <= 0.0) slack = ((int64_t) s->TX * s->TY * s->ppc_hint > 4500 || np > (int64_t) 200000000) ? 1.25 : 2.0;
 	std::vector<int64_t>& off = *s->h_off;
 	off.assign(s->ntiles + 1, 0);
 	int64_t max_cap = 0;
@@ -811,19 +813,31 @@ __device__ __forceinline__ void deposit_seg(const jtile& t, int W3, const seg2d&
 	jt_weights(t, (s.ix + 1) * 3 + (s.iy + 1) * W3, W3, w);
 }
 
-// one queued move (warp-private shared-memory queue): what is left of a move after its first cell face;
-// cij = (ix+1) | (iy+1) << 8 | dij << 16 with ix, iy tile local (-1 .. TX) and dij = the face it still has to
-// cross, if any: (di+1) | (dj+1) << 2
-struct __align__(8) xq_entry { int cij; float x0, y0, dx, dy, qvz; };
+// one queued move (warp-private shared-memory queue): a move that leaves its cell, as the push computed it.
+// cij = cell key | (di+1) << 16 | (dj+1) << 18.  The lanes have deposited its first in-cell piece; the drain
+// recomputes where that piece ended (the same operations on the same operands, so the pieces join exactly) and
+// deposits the rest.  Queueing the raw move instead of the remainder keeps the enqueue - which runs for every
+// 64 particles although only ~6 of them cross - down to a few instructions; the arithmetic runs in the drain,
+// 32 entries at a time.
+struct __align__(8) xq_entry { int cij; float x, y, dx, dy, qvz; };
 
 // split + deposit up to 32 queued moves, one per lane
+template <int TX>
 __device__ __forceinline__ void drain_queue(const xq_entry* q, int n, int lane, const jtile& t, int W3,
                                             float qnx, float qny) {
 	if (lane < n) {
-		xq_entry e = q[lane];
+		const xq_entry e = q[lane];
+		const int key = e.cij & 0xffff, di = ((e.cij >> 16) & 3) - 1, dj = ((e.cij >> 18) & 3) - 1;
+		// end of the first piece: the scalar twins of the packed operations of the push (same roundings)
+		const float fx = di > 0 ? 1.0f : 0.0f, fy = dj > 0 ? 1.0f : 0.0f;
+		float tx = (fx - e.x) * rcp_approx1(e.dx), ty = (fy - e.y) * rcp_approx1(e.dy);
+		tx = di ? tx : 2.0f; ty = dj ? ty : 2.0f;
+		const float t1 = fmaxf(fminf(fminf(tx, ty), 1.0f), 0.0f);
+		const bool xf = di != 0 && tx <= ty, yf = dj != 0 && !xf;
+		const float xe = e.x + e.dx * t1, ye = e.y + e.dy * t1, r1 = 1.0f - t1;
 		seg2d vp[2];
-		int vnp = split_once((e.cij & 0xff) - 1, ((e.cij >> 8) & 0xff) - 1, ((e.cij >> 16) & 3) - 1, ((e.cij >> 18) & 3) - 1,
-		                     e.x0, e.y0, e.dx, e.dy, e.qvz, vp);
+		int vnp = split_once((key & (TX - 1)) + (xf ? di : 0), key / TX + (yf ? dj : 0), xf ? 0 : di, yf ? 0 : dj,
+		                     xf ? 1.0f - fx : xe, yf ? 1.0f - fy : ye, e.dx * r1, e.dy * r1, e.qvz * r1, vp);
 		deposit_seg(t, W3, vp[0], qnx, qny);
 		if (vnp > 1) deposit_seg(t, W3, vp[1], qnx, qny);
 	}
@@ -1160,30 +1174,23 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			const unsigned ma = __ballot_sync(0xffffffffu, xa), mb = __ballot_sync(0xffffffffu, xb);
 #endif
 			if (ma | mb) {
-				// what is left of the two moves, in the frame of the cell behind the face
 				if (xa) {
 					xq_entry e;
-					e.cij = (lxa + (xfa ? dia : 0) + 1) | ((lya + (yfa ? dja : 0) + 1) << 8) |
-					        (((xfa ? 0 : dia) + 1) << 16) | (((yfa ? 0 : dja) + 1) << 18);
-					{ const float r1 = 1.0f - t1.x;
-					e.x0 = xfa ? 1.0f - fx.x : xe.x; e.y0 = yfa ? 1.0f - fy.x : ye.x;
-					e.dx = dx.x * r1; e.dy = dy.x * r1; e.qvz = qvz.x * r1; }
+					e.cij = v.ca + ((dia + 1) << 16) + ((dja + 1) << 18);
+					e.x = x.x; e.y = y.x; e.dx = dx.x; e.dy = dy.x; e.qvz = qvz.x;
 					xq[nxq + __popc(ma & lt)] = e;
 				}
 				nxq += __popc(ma);
 				if (xb) {
 					xq_entry e;
-					e.cij = (lxb + (xfb ? dib : 0) + 1) | ((lyb + (yfb ? djb : 0) + 1) << 8) |
-					        (((xfb ? 0 : dib) + 1) << 16) | (((yfb ? 0 : djb) + 1) << 18);
-					{ const float r1 = 1.0f - t1.y;
-					e.x0 = xfb ? 1.0f - fx.y : xe.y; e.y0 = yfb ? 1.0f - fy.y : ye.y;
-					e.dx = dx.y * r1; e.dy = dy.y * r1; e.qvz = qvz.y * r1; }
+					e.cij = v.cb + ((dib + 1) << 16) + ((djb + 1) << 18);
+					e.x = x.y; e.y = y.y; e.dx = dx.y; e.dy = dy.y; e.qvz = qvz.y;
 					xq[nxq + __popc(mb & lt)] = e;
 				}
 				nxq += __popc(mb);
 				__syncwarp();
 				while (nxq >= 32) {
-					drain_queue(xq + nxq - 32, 32, lane, jt, JW3, prm.qnx, prm.qny);
+					drain_queue<TX>(xq + nxq - 32, 32, lane, jt, JW3, prm.qnx, prm.qny);
 					nxq -= 32;
 				}
 				__syncwarp();
@@ -1243,7 +1250,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		if (p0 < pend) advance64(p0, std::false_type());
 	}
 	if (cur >= 0) flush_cell<TX>(acc, cur, lane, jt, JW3);
-	if (nxq) drain_queue(xq, nxq, lane, jt, JW3, prm.qnx, prm.qny);
+	if (nxq) drain_queue<TX>(xq, nxq, lane, jt, JW3, prm.qnx, prm.qny);
 
 	// ---- tile epilogue (no block barrier: warps retire independently): energy, slots in use, migrants
 	double e = (double) energy;
