@@ -891,12 +891,13 @@ struct push_smem { size_t front, raw, total; };
 static push_smem push_smem_layout(int TX, int TY, int max_cap) {
 	const size_t plane = (size_t) (TX + 2) * (TY + 2);
 	const size_t corner = 6 * plane * 16, queues = (size_t) PUSH_WARPS * XQ_CAP * sizeof(xq_entry);
-	const size_t keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	// + 128 keys: the sort walks 64 * S >= n keys and the ones past n are padded with KEY_EMPTY in place
+	const size_t keys = ((size_t) (max_cap + 128) * 2 + 15) & ~(size_t) 15;
 	push_smem L;
 	L.raw = keys > corner ? keys : corner;
 	L.front = corner + queues > L.raw + 6 * plane * 4 ? corner + queues : L.raw + 6 * plane * 4;
 	L.front = (L.front + 15) & ~(size_t) 15;
-	L.total = L.front + (size_t) max_cap * 4;
+	L.total = L.front + (size_t) (max_cap + 128) * 4;     // the holes are sorted too (behind the live entries)
 	return L;
 }
 
@@ -918,7 +919,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	unsigned* const s_perm = reinterpret_cast<unsigned*>(s_dyn + smem_front);
 	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_raw);
 	const int JW3 = 3 * g.nrow;
-	__shared__ int s_cnt[NC], s_cur[NC];
+	__shared__ int s_cnt[NC + 1], s_cur[NC + 1];          // bin NC: the holes
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
@@ -945,7 +946,7 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_raw[o] = e.x; s_raw[o + PLANE] = e.y; s_raw[o + 2 * PLANE] = e.z;
 		s_raw[o + 3 * PLANE] = b.x; s_raw[o + 4 * PLANE] = b.y; s_raw[o + 5 * PLANE] = b.z;
 	}
-	for (int k = threadIdx.x; k < NC; k += PUSH_THREADS) s_cnt[k] = 0;
+	for (int k = threadIdx.x; k <= NC; k += PUSH_THREADS) s_cnt[k] = 0;
 	__syncthreads();
 	if (n > 0) mbar_wait(&s_bar, 0);
 
@@ -958,23 +959,26 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	// Lane l owns the words [l*S, (l+1)*S) of the key array (S odd: the lanes of a warp read distinct banks
 	// and sit S*2 keys apart, i.e. in different cells as long as a cell holds fewer particles than that);
 	// the warps split every lane's stretch into WARPS consecutive pieces.
+	// Branch-free: the keys past n (up to the 64 * S the lanes cover) are padded with KEY_EMPTY, and a hole counts
+	// as cell NC - it gets a counter and a stretch of perm[] behind the live entries like any other cell.
 	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	{
+		unsigned short* const kw = const_cast<unsigned short*>(s_key);
+		for (int k = n + threadIdx.x; k < 64 * S; k += PUSH_THREADS) kw[k] = (unsigned short) KEY_EMPTY;
+		__syncthreads();
+	}
 	const int ws = (S + PUSH_WARPS - 1) / PUSH_WARPS;
 	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
 	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
 	#pragma unroll 4
 	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) atomicAdd(&s_cnt[c0], 1);
-			if (c1 != KEY_EMPTY) atomicAdd(&s_cnt[c1], 1);
-		}
+		const unsigned two = s_key2[j];
+		atomicAdd(&s_cnt[min(two & 0xffffu, (unsigned) NC)], 1);
+		atomicAdd(&s_cnt[min(two >> 16, (unsigned) NC)], 1);
 	}
 	__syncthreads();
 	int nlive;
-	{	// exclusive scan of s_cnt (NC <= 256 == PUSH_THREADS)
+	{	// exclusive scan of s_cnt (NC <= 256 == PUSH_THREADS); the holes start at nlive
 		__shared__ int s_wsum[PUSH_WARPS];
 		int v = (threadIdx.x < NC) ? s_cnt[threadIdx.x] : 0;
 		int incl = v;
@@ -985,18 +989,17 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		#pragma unroll
 		for (int w = 0; w < PUSH_WARPS; w++) { int c = s_wsum[w]; woff += (w < warp) ? c : 0; tot += c; }
 		if (threadIdx.x < NC) s_cur[threadIdx.x] = woff + incl - v;
+		if (threadIdx.x == 0) s_cur[NC] = tot;
 		nlive = tot;
 		__syncthreads();
 	}
 	#pragma unroll 4
 	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY_EMPTY;
-			if (c0 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (c0 << 16) | (unsigned) i;
-			if (c1 != KEY_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (c1 << 16) | (unsigned) (i + 1);
-		}
+		const unsigned two = s_key2[j];
+		const unsigned c0 = min(two & 0xffffu, (unsigned) NC), c1 = min(two >> 16, (unsigned) NC);
+		const unsigned i = 2u * (unsigned) (w0 + j);
+		s_perm[atomicAdd(&s_cur[c0], 1)] = (c0 << 16) | i;
+		s_perm[atomicAdd(&s_cur[c1], 1)] = (c1 << 16) | (i + 1u);
 	}
 	__syncthreads();                                    // the keys are dead: their bytes become corner tile + queues
 	// ---- the fields as the four corners of every cell (entries of the last row / column are never read)
