@@ -1249,6 +1249,8 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	};
 	{
 		int p0 = pbeg;
+		// (unrolling this loop by two to drop the pipeline's register moves doubles the 21 KB body past the 32 KB
+		//  instruction cache: measured -24 %)
 		for (; p0 + 64 <= pend; p0 += 64) advance64(p0, std::true_type());
 		if (p0 < pend) advance64(p0, std::false_type());
 	}
