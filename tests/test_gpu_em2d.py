@@ -16,7 +16,11 @@ from zpic_b200 import abi_em2d as A
 pytestmark = pytest.mark.gpu
 
 TOL_FIELD = 1e-5      # relative L2 on E, B, J (north_star)
-TOL_ENERGY = 1e-6     # relative, energy diagnostics
+TOL_ENERGY = 1e-6     # relative: per-species kinetic energy, and the total (field + kinetic) energy diagnostic
+# The field energy ALONE is a sum of squares of fields that agree to ~3e-6 (rel-L2) after 100 steps of a growing
+# instability, so it cannot agree better than ~2x that; the reference's own -Ofast and strict builds differ by
+# 9.8e-7 there (1.2e-8 on the total energy, which the kinetic part dominates).  Stated bar for it:
+TOL_FIELD_ENERGY = 5e-6
 
 
 @pytest.fixture(autouse=True)
@@ -239,9 +243,29 @@ def test_weibel_100_steps_within_tolerance(ours, ref):
                 err = H.rel_l2(sa["parts"][k][q], sb["parts"][k][q])
                 assert err < TOL_FIELD, (cp, k, q, err)
             assert abs(sa["energy"][k] - sb["energy"][k]) <= TOL_ENERGY * abs(sb["energy"][k])
-        tot_a, tot_b = ea.sum(), eb.sum()
-        if tot_b > 0:
-            assert abs(tot_a - tot_b) <= 1e-5 * tot_b, (cp, tot_a, tot_b)
+        fld_a, fld_b = ea.sum(), eb.sum()
+        if fld_b > 0:
+            assert abs(fld_a - fld_b) <= TOL_FIELD_ENERGY * fld_b, (cp, fld_a, fld_b)
+        # the total-energy diagnostic (sim_report_energy: field + kinetic), north_star bar 1e-6
+        tot_a, tot_b = fld_a + sum(sa["energy"]), fld_b + sum(sb["energy"])
+        assert abs(tot_a - tot_b) <= TOL_ENERGY * abs(tot_b), (cp, tot_a, tot_b)
+
+
+def test_field_energy_kernel_on_identical_grids(ours, ref):
+    """k_energy against emf_get_energy (em2d/emf.c:729-750) on the SAME random E, B: both widen the float
+    products to double and differ only in the order of the double additions -> 1e-12"""
+    rng = np.random.default_rng(11)
+    a, b = H.Deck(ours, (70, 45), (7.0, 9.0), 0.05), H.Deck(ref, (70, 45), (7.0, 9.0), 0.05)
+    e, bb, _ = _fill_random(a, rng, amp=3.0)
+    for d in (a, b):
+        d.E()[...] = e
+        d.B()[...] = bb
+    a.touch()
+    ea, eb = a.emf_energy(), b.emf_energy()
+    assert np.all(eb > 0)
+    assert np.abs(ea - eb).max() <= 1e-12 * eb.max(), (ea, eb)
+    a.delete()
+    b.delete()
 
 
 def test_charge_deposit(ours, ref):
@@ -327,6 +351,9 @@ def test_lwfa_moving_window(ours, ref):
         a.iter(cp - done)
         b.iter(cp - done)
         done = cp
+        # the particle count the step itself reports (no sync in between): a window-shift step appends the
+        # injected column before the count is taken
+        assert a.species[0].np == b.species[0].np, (cp, a.species[0].np, b.species[0].np)
         sa, sb = a.snapshot(), b.snapshot()
         assert a.sim.emf.n_move == b.sim.emf.n_move
         assert a.species[0].n_move == b.species[0].n_move
@@ -337,6 +364,90 @@ def test_lwfa_moving_window(ours, ref):
         pa, pb = H.canon(sa["parts"][0]), H.canon(sb["parts"][0])
         assert np.array_equal(pa["ix"], pb["ix"]) and np.array_equal(pa["iy"], pb["iy"]), cp
     assert b.sim.emf.n_move > 0 and sb["np"][0] > 0
+    a.delete()
+    b.delete()
+
+
+def _match_in_cells(pa, pb):
+    """pair the particles of two runs cell by cell (canonical order inside a cell); returns the two arrays in
+    matched order.  Two particles of a cell whose positions agree to rounding can pair the wrong way round:
+    the callers bound the number of such outliers instead of trusting every pair."""
+    return H.canon(pa), H.canon(pb)
+
+
+def test_lwfa_shipped_deck_400_steps(ours, ref):
+    """em2d/input/lwfa.c AS SHIPPED (1500 x 128 cells, 4x2 ppc, a0 = 2 laser, moving window, compensated
+    smoothing level 4; reference input/lwfa.c:15-63) at steps 1, 100 and 400 (the box is empty at
+    step 1, the laser reaches the plasma after ~214 steps, so 400 is the first checkpoint with field-particle
+    coupling): counts and cells exact, E/B/J and momenta rel-L2 <= 1e-5"""
+    a, b = H.lwfa(ours, n_sort=0), H.lwfa(ref, n_sort=0)
+    for cp in (1, 100, 400):
+        a.iter(cp - a.sim.emf.iter)
+        b.iter(cp - b.sim.emf.iter)
+        assert a.species[0].np == b.species[0].np, cp
+        sa, sb = a.snapshot(), b.snapshot()
+        assert a.sim.emf.n_move == b.sim.emf.n_move and a.species[0].n_move == b.species[0].n_move
+        assert sa["np"][0] == sb["np"][0] == {1: 0, 100: 71680, 400: 286720}[cp]
+        for q in ("E", "B", "J"):
+            err = H.rel_l2(sa[q], sb[q])
+            assert err < TOL_FIELD, (cp, q, err)
+        if sa["np"][0] == 0:
+            continue
+        pa, pb = _match_in_cells(sa["parts"][0], sb["parts"][0])
+        same = (pa["ix"] == pb["ix"]) & (pa["iy"] == pb["iy"])
+        assert (~same).sum() <= 3, (cp, (~same).sum())
+        # momenta over the matched pairs; a pair of near-coincident particles may be matched crosswise
+        d2 = sum((pa[q].astype(np.float64) - pb[q]) ** 2 for q in ("ux", "uy", "uz"))
+        n2 = sum(pb[q].astype(np.float64) ** 2 for q in ("ux", "uy", "uz"))
+        bad = d2 > 1e-6 * max(n2.max(), 1e-30)
+        assert bad.sum() <= 1e-4 * len(pa), (cp, bad.sum())
+        err = np.sqrt(d2[~bad].sum() / max(n2[~bad].sum(), 1e-300)) if n2.sum() > 0 else np.sqrt(d2[~bad].sum())
+        assert err < TOL_FIELD, (cp, "u", err)
+        ea, eb = a.emf_energy(), b.emf_energy()
+        tot_a, tot_b = ea.sum() + sa["energy"][0], eb.sum() + sb["energy"][0]
+        assert abs(tot_a - tot_b) <= TOL_ENERGY * abs(tot_b), (cp, tot_a, tot_b)
+    a.delete()
+    b.delete()
+
+
+def test_external_custom_fields(ours, ref, tmp_path):
+    """CUSTOM external fields (em2d/input/extfld.c:25-80: the field of a current-carrying wire, evaluated by a
+    callback at the staggered positions of every cell): E_part / B_part as the push sees them and the
+    particles after 2 and 20 steps"""
+    import subprocess
+    so = str(tmp_path / "ext_callbacks.so")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                           os.path.join(H.REPO, "tests", "ext_callbacks.c"), "-lm"])
+    cbs = C.CDLL(so)
+    cb_b = C.cast(cbs.ext_wire_B, A.FIELD_FN)
+    cb_e = C.cast(cbs.ext_ripple_E, A.FIELD_FN)
+    sp = [dict(name="electrons", m_q=-1.0, ppc=(2, 2), uth=(0.01, 0.01, 0.01), n_sort=0)]
+    a = H.Deck(ours, (64, 64), (12.8, 12.8), 0.07, sp)
+    b = H.Deck(ref, (64, 64), (12.8, 12.8), 0.07, sp)
+    for d in (a, b):
+        ext = A.ExtField()
+        ext.B_type = A.EMF_FLD_TYPE_CUSTOM
+        ext.B_custom = cb_b
+        ext.E_type = A.EMF_FLD_TYPE_CUSTOM
+        ext.E_custom = cb_e
+        d.lib.sim_set_ext_fld(C.byref(d.sim), C.byref(ext))
+    for cp in (2, 20):
+        a.iter(cp - a.sim.emf.iter)
+        b.iter(cp - b.sim.emf.iter)
+        sa, sb = a.snapshot(), b.snapshot()
+        # the fields seen by the particles (E_part = E + external): the reference's own buffers, em2d/emf.c:838-914
+        for name in ("E_part", "B_part"):
+            ga = A.grid_view(getattr(a.sim.emf.ext_fld, name + "_buf"), 64, 64)
+            gb = A.grid_view(getattr(b.sim.emf.ext_fld, name + "_buf"), 64, 64)
+            assert H.rel_l2(ga[1:65, 1:65], gb[1:65, 1:65]) < TOL_FIELD, (cp, name)
+        assert sa["np"][0] == sb["np"][0]
+        pa, pb = sa["parts"][0], sb["parts"][0]
+        same = (pa["ix"] == pb["ix"]) & (pa["iy"] == pb["iy"])
+        assert (~same).sum() <= (0 if cp == 2 else 3)
+        for q in ("ux", "uy", "uz"):
+            assert H.rel_l2(pa[q], pb[q]) < TOL_FIELD, (cp, q)
+        for q in ("E", "B", "J"):
+            assert H.rel_l2(sa[q], sb[q]) < TOL_FIELD, (cp, q)
     a.delete()
     b.delete()
 

@@ -356,7 +356,6 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 	gc->j_host_stale = 1;
 	spec->iter += 1;
 
-	int n_injected = 0;
 	if (prm.shift_window) {
 		/* new plasma enters through the right edge: host injector (global random stream),
 		   then the column is appended to the device tiles */
@@ -366,14 +365,14 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		spec_inject_into(spec, range, &col, &ncol, &ncol_max);
 		zdev_spec2d_append(zb_spec_dev(s), col, ncol);
 		free(col);
-		n_injected = ncol;
 	}
 
 	if (!zb_opt_lazy()) {
 		double esum; int64_t np;
 		zdev_spec2d_fetch(zb_spec_dev(s), &esum, &np);
 		spec->energy = spec->q * spec->m_q * esum * spec->dx[0] * spec->dx[1];
-		spec->np = (int) (np + n_injected);
+		/* the count is taken after the append: the injected column is already in it */
+		spec->np = (np > 0x7fffffffLL) ? 0x7fffffff : (int) np;
 		s->np_seen = spec->np;
 		push_count += spec->np;
 	} else {
