@@ -157,55 +157,55 @@ def time_grid_term(lib, sim, n, reps=20):
                     "step; with the particles it is %s of a step)" % (n, n, "%.1f %%")}
 
 
-def run_slabs(args, lib, rank, world, local):
-    """N > 1: the box grows along x with N (weak scaling), one slab per GPU, halo / particle exchange
-    over NCCL (zpic_b200.parallel).  Returns (ms for K steps - max over ranks, particles per GPU,
-    push kernel ms, push launches, grid n)."""
-    import torch
-    import torch.distributed as dist
-    from zpic_b200 import parallel as P
-    stream = P.share_stream_with_torch(lib)      # one stream for kernels, torch buffers and NCCL
-    n, _ = fit_grid(lib, args.n, args.ppc * args.ppc)
-    geom = P.Geometry(n * world, n, world, rank, moving_window=False)
-    npc = args.ppc * args.ppc
-    cfg = [dict(m_q=-1.0, q=-1.0 / npc, ppc=(args.ppc, args.ppc)), dict(m_q=1.0, q=1.0 / npc, ppc=(args.ppc, args.ppc))]
-    slab = P.CudaSlab(lib, geom, DT, CELL, CELL, cfg)
-    for k, uz in enumerate((0.6, -0.6)):
-        slab.inject_uniform(k, (args.ppc, args.ppc), (0.0, 0.0, uz), (0.1, 0.1, 0.1), 1234 + 7919 * rank + k)
-    comm = P.TorchComm(geom)
-    lib.zdev_set_push_timing(1)
-    for _ in range(max(args.warmup, 1)):
-        P.slab_step(slab, comm)
-    lib.zdev_sync()
-    dist.barrier()
-    torch.cuda.synchronize()
-    for sp in slab.species:
-        lib.zdev_spec2d_push_timing(sp["handle"], None, None, 1)
-    launches0 = lib.zdev_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        P.slab_step(slab, comm)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    dist.barrier()
-    t = torch.tensor([ms], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    push_ms, push_n = 0.0, 0
-    for sp in slab.species:
-        tt, c = C.c_double(), C.c_int64()
-        lib.zdev_spec2d_push_timing(sp["handle"], C.byref(tt), C.byref(c), 1)
-        push_ms += tt.value
-        push_n += c.value
-    # population conserved over the whole ring
-    cnt = torch.tensor([sum(slab.fetch(k)[1] for k in range(2))], device="cuda", dtype=torch.int64)
-    dist.all_reduce(cnt)
-    assert int(cnt.item()) == 2 * n * n * npc * world, "particles were lost: %d" % int(cnt.item())
-    launches = lib.zdev_launch_count() - launches0
-    slab.destroy()
-    lib.zdev_set_stream(None)
-    return float(t.item()), 2 * n * n * npc, push_ms, push_n, n, launches
+def slab_parity(lib, A, rank, world):
+    """N > 1, after the timed region: a small Weibel box (64 cells per slab along x, 64 along y, 2 x 16 ppc, host
+    initialisation = the reference random stream) advanced 10 steps by the N slabs through the C API, gathered on
+    rank 0 and compared with the unmodified reference (oracle/_ref) running the whole box on the host: particle
+    counts equal, cells bit-identical after step 1, E/B/J within 1e-5 (relative L2)."""
+    lib.zpic_b200_set_option(b"device_init", 0)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    nx, ny, ppc = 64 * world, 64, (4, 4)
+    sim, species, _ = build_weibel(lib, A, nx, ny, ppc)
+    ref = None
+    if rank == 0:
+        path = os.path.join(REPO, "oracle", "_ref", "libzpic_ref_em2d.so")
+        if os.path.exists(path):
+            ref = A.declare(C.CDLL(path))
+            rsim, rspecies, _ = build_weibel(ref, A, nx, ny, ppc)
+    res = {"deck": "Weibel %dx%d, 2 x 16 ppc, %d slabs, 10 steps vs the reference on the host" % (nx, ny, world)}
+    ok = True
+    for cp in (1, 10):
+        for _ in range(cp - sim.emf.iter):
+            lib.sim_iter(C.byref(sim))
+        lib.zpic_b200_sync_host(C.byref(sim))                 # collective: gathers the slabs into every mirror
+        if ref is None:
+            continue
+        for _ in range(cp - rsim.emf.iter):
+            ref.sim_iter(C.byref(rsim))
+        for name, a, b in (("E", sim.emf.E_buf, rsim.emf.E_buf), ("B", sim.emf.B_buf, rsim.emf.B_buf),
+                           ("J", sim.current.J_buf, rsim.current.J_buf)):
+            x, y = A.grid_view(a, nx, ny).astype(np.float64), A.grid_view(b, nx, ny).astype(np.float64)
+            err = float(np.sqrt(((x - y) ** 2).sum() / max((y ** 2).sum(), 1e-300)))
+            res["%s_rel_l2_step%d" % (name, cp)] = err
+            ok = ok and err < 1e-5
+        for k in range(2):
+            pa, pb = A.part_view(species[k]), A.part_view(rspecies[k])
+            ok = ok and len(pa) == len(pb)
+            if cp == 1 and len(pa) == len(pb):
+                ca = np.sort(pa["ix"].astype(np.int64) * ny + pa["iy"])
+                cb = np.sort(pb["ix"].astype(np.int64) * ny + pb["iy"])
+                same = bool(np.array_equal(ca, cb))
+                res["cells_identical_step1_species%d" % k] = same
+                ok = ok and same
+    lib.sim_delete(C.byref(sim))
+    if ref is not None:
+        ref.sim_delete(C.byref(rsim))
+        res["ok"] = bool(ok)
+        sys.stderr.write("slab_parity: %s\n" % ("ok" if ok else "FAILED"))
+    else:
+        res["ok"] = None
+        res["note"] = "oracle/_ref not present on this box"
+    return res if rank == 0 else None
 
 
 def run_ours(args):
@@ -220,6 +220,7 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("ZPIC_JOB", "bench" + os.environ.get("MASTER_PORT", "0"))
     lib = load("em2d")
     if lib.zdev_init(local) != 0:
         raise SystemExit("bench.py: no CUDA device - the CUDA path is the only path")
@@ -228,56 +229,72 @@ def run_ours(args):
     os.environ.setdefault("ZPIC_TILE_SLACK", "1.25")
     sampler = ClockSampler(local)
 
-    if world > 1:
-        if rank == 0:
-            sampler.start()
-        ms, np_total, push_ms, push_n, n, launches = run_slabs(args, lib, rank, world, local)
-        clocks = sampler.finish() if rank == 0 else None
-        value = world * np_total * K / (ms * 1e-3)
-    else:
-        # ---- state resident in HBM (device-side initialisation), fully asynchronous stepping
-        n, free_b = fit_grid(lib, args.n, args.ppc * args.ppc)
-        lib.zpic_b200_set_option(b"device_init", 1)
-        lib.zpic_b200_set_option(b"lazy", 1)
-        lib.zpic_b200_set_option(b"coherent", 0)
-        lib.zdev_set_push_timing(1)
-        sim, species, _ = build_weibel(lib, A, n, n, ppc)
-        np_total = 2 * n * n * args.ppc * args.ppc
-        for _ in range(max(W, 1)):
-            lib.sim_iter(C.byref(sim))
-        lib.zdev_sync()
-        from zpic_b200._lib import spec_handle
-        handles = [spec_handle(lib, C.byref(species[k])) for k in range(2)]
-        for h in handles:
-            lib.zdev_spec2d_push_timing(h, None, None, 1)
-        launches0 = lib.zdev_launch_count()
+    # ---- state resident in HBM (device-side initialisation), fully asynchronous stepping.  N > 1: the SAME calls -
+    #      sim_new / sim_iter of the reference API on a box that grows along x with N (weak scaling); the library
+    #      reads RANK / WORLD_SIZE, keeps one slab per process / GPU and exchanges guard cells and particles GPU to
+    #      GPU inside spec_advance / current_update / emf_advance (csrc/dev/zdev_slab.cuh).  torch.distributed
+    #      (NCCL) only carries the barrier and the max-over-ranks of the timing.
+    n, free_b = fit_grid(lib, args.n, args.ppc * args.ppc)
+    lib.zpic_b200_set_option(b"device_init", 1)
+    lib.zpic_b200_set_option(b"lazy", 1)
+    lib.zpic_b200_set_option(b"coherent", 0)
+    lib.zdev_set_push_timing(1)
+    sim, species, _ = build_weibel(lib, A, n * world, n, ppc)
+    np_total = 2 * n * n * args.ppc * args.ppc            # per GPU
+    for _ in range(max(W, 1)):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    from zpic_b200._lib import spec_handle
+    handles = [spec_handle(lib, C.byref(species[k])) for k in range(2)]
+    for h in handles:
+        lib.zdev_spec2d_push_timing(h, None, None, 1)
+    launches0 = lib.zdev_launch_count()
+    if rank == 0:
         sampler.start()
-        e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
-        lib.zdev_sync()
-        lib.zdev_event_record(e0)
-        for _ in range(K):
-            lib.sim_iter(C.byref(sim))
-        lib.zdev_event_record(e1)
-        ms = lib.zdev_event_elapsed_ms(e0, e1)
-        lib.zdev_sync()
-        clocks = sampler.finish()
-        launches = lib.zdev_launch_count() - launches0
-        push_ms, push_n = 0.0, 0
-        for h in handles:
-            t, c = C.c_double(), C.c_int64()
-            lib.zdev_spec2d_push_timing(h, C.byref(t), C.byref(c), 1)
-            push_ms += t.value
-            push_n += c.value
-        lib.zdev_set_push_timing(0)
-        # sanity: the population did not leak (periodic box)
-        lib.zpic_b200_set_option(b"lazy", 0)
-        en, cnt = C.c_double(), C.c_int64()
-        lib.zdev_spec2d_fetch(handles[0], C.byref(en), C.byref(cnt))
-        assert cnt.value == n * n * args.ppc * args.ppc, "particles were lost: %d" % cnt.value
-        value = np_total * K / (ms * 1e-3)
+    e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
+    lib.zdev_sync()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    lib.zdev_event_record(e0)
+    for _ in range(K):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_event_record(e1)
+    ms = lib.zdev_event_elapsed_ms(e0, e1)
+    lib.zdev_sync()
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.finish() if rank == 0 else None
+    launches = lib.zdev_launch_count() - launches0
+    push_ms, push_n = 0.0, 0
+    for h in handles:
+        t, c = C.c_double(), C.c_int64()
+        lib.zdev_spec2d_push_timing(h, C.byref(t), C.byref(c), 1)
+        push_ms += t.value
+        push_n += c.value
+    lib.zdev_set_push_timing(0)
+    # sanity: the population did not leak (periodic box; over all slabs when decomposed)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    en, cnt = C.c_double(), C.c_int64()
+    lib.zdev_spec2d_fetch(handles[0], C.byref(en), C.byref(cnt))
+    total = cnt.value
+    if dist is not None:
+        tt = torch.tensor([total], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt)
+        total = int(tt.item())
+    assert total == world * n * n * args.ppc * args.ppc, "particles were lost: %d" % total
+    value = world * np_total * K / (ms * 1e-3)
+    cells = None
+    parity = None
+    if world == 1:
         cells = time_grid_term(lib, sim, n)
         cells["what"] = cells["what"] % (100.0 * cells["ms_per_step"] / (ms / K))
-        lib.sim_delete(C.byref(sim))
+    lib.sim_delete(C.byref(sim))
+    if world > 1 and not args.no_check:
+        parity = slab_parity(lib, A, rank, world)
 
     out = None
     if rank == 0:
@@ -300,10 +317,16 @@ def run_ours(args):
                        "particles_per_gpu": np_total, "dt": DT, "dx": CELL,
                        "init": "device-side counter-based thermal+fluid distribution",
                        "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (np_total * 52 / 1e9),
-                       "decomposition": ("%d slabs along x, one process per GPU; NCCL send/recv of J guard columns (add), "
-                                         "E/B halos and migrating particles every step" % world) if world > 1 else "single GPU"},
+                       "decomposition": ("%d slabs along x, one process per GPU, through sim_new / sim_iter of the C API; J guard "
+                                         "columns (add), E/B halos and migrating particles are written by the sending kernels "
+                                         "straight into the neighbour GPU's memory over NVLink (CUDA IPC mailboxes + flags, no "
+                                         "host synchronisation); NCCL carries only the bench's barrier / timing reduction" % world)
+                       if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "kernel": "k_push2d", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_source": "ncu constant (profiles/push_traffic.json: DRAM bytes per particle of the committed "
+                                           "--set full capture of this kernel version) x particles per launch; not measured in this run",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": BYTES_PER_PUSH, "particles_per_launch": per_launch,
                          "avg_launch_ms": avg_ms, "launches_timed": push_n,
                          "kernel_share_of_step": push_ms / ms},
@@ -314,9 +337,11 @@ def run_ours(args):
             out["e2e"] = run_e2e(lib, A, args, n)
             out["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds, threads=1)
         else:
-            out["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 2 * 32 * world, "d2h_bytes_per_step": 2 * 16 * world,
-                          "mode": "multi-GPU runs drive the device seam directly (zpic_b200.parallel); per step only push "
-                                  "scalars go in and the slab export counts come out; the host-buffer legs are measured at N=1"}
+            out["slab_parity"] = parity
+            out["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 2 * 32 * world, "d2h_bytes_per_step": 2 * 48 * world,
+                          "mode": "the timed loop IS the public C API (sim_iter on every rank); per step only kernel parameters "
+                                  "go in and the 48-byte control block of every species comes out (read one step late); the "
+                                  "host-buffer legs (host-initialised species, per-step diagnostics, report set) are measured at N=1"}
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -556,6 +581,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
     ap.add_argument("--workload", default="em2d", choices=["em2d", "em1d"],
                     help="em2d = BASELINE configs[1] (the default, what the driver runs); em1d = configs[4], one GPU")
+    ap.add_argument("--no-check", action="store_true", dest="no_check", help="N > 1: skip the slab-parity check")
     ap.add_argument("--log2-cells", type=int, default=22, dest="log2_cells", help="em1d: log2 of the cell count")
     ap.add_argument("--ppc1d", type=int, default=256, help="em1d: particles per cell per beam")
     args = ap.parse_args()

@@ -76,6 +76,17 @@ void zdev_grid2d_destroy( zdev_grid2d* g );
 /* host mirror -> device / device -> host mirror, whole buffer incl. guards */
 void zdev_grid2d_upload( zdev_grid2d* g, int which, const float* host_buf );
 void zdev_grid2d_download( zdev_grid2d* g, int which, float* host_buf );
+/* the same for a grid that is one slab of a wider box: the slab's window (guards included) of a host buffer
+ * whose rows are host_nrow cells long; local buffer column c = host buffer column x0 + c */
+void zdev_grid2d_upload_window( zdev_grid2d* g, int which, const float* host_buf, int host_nrow, int x0 );
+void zdev_grid2d_download_window( zdev_grid2d* g, int which, float* host_buf, int host_nrow, int x0 );
+/* Slab decomposition along x, one process per GPU (csrc/dev/zdev_slab.cuh): this grid is the slab
+ * between the ranks `left` and `right` (-1: none - the open end of a moving-window chain).  Collective over the
+ * ranks of the job (zb_par.h).  From then on zdev_current_update and zdev_emf_advance exchange the guard columns
+ * with the neighbour slabs - kernels that store straight into the neighbour's memory over NVLink and flag the
+ * message, no host synchronisation, no library collective.  wrap_*: that edge is the periodic box boundary
+ * (the reference leaves guard columns un-filtered by kernel_y there, em2d/current.c:382-411). */
+void zdev_grid2d_set_slab( zdev_grid2d* g, int left, int right, int wrap_left, int wrap_right );
 /* raw device pointer of a grid buffer (cell [-1,-1]); for tests / multi-GPU glue */
 float* zdev_grid2d_ptr( zdev_grid2d* g, int which );
 
@@ -205,6 +216,14 @@ void zdev_spec2d_deposit_pha( zdev_spec2d* s, int quant1, int quant2, const int 
 void  zdev_spec2d_export_counts( zdev_spec2d* s, int64_t counts[2] );
 void* zdev_spec2d_export_ptr( zdev_spec2d* s, int side );
 void  zdev_spec2d_append_device( zdev_spec2d* s, const void* dev_part_aos, int64_t np );
+/* The linked form of the same (one process per GPU on one node, csrc/dev/zdev_slab.cuh): collective over the ranks
+ * of the job.  From then on zdev_spec2d_advance writes the particles that leave through a slab edge straight into
+ * the neighbour's mailbox over NVLink and appends what the neighbours sent, all on the device; slab_left / slab_right
+ * of the push parameters are taken from the link.  gx0, gnx: the slab's first column in the whole box and the box
+ * width (the device-side injector and the phasespace axis work in box coordinates). */
+void  zdev_spec2d_set_slab( zdev_spec2d* s, int left, int right, int gx0, int gnx );
+/* the slab's own charge deposit: rho = (nx+1)*(ny+1) floats, overwritten, not folded */
+void  zdev_spec2d_deposit_charge_raw( zdev_spec2d* s, float q, float* rho );
 /* Device timing of the push kernel alone (k_push2d, not the migration pass): when enabled
  * every launch is bracketed by CUDA events on the library stream; the accumulated time and
  * launch count are read back (and optionally reset) per species.  Used by bench.py for

@@ -8,6 +8,8 @@
 // 384-byte span per float3 array.  Compiled with --fmad=false: every expression
 // below keeps the reference's operation order so results are bit-identical.
 #include "zdev_common.cuh"
+#include "zdev_slab.cuh"
+#include <algorithm>
 
 struct zdev_grid2d {
 	int nx, ny, nrow, nrows;
@@ -20,6 +22,10 @@ struct zdev_grid2d {
 	int e_ext, b_ext;        // 0 none, 1 uniform, 2 grid
 	f3 e0, b0;
 	double* d_sums;          // 6 doubles
+	// slab decomposition along x (zdev_slab.cuh): this grid is one slab of a wider box
+	int slab;                // 1: guard columns towards a neighbour slab are exchanged, not wrapped
+	int wrap_left, wrap_right;   // that edge of the slab is the (periodic) box boundary
+	zdev_link link;
 };
 
 // cell (i,j), i in [-1,nx+1], j in [-1,ny+1] -> linear index from buffer start
@@ -58,6 +64,7 @@ extern "C" void zdev_grid2d_destroy(zdev_grid2d* g) {
 	if (g->b_ext) cudaFree(g->Bpart);
 	cudaFree(g->Eext); cudaFree(g->Bext);
 	cudaFree(g->E); cudaFree(g->B); cudaFree(g->J); cudaFree(g->tmp); cudaFree(g->tmp2); cudaFree(g->d_sums);
+	if (g->slab) zdev_link_close(&g->link);
 	free(g);
 }
 
@@ -82,6 +89,93 @@ extern "C" void zdev_grid2d_download(zdev_grid2d* g, int which, float* host_buf)
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 }
 extern "C" float* zdev_grid2d_ptr(zdev_grid2d* g, int which) { return (float*) grid_sel(g, which); }
+
+// the slab's window of a wider host buffer (row stride host_nrow cells): local buffer column c = host buffer
+// column x0 + c, guards included (the host mirrors of a decomposed run are global, the device grids local)
+extern "C" void zdev_grid2d_upload_window(zdev_grid2d* g, int which, const float* host_buf, int host_nrow, int x0) {
+	ZDEV_CHECK(cudaMemcpy2DAsync(grid_sel(g, which), (size_t) g->nrow * sizeof(f3), (const f3*) host_buf + x0,
+	                             (size_t) host_nrow * sizeof(f3), (size_t) g->nrow * sizeof(f3), g->nrows,
+	                             cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+}
+extern "C" void zdev_grid2d_download_window(zdev_grid2d* g, int which, float* host_buf, int host_nrow, int x0) {
+	ZDEV_CHECK(cudaMemcpy2DAsync((f3*) host_buf + x0, (size_t) host_nrow * sizeof(f3), grid_sel(g, which),
+	                             (size_t) g->nrow * sizeof(f3), (size_t) g->nrow * sizeof(f3), g->nrows,
+	                             cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+}
+
+// ------------------------------------------------------------------ slab links (zdev_slab.cuh)
+
+extern "C" void zdev_grid2d_set_slab(zdev_grid2d* g, int left, int right, int wrap_left, int wrap_right) {
+	if (g->slab) return;
+	// the largest message: three columns of two grids, every row
+	zdev_link_open(&g->link, (size_t) 2 * 3 * g->nrows * sizeof(f3), left, right);
+	g->slab = 1; g->wrap_left = wrap_left; g->wrap_right = wrap_right;
+}
+
+struct slab_msg { f3* buf; unsigned* flag; int i0, ncols; };      // one side of an exchange; buf == nullptr: nothing
+
+// blockIdx.y = side.  Columns [i0, i0+ncols) x rows [j0, j0+nrows) of up to two grids -> the neighbour's payload
+__global__ void k_slab_send(const f3* __restrict__ G0, const f3* __restrict__ G1, int ngrids, int nrow, int j0, int nrows,
+                            slab_msg L, slab_msg R, unsigned seq_l, unsigned seq_r, unsigned* ticket) {
+	const slab_msg m = blockIdx.y ? R : L;
+	const unsigned seq = blockIdx.y ? seq_r : seq_l;
+	if (!m.buf) return;
+	const int per = m.ncols * nrows, n = ngrids * per;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const int gsel = k / per, q = k - gsel * per, r = q / m.ncols, c = q - r * m.ncols;
+		m.buf[k] = (gsel ? G1 : G0)[cidx(m.i0 + c, j0 + r, nrow)];
+	}
+	slab_publish(ticket + blockIdx.y, gridDim.x, m.flag, seq);
+}
+// ... and my payload -> my guard columns (add = 1: the J fold)
+__global__ void k_slab_recv(f3* __restrict__ G0, f3* __restrict__ G1, int ngrids, int nrow, int j0, int nrows,
+                            slab_msg L, slab_msg R, unsigned seq_l, unsigned seq_r, int add) {
+	const slab_msg m = blockIdx.y ? R : L;
+	const unsigned seq = blockIdx.y ? seq_r : seq_l;
+	if (!m.buf) return;
+	slab_wait(m.flag, seq);
+	const int per = m.ncols * nrows, n = ngrids * per;
+	for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const int gsel = k / per, q = k - gsel * per, r = q / m.ncols, c = q - r * m.ncols;
+		const float* src = reinterpret_cast<const float*>(m.buf + k);
+		f3 v; v.x = __ldcg(src); v.y = __ldcg(src + 1); v.z = __ldcg(src + 2);       // written by another GPU: past L1
+		f3* d = &(gsel ? G1 : G0)[cidx(m.i0 + c, j0 + r, nrow)];
+		if (add) { f3 o = *d; o.x += v.x; o.y += v.y; o.z += v.z; *d = o; } else *d = v;
+	}
+}
+
+// One exchange with both neighbours: columns [sl, sl+nsl) go to the left neighbour and [sr, sr+nsr) to the right
+// one; what the left neighbour sent lands in [rl, rl+nrl), the right one's in [rr, rr+nrr).
+static void slab_exchange(zdev_grid2d* g, f3* G0, f3* G1, int sl, int nsl, int sr, int nsr, int rl, int nrl, int rr, int nrr,
+                          int j0, int nrows, int add, bool do_l, bool do_r) {
+	zdev_link& K = g->link;
+	do_l = do_l && K.left >= 0; do_r = do_r && K.right >= 0;
+	if (!do_l && !do_r) return;
+	const int ngrids = G1 ? 2 : 1;
+	slab_msg SL = { nullptr, nullptr, 0, 0 }, SR = SL, RL = SL, RR = SL;
+	unsigned seq_l = 0, seq_r = 0;
+	if (do_l) {
+		seq_l = ++K.seq[0];
+		SL = { (f3*) zdev_link_out(K, 0, seq_l), &zdev_link_out_hdr(K, 0)->flag[1], sl, nsl };
+		RL = { (f3*) zdev_link_in(K, 0, seq_l), &zdev_link_in_hdr(K)->flag[0], rl, nrl };
+	}
+	if (do_r) {
+		seq_r = ++K.seq[1];
+		SR = { (f3*) zdev_link_out(K, 1, seq_r), &zdev_link_out_hdr(K, 1)->flag[0], sr, nsr };
+		RR = { (f3*) zdev_link_in(K, 1, seq_r), &zdev_link_in_hdr(K)->flag[1], rr, nrr };
+	}
+	const int nmax = ngrids * 3 * nrows;
+	dim3 grd(std::max(1, std::min(zdev_div_up(nmax, 256), 32)), 2);
+	ZDEV_LAUNCH(k_slab_send, grd, 256, 0, G0, G1, ngrids, g->nrow, j0, nrows, SL, SR, seq_l, seq_r, K.ticket);
+	ZDEV_LAUNCH(k_slab_recv, grd, 256, 0, G0, G1, ngrids, g->nrow, j0, nrows, RL, RR, seq_l, seq_r, add);
+}
+// guards <- neighbour interior: (-1) <- left's (nx-1); (nx, nx+1) <- right's (0, 1)
+static void slab_halo_refresh(zdev_grid2d* g, f3* G0, f3* G1, int j0, int nrows, bool skip_wrap) {
+	slab_exchange(g, G0, G1, 0, 2, g->nx - 1, 1, -1, 1, g->nx, 2, j0, nrows, 0,
+	              !(skip_wrap && g->wrap_left), !(skip_wrap && g->wrap_right));
+}
 
 extern "C" void zdev_current_zero(zdev_grid2d* g) {
 	need_J(g);
@@ -605,8 +699,31 @@ extern "C" void zdev_grid2d_unpack_cols(zdev_grid2d* g, int which, int i0, int n
 }
 
 extern "C" void zdev_current_update(zdev_grid2d* g, int moving_window, int xtype, int ytype, int xlevel, int ylevel) {
-	zdev_current_update_gc(g, moving_window);
-	zdev_current_smooth(g, moving_window, xtype, ytype, xlevel, ylevel);
+	if (!g->slab) {
+		zdev_current_update_gc(g, moving_window);
+		zdev_current_smooth(g, moving_window, xtype, ytype, xlevel, ylevel);
+		return;
+	}
+	// One slab of a wider box.  Guard fold: the three aliased columns (nx-1, nx, nx+1) <-> (-1, 0, 1)
+	// of two neighbours are swapped and ADDED on both sides (addition commutes: both end up with the sums the
+	// reference's fold-and-copy-back leaves, em2d/current.c:128-137); then the local y fold.
+	need_J(g);
+	slab_exchange(g, g->J, nullptr, -1, 3, g->nx - 1, 3, -1, 3, g->nx - 1, 3, -1, g->nrows, 1, true, true);
+	ZDEV_LAUNCH(k_fold_y, zdev_div_up(g->nrow, 128), 128, 0, g->J, g->ny, g->nrow);
+	// Smoothing: a pass leaves the x guards alone (as under a moving window); guards that mirror a neighbour's
+	// cells are refreshed from it after every x pass (em2d/current.c:346-352).
+	int dirs[64]; float sa[64], sb[64];
+	const int np = zdev_smooth_plan(xtype, ytype, xlevel, ylevel, dirs, sa, sb);
+	bool y_passes = false;
+	for (int k = 0; k < np; k++) {
+		smooth_pass(g, dirs[k], sa[k], sb[k], 1);
+		if (dirs[k] == 0) slab_halo_refresh(g, g->J, nullptr, 0, g->ny, false);
+		else y_passes = true;
+	}
+	// kernel_y leaves the x guard columns un-filtered (em2d/current.c:382-411).  Across the box boundary that is
+	// what the reference feeds to yee_e, so the wrap-around edge keeps it; guards that mirror interior cells of a
+	// neighbour slab must see the filtered values.
+	if (y_passes) slab_halo_refresh(g, g->J, nullptr, -1, g->nrows, true);
 }
 
 // ------------------------------------------------------------------ moving window
@@ -702,6 +819,17 @@ extern "C" void zdev_emf_advance(zdev_grid2d* g, zdev_grid2d* gj, float dt, floa
 		zdev_yee_b(g, dtb / dx, dtb / dy);
 		zdev_yee_e(g, gj, dt / dx, dt / dy, dt);
 		zdev_yee_b(g, dtb / dx, dtb / dy);
+	}
+	if (g->slab) {
+		// guards towards a neighbour slab come from its interior (every row), then the local periodic y copies
+		slab_halo_refresh(g, g->E, g->B, -1, g->nrows, false);
+		zdev_emf_update_gc(g, 1);
+		update_part_fld(g);
+		if (shift_window) {
+			zdev_emf_shift(g, g->link.right < 0);     // interior right edges shift without zeroing ...
+			slab_halo_refresh(g, g->E, g->B, -1, g->nrows, false);       // ... and take the new columns from the neighbour
+		}
+		return;
 	}
 	zdev_emf_update_gc(g, moving_window);
 	update_part_fld(g);

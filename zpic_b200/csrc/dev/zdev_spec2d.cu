@@ -40,6 +40,7 @@
 #include "pic2d_core.cuh"
 #include "pic2d_packed.cuh"
 #include "zdev_tma.cuh"
+#include "zdev_slab.cuh"
 #include <vector>
 #include <algorithm>
 #include <cstring>
@@ -126,6 +127,14 @@ struct zdev_spec2d {
 	int64_t np_host;                 // last known particle count
 	int np_known;                    // np_host is exact (no absorbing boundary / slab exchange since it was counted)
 	ctl2d last; int last_valid;      // control block of the last advance as read by the overflow check
+	// The step's control block travels to a pinned host copy behind the step's kernels; the host looks at it
+	// (full tiles? overflowed lists?) only when it next needs to - normally at the start of the next advance,
+	// when the copy has long arrived - so a time step never waits for the stream to drain.
+	ctl2d* h_ctl; cudaEvent_t ev_ctl; int ctl_pending;
+	// slab decomposition (zdev_slab.cuh): particles that leave through a slab edge are written straight into the
+	// neighbour's mailbox by k_migrate2d and appended there by k_slab_import
+	int slab; zdev_link link;
+	int gx0, gnx;                    // this slab's first column in the whole box, and the box width
 	int ids_valid;                   // tags are a permutation of [0,np)
 	std::vector<int64_t>* h_off;     // host copy of tile_off
 	// optional device timing of the push kernel alone (bench roofline): ring of event pairs
@@ -228,6 +237,9 @@ extern "C" zdev_spec2d* zdev_spec2d_create(int nx, int ny, int ppc_hint, int tra
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np_q, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_CHECK(cudaMalloc(&s->ctl, sizeof(ctl2d)));
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
+	ZDEV_CHECK(cudaHostAlloc((void**) &s->h_ctl, sizeof(ctl2d), cudaHostAllocPortable));
+	ZDEV_CHECK(cudaEventCreateWithFlags(&s->ev_ctl, cudaEventDisableTiming));
+	s->gnx = nx;
 	s->h_off = new std::vector<int64_t>();
 	return s;
 }
@@ -250,7 +262,7 @@ static void mig_alloc(zdev_spec2d* s, int div) {
 static void spec_free_particles(zdev_spec2d* s) {
 	for (int k = 0; k < 2; k++) { cudaFree(s->exp_buf[k]); s->exp_buf[k] = nullptr; }
 	cudaFree(s->stage); s->stage = nullptr; s->stage_cap = 0;
-	s->exp_cap = 0;
+	if (!s->slab) s->exp_cap = 0;        // (linked slabs export into the neighbours' mailboxes, sized once)
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); }
 	mig_free(s);
 	cudaFree(s->ovf); cudaFree(s->ovf_tag); s->ovf = nullptr; s->ovf_tag = nullptr; s->ovf_cap = 0;
@@ -262,6 +274,8 @@ extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	spec_free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl); cudaFree(s->tile_list);
+	cudaFreeHost(s->h_ctl); cudaEventDestroy(s->ev_ctl);
+	if (s->slab) zdev_link_close(&s->link);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -371,6 +385,14 @@ __global__ void k_scatter_tiles(const part_aos* __restrict__ a, int64_t np, int 
 }
 
 static void spec_resolve_overflow(zdev_spec2d* s);
+// send the control block to the host behind everything enqueued so far (no wait)
+static void spec_snapshot_ctl(zdev_spec2d* s) {
+	ZDEV_CHECK(cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(ctl2d), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaEventRecord(s->ev_ctl, zdev_strm));
+	s->ctl_pending = 1;
+}
+// look at the last snapshot (waits for it if it is still in flight) and deal with full tiles
+static void spec_settle(zdev_spec2d* s) { if (s->ctl_pending) spec_resolve_overflow(s); }
 static void check_flags(zdev_spec2d* s, unsigned int flags) {
 	if (flags & 8u) {
 		fprintf(stderr, "(*error*) zpic-b200: more than %u particles found their tile full in one step (tile %dx%d cells); "
@@ -470,6 +492,7 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np) {
 	if (np <= 0) return;
 	if (!s->cap_total) { zdev_spec2d_upload(s, part, np); return; }
+	spec_settle(s);
 	if (np > s->stage_cap) {
 		if (s->stage) { ZDEV_CHECK(cudaStreamSynchronize(zdev_strm)); cudaFree(s->stage); }
 		s->stage_cap = np + np / 2 + 1024;
@@ -479,7 +502,7 @@ extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np)
 	ZDEV_CHECK(cudaMemcpyAsync(s->stage, part, (size_t) np * sizeof(part_aos), cudaMemcpyHostToDevice, zdev_strm));
 	spec_append_dev(s, s->stage, np, (int) s->np_host);
 	s->np_host += np;
-	spec_resolve_overflow(s);          // a full tile: grow now, so that every consumer sees the whole population
+	spec_snapshot_ctl(s);              // a full tile is dealt with before anybody looks at the population again
 }
 
 // per tile: number of live slots (slots whose cell is not -1)
@@ -527,6 +550,7 @@ __global__ void k_gather_aos(soa2d p, const int64_t* __restrict__ off, const int
 
 // live particles per tile -> host vector; returns the total
 static int64_t spec_live_counts(zdev_spec2d* s, std::vector<int>& cnt) {
+	spec_settle(s);
 	int* d_live; ZDEV_CHECK(cudaMalloc(&d_live, (size_t) s->ntiles * sizeof(int)));
 	ZDEV_LAUNCH(k_count_live, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_live);
 	cnt.resize(s->ntiles);
@@ -598,8 +622,14 @@ __global__ void k_relayout(soa2d src, const int64_t* __restrict__ off_src, soa2d
 static void spec_resolve_overflow(zdev_spec2d* s) {
 	s->appended = 0;
 	ctl2d h;
-	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
-	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	if (s->ctl_pending) {
+		ZDEV_CHECK(cudaEventSynchronize(s->ev_ctl));
+		h = *s->h_ctl;
+		s->ctl_pending = 0;
+	} else {
+		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	}
 	while (h.flags & 1u) {
 		const auto t_start = std::chrono::steady_clock::now();
 		check_flags(s, h.flags & (2u | 4u | 8u));
@@ -706,7 +736,7 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t gid, float& a, f
 // 335-347), momenta as spec_set_u (thermal, minus the cell mean, plus fluid; :96-142)
 __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* tile_np,
                                  int nx, int ny, int TX, int TY, int ntx, int ppcx, int ppcy,
-                                 f3 ufl, f3 uth, uint64_t seed, int iy0, int iy1) {
+                                 f3 ufl, f3 uth, uint64_t seed, int iy0, int iy1, int gx0, int gnx) {
 	int64_t cell = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (cell >= (int64_t) nx * ny) return;
 	int iy = (int) (cell / nx), ix = (int) (cell - (int64_t) iy * nx);
@@ -718,7 +748,7 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 	// rows of the tile inside the band are packed from the tile's first slot
 	const int ly0 = max(iy0 - ty * TY, 0);
 	int64_t base = off[t] + (int64_t) (lx + (ly - ly0) * cx) * npc;
-	uint64_t gid0 = (uint64_t) cell * npc;
+	uint64_t gid0 = ((uint64_t) (gx0 + ix) + (uint64_t) gnx * iy) * npc;     // numbered by cell of the WHOLE box
 	float sx = 0, sy = 0, sz = 0;
 	for (int k = 0; k < npc; k++) {
 		float a, b, c; normal3(seed, gid0 + k, a, b, c);
@@ -769,7 +799,7 @@ extern "C" void zdev_spec2d_inject_band(zdev_spec2d* s, int ppcx, int ppcy, cons
 	int64_t ncell = (int64_t) s->nx * s->ny;
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 	ZDEV_LAUNCH(k_inject_uniform, zdev_div_up(ncell, 128), 128, 0, s->p, s->tile_off, s->tile_np,
-	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed, iy0, iy1);
+	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed, iy0, iy1, s->gx0, s->gnx);
 	s->np_host = np; s->np_known = 1;
 	s->ids_valid = s->track_ids && np < 0x7fffffff;
 }
@@ -1273,6 +1303,10 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	}
 }
 
+// linked slabs (zdev_slab.cuh): where k_migrate2d announces its exports, and where k_slab_import finds the imports
+struct slab_pub { unsigned* ticket; unsigned* flag[2]; unsigned* count[2]; unsigned seq[2]; };
+struct slab_in { const unsigned* flag[2]; const unsigned* count[2]; const part_aos* rec[2]; unsigned seq[2]; };
+
 // Boundary conditions for the particles that left their tile (reference particles.c:1237-1259: periodic y
 // always; x periodic, absorbing under a moving window, or handed to the neighbour slab), then append them
 // to their destination tiles.  One warp per tile segment.
@@ -1280,7 +1314,7 @@ __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* 
                             ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int ntiles, int nx, int ny,
                             int moving_window, int slab_left, int slab_right,
                             part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap,
-                            part_aos* __restrict__ ovf, int* __restrict__ ovf_tag, unsigned int ovf_cap) {
+                            part_aos* __restrict__ ovf, int* __restrict__ ovf_tag, unsigned int ovf_cap, slab_pub pub) {
 	const int lane = threadIdx.x & 31;
 	const int nwarp = (gridDim.x * blockDim.x) >> 5;
 	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
@@ -1317,6 +1351,35 @@ __global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* 
 			p.key[d] = (unsigned short) (lx + ly * TX);
 			if (p.tag) p.tag[d] = mig.tag[mb + k];
 		}
+	}
+	// linked slabs: the export lists ARE the neighbours' mailboxes; tell them how many records arrived
+	if (pub.flag[0]) slab_publish(pub.ticket, gridDim.x, pub.flag[0], pub.seq[0], pub.count[0], &ctl->n_exp[0]);
+	if (pub.flag[1]) slab_publish(pub.ticket + 1, gridDim.x, pub.flag[1], pub.seq[1], pub.count[1], &ctl->n_exp[1]);
+}
+
+// What the neighbour slabs sent (blockIdx.y = side): wait for the message, then append its records to their tiles
+__global__ void k_slab_import(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, ctl2d* __restrict__ ctl,
+                              int TX, int TY, int ntx, slab_in in, unsigned int cap, part_aos* __restrict__ ovf,
+                              int* __restrict__ ovf_tag, unsigned int ovf_cap) {
+	const int side = blockIdx.y;
+	if (!in.flag[side]) return;
+	slab_wait(in.flag[side], in.seq[side]);
+	const unsigned n = min(__ldcg(in.count[side]), cap);       // (a sender whose list overflowed aborts at its next step)
+	const int* src = reinterpret_cast<const int*>(in.rec[side]);
+	for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+		const int* w = src + (size_t) k * 7;
+		part_aos r;
+		r.ix = __ldcg(w); r.iy = __ldcg(w + 1);
+		r.x = __int_as_float(__ldcg(w + 2)); r.y = __int_as_float(__ldcg(w + 3));
+		r.ux = __int_as_float(__ldcg(w + 4)); r.uy = __int_as_float(__ldcg(w + 5)); r.uz = __int_as_float(__ldcg(w + 6));
+		const int tx = r.ix / TX, ty = r.iy / TY, t = tx + ty * ntx;
+		const int slot = atomicAdd(&tile_np[t], 1);
+		const int64_t d = tile_off[t] + slot;
+		if (d >= tile_off[t + 1]) { atomicSub(&tile_np[t], 1); ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, 0); continue; }
+		const int lx = r.ix - tx * TX, ly = r.iy - ty * TY;
+		rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz);
+		p.key[d] = (unsigned short) (lx + ly * TX);
+		if (p.tag) p.tag[d] = 0;
 	}
 }
 
@@ -1374,8 +1437,14 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	    zdev_grid2d_nx(gcur) != s->nx || zdev_grid2d_ny(gcur) != s->ny) {
 		fprintf(stderr, "(*error*) zdev_spec2d_advance: species / grid size mismatch\n"); exit(-1);
 	}
-	if (s->cap_total && s->appended) spec_resolve_overflow(s);      // appends since the last step may have hit a full tile
+	spec_settle(s);                  // the last step (or an append since) may have hit a full tile: grow before pushing
+	if (s->cap_total && s->appended) spec_resolve_overflow(s);
 	s->last_valid = 0;
+	const int slab_left = s->slab ? (s->link.left >= 0) : prm->slab_left;
+	const int slab_right = s->slab ? (s->link.right >= 0) : prm->slab_right;
+	zdev_push2d_params prm_local = *prm;
+	prm_local.slab_left = slab_left; prm_local.slab_right = slab_right;
+	prm = &prm_local;
 	if (prm->moving_window || prm->slab_left || prm->slab_right) s->np_known = 0;
 	ZDEV_CHECK(cudaMemsetAsync(s->ctl, 0, sizeof(ctl2d), zdev_strm));
 	if (!s->cap_total) return;
@@ -1391,22 +1460,43 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	// B becomes the current buffer
 	{ soa2d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
-	if ((prm->slab_left || prm->slab_right) && !s->exp_cap) {
+	if ((prm->slab_left || prm->slab_right) && !s->exp_cap && !s->slab) {
 		// a window shift sends a whole column at once: size the export lists for two columns
 		int64_t cap = (int64_t) 2 * s->ppc_hint * s->ny + 65536;
 		s->exp_cap = (unsigned int) cap;
 		for (int k = 0; k < 2; k++) ZDEV_CHECK(cudaMalloc(&s->exp_buf[k], (size_t) cap * sizeof(part_aos)));
 	}
+	slab_pub pub; memset(&pub, 0, sizeof pub);
+	slab_in in; memset(&in, 0, sizeof in);
+	part_aos* exp_l = s->exp_buf[0]; part_aos* exp_r = s->exp_buf[1];
+	if (s->slab) {
+		zdev_link& K = s->link;
+		pub.ticket = K.ticket;
+		for (int side = 0; side < 2; side++) {
+			if ((side ? K.right : K.left) < 0) continue;
+			const unsigned seq = ++K.seq[side];
+			zdev_mbox_hdr* out = zdev_link_out_hdr(K, side);
+			pub.flag[side] = &out->flag[1 - side]; pub.count[side] = &out->count[1 - side][seq & 1u]; pub.seq[side] = seq;
+			(side ? exp_r : exp_l) = (part_aos*) zdev_link_out(K, side, seq);
+			zdev_mbox_hdr* me = zdev_link_in_hdr(K);
+			in.flag[side] = &me->flag[side]; in.count[side] = &me->count[side][seq & 1u]; in.seq[side] = seq;
+			in.rec[side] = (const part_aos*) zdev_link_in(K, side, seq);
+		}
+	}
 	ZDEV_LAUNCH(k_migrate2d, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
 	            s->TX, s->TY, s->ntx, s->ntiles, s->nx, s->ny, prm->moving_window, prm->slab_left, prm->slab_right,
-	            s->exp_buf[0], s->exp_buf[1], s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap);
-	spec_resolve_overflow(s);
+	            exp_l, exp_r, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap, pub);
+	if (s->slab)
+		ZDEV_LAUNCH(k_slab_import, dim3(2 * zdev_num_sm, 2), 256, 0, s->p, s->tile_off, s->tile_np, s->ctl, s->TX, s->TY, s->ntx,
+		            in, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap);
+	spec_snapshot_ctl(s);
 	if (prm->moving_window || prm->slab_left || prm->slab_right) s->ids_valid = 0;
 }
 
 extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* np) {
 	// the overflow check at the end of the advance has already brought the step's control block to the host;
 	// the particle count only changes through absorbing boundaries, slab exchange and appends
+	spec_settle(s);
 	if (s->last_valid && (!np || s->np_known)) {
 		check_flags(s, s->last.flags);
 		if (np) *np = s->np_host;
@@ -1483,6 +1573,7 @@ static float* g_rho_pin = nullptr;
 static size_t g_rho_cap = 0;
 
 extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_window, float* charge) {
+	spec_settle(s);
 	size_t n = (size_t) (s->nx + 1) * (s->ny + 1);
 	if (n > g_rho_cap) {
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -1504,6 +1595,20 @@ extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_w
 	memcpy(charge, g_rho_pin, n * sizeof(float));
 }
 
+// the slab's own deposit alone: rho = (nx+1)*(ny+1) floats, overwritten, NOT folded (the caller joins the slabs,
+// adds the shared edge columns and applies the box's periodic folds)
+extern "C" void zdev_spec2d_deposit_charge_raw(zdev_spec2d* s, float q, float* rho) {
+	spec_settle(s);
+	const size_t n = (size_t) (s->nx + 1) * (s->ny + 1);
+	float* d_rho; ZDEV_CHECK(cudaMalloc(&d_rho, n * sizeof(float)));
+	ZDEV_CHECK(cudaMemsetAsync(d_rho, 0, n * sizeof(float), zdev_strm));
+	if (s->cap_total)
+		ZDEV_LAUNCH(k_deposit_charge, s->ntiles, 256, 0, s->p, s->tile_off, s->tile_np, d_rho, s->nx + 1, q, s->TX, s->TY, s->ntx);
+	ZDEV_CHECK(cudaMemcpyAsync(rho, d_rho, n * sizeof(float), cudaMemcpyDeviceToHost, zdev_strm));
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	cudaFree(d_rho);
+}
+
 // ------------------------------------------------------------------ phasespace density
 
 // reference spec_deposit_pha, em2d/particles.c:1569-1632: linear deposit of the charge on a 2-D grid over two of
@@ -1511,7 +1616,7 @@ extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_w
 // accumulated per CTA in shared memory and merged with one L2 reduction per touched bin; larger ones go
 // straight to L2.
 #define PHA_SMEM_BINS 8192
-struct pha_params { int q1, q2, n1, n2; float min1, min2, rd1, rd2, q, dx, dy; };
+struct pha_params { int q1, q2, n1, n2; float min1, min2, rd1, rd2, q, dx, dy; int gx0; };
 
 __device__ __forceinline__ float pha_axis(int quant, float x, float y, float ux, float uy, float uz, int ix, int iy, float dx, float dy) {
 	switch (quant) {                      // the reference's X1, X2, U1, U2, U3 (em2d/particles.h:236-240)
@@ -1540,7 +1645,7 @@ __global__ void k_deposit_pha(soa2d p, const int64_t* __restrict__ off, const in
 			const unsigned key = p.key[b + k];
 			if (key == KEY_EMPTY) continue;
 			const rec20 v = rec_load(p.rec, b + k);
-			const int ix = x0 + (int) (key % TX), iy = y0 + (int) (key / TX);
+			const int ix = a.gx0 + x0 + (int) (key % TX), iy = y0 + (int) (key / TX);
 			const float nx1 = (pha_axis(a.q1, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min1) * a.rd1;
 			const float nx2 = (pha_axis(a.q2, v.x, v.y, v.ux, v.uy, v.uz, ix, iy, a.dx, a.dy) - a.min2) * a.rd2;
 			const int i1 = (int) (nx1 + 0.5f), i2 = (int) (nx2 + 0.5f);
@@ -1565,6 +1670,7 @@ __global__ void k_deposit_pha(soa2d p, const int64_t* __restrict__ off, const in
 
 extern "C" void zdev_spec2d_deposit_pha(zdev_spec2d* s, int quant1, int quant2, const int pha_nx[2], const float pha_range[2][2],
                                         float q, float dx, float dy, float* host_buf) {
+	spec_settle(s);
 	const size_t n = (size_t) pha_nx[0] * pha_nx[1];
 	float* d_buf; ZDEV_CHECK(cudaMalloc(&d_buf, n * sizeof(float)));
 	ZDEV_CHECK(cudaMemcpyAsync(d_buf, host_buf, n * sizeof(float), cudaMemcpyHostToDevice, zdev_strm));
@@ -1574,7 +1680,7 @@ extern "C" void zdev_spec2d_deposit_pha(zdev_spec2d* s, int quant1, int quant2, 
 		a.min1 = pha_range[0][0]; a.min2 = pha_range[1][0];
 		a.rd1 = pha_nx[0] / (pha_range[0][1] - pha_range[0][0]);       // float arithmetic as the reference (:1583-1584)
 		a.rd2 = pha_nx[1] / (pha_range[1][1] - pha_range[1][0]);
-		a.q = q; a.dx = dx; a.dy = dy;
+		a.q = q; a.dx = dx; a.dy = dy; a.gx0 = s->gx0;
 		const int use_smem = n <= PHA_SMEM_BINS;
 		const int grid = s->ntiles < 4 * zdev_num_sm ? s->ntiles : 4 * zdev_num_sm;
 		ZDEV_LAUNCH(k_deposit_pha, grid, 256, use_smem ? n * sizeof(float) : 0, s->p, s->tile_off, s->tile_np, s->ntiles,
@@ -1588,6 +1694,7 @@ extern "C" void zdev_spec2d_deposit_pha(zdev_spec2d* s, int quant1, int quant2, 
 // ------------------------------------------------------------------ slab decomposition support
 
 extern "C" void zdev_spec2d_export_counts(zdev_spec2d* s, int64_t counts[2]) {
+	spec_settle(s);
 	ctl2d h;
 	ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof(h), cudaMemcpyDeviceToHost, zdev_strm));
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -1602,8 +1709,21 @@ extern "C" void zdev_spec2d_append_device(zdev_spec2d* s, const void* dev_aos, i
 		fprintf(stderr, "(*error*) zdev_spec2d_append_device: species has no tile layout yet (upload or inject first)\n");
 		exit(-1);
 	}
+	spec_settle(s);
 	spec_append_dev(s, (const part_aos*) dev_aos, np, 0);
 	s->np_host += np;
 	s->ids_valid = 0;
-	spec_resolve_overflow(s);
+	spec_snapshot_ctl(s);
+}
+
+// This species is one slab of a wider box: open the links to the neighbour slabs (collective over the ranks).
+// gx0 / gnx: the slab's first column in the whole box and the box width (the device-side injector numbers its
+// particles by GLOBAL cell, so the decomposed population is the single-domain one).
+extern "C" void zdev_spec2d_set_slab(zdev_spec2d* s, int left, int right, int gx0, int gnx) {
+	if (s->slab) return;
+	// a window shift sends a whole column at once: room for two columns of the nominal fill, and then some
+	const int64_t cap = (int64_t) 2 * s->ppc_hint * s->ny + 65536;
+	s->exp_cap = (unsigned int) cap;
+	zdev_link_open(&s->link, (size_t) cap * sizeof(part_aos), left, right);
+	s->slab = 1; s->gx0 = gx0; s->gnx = gnx;
 }

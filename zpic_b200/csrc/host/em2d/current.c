@@ -67,6 +67,7 @@ void current_report( const t_current *current, const int jc )
 		return;
 	}
 	zb_cur_to_host(current);
+	if (zb_par_rank() != 0) return;          /* one file per box: rank 0 writes it */
 
 	const int nx = current->nx[0], ny = current->nx[1];
 	float* buf = malloc((size_t) nx * ny * sizeof(float));

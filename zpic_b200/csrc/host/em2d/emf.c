@@ -271,6 +271,18 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	float3 *ge = NULL, *gb = NULL;
 	if (ext_fld->E_type == EMF_FLD_TYPE_CUSTOM) ge = eval_ext_grid(emf, ext_fld->E_custom, ext_fld->E_custom_data);
 	if (ext_fld->B_type == EMF_FLD_TYPE_CUSTOM) gb = eval_ext_grid(emf, ext_fld->B_custom, ext_fld->B_custom_data);
+	if (e->slab.on) {
+		/* the device grid is this rank's window of the box-wide buffers */
+		const int nrl = e->slab.nxl + 3, nrows = emf->nx[1] + 3;
+		for (int f = 0; f < 2; f++) {
+			float3** gp = f ? &gb : &ge;
+			if (!*gp) continue;
+			float3* w = malloc((size_t) nrl * nrows * sizeof(float3));
+			for (int r = 0; r < nrows; r++)
+				memcpy(w + (size_t) r * nrl, *gp + (size_t) r * emf->nrow + e->slab.x0, (size_t) nrl * sizeof(float3));
+			free(*gp); *gp = w;
+		}
+	}
 	if (ge || gb) zdev_emf_set_ext_grid(zb_dev(e), (const float*) ge, (const float*) gb);
 	free(ge); free(gb);
 	e->part_host_stale = 1;
@@ -308,6 +320,7 @@ void emf_get_energy( const t_emf *emf, double energy[] )
 	zb_emf_to_device((t_emf*) emf);
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	zdev_emf_energy(zb_dev(e), energy);
+	if (e->slab.on) zb_par_allreduce_sum_d(energy, 6);      /* the slabs' interiors tile the box */
 	for (int i = 0; i < 6; i++) energy[i] *= 0.5 * emf->dx[0] * emf->dx[1];
 }
 
@@ -320,6 +333,7 @@ void emf_report( const t_emf *emf, const char field, const int fc )
 		return;
 	}
 	zb_emf_to_host(emf);
+	if (zb_par_rank() != 0) return;          /* one file per box: rank 0 writes it */
 
 	char name[16], label[16];
 	const float3* f;

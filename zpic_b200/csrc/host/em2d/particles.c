@@ -363,13 +363,24 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
 		t_part* col = NULL; int ncol = 0, ncol_max = 0;
 		spec_inject_into(spec, range, &col, &ncol, &ncol_max);
-		zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+		if (!s->slab.on) zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+		else if (s->slab.is_last) {
+			/* every rank runs the injector (the global random stream stays in step); the column belongs to the last slab */
+			for (int i = 0; i < ncol; i++) col[i].ix -= s->slab.x0;
+			zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+		}
 		free(col);
 	}
 
 	if (!zb_opt_lazy()) {
 		double esum; int64_t np;
 		zdev_spec2d_fetch(zb_spec_dev(s), &esum, &np);
+		if (s->slab.on) {          /* the diagnostics of the API are those of the whole box */
+			long long n = np;
+			zb_par_allreduce_sum_d(&esum, 1);
+			zb_par_allreduce_sum_ll(&n, 1);
+			np = n;
+		}
 		spec->energy = spec->q * spec->m_q * esum * spec->dx[0] * spec->dx[1];
 		/* the count is taken after the append: the injected column is already in it */
 		spec->np = (np > 0x7fffffffLL) ? 0x7fffffff : (int) np;
@@ -387,7 +398,25 @@ void spec_deposit_charge( const t_species* spec, float* charge )
 {
 	zb_spec_to_device((t_species*) spec);
 	zb_spec* s = zb_spec_of(spec, 1);
-	zdev_spec2d_deposit_charge(zb_spec_dev(s), spec->q, spec->moving_window, charge);
+	if (!s->slab.on) {
+		zdev_spec2d_deposit_charge(zb_spec_dev(s), spec->q, spec->moving_window, charge);
+		return;
+	}
+	/* slabs: every rank deposits its own particles on its (nxl+1) x (ny+1) nodes; the slabs are joined in box
+	   coordinates (a slab's last node column is its right neighbour's first: summed), then the box's periodic
+	   folds of the reference (particles.c:1310-1322) are applied and the result ADDED to the caller's array */
+	const int nx = spec->nx[0], ny = spec->nx[1], nxl = s->slab.nxl, x0 = s->slab.x0;
+	float* loc = malloc((size_t) (nxl + 1) * (ny + 1) * sizeof(float));
+	zdev_spec2d_deposit_charge_raw(zb_spec_dev(s), spec->q, loc);
+	float* box = calloc((size_t) (nx + 1) * (ny + 1), sizeof(float));
+	for (int j = 0; j <= ny; j++)
+		for (int i = 0; i <= nxl; i++) box[(size_t) j * (nx + 1) + x0 + i] = loc[(size_t) j * (nxl + 1) + i];
+	zb_par_allreduce_sum_f(box, (size_t) (nx + 1) * (ny + 1));
+	if (!spec->moving_window)
+		for (int j = 0; j <= ny; j++) box[(size_t) j * (nx + 1)] += box[(size_t) j * (nx + 1) + nx];
+	for (int i = 0; i <= nx; i++) box[i] += box[(size_t) ny * (nx + 1) + i];
+	for (size_t k = 0; k < (size_t) (nx + 1) * (ny + 1); k++) charge[k] += box[k];
+	free(loc); free(box);
 }
 
 /* ------------------------------------------------------------------ reports (host, ZDF) */
@@ -430,6 +459,7 @@ static void report_charge( const t_species *spec )
 	const int nx = spec->nx[0], ny = spec->nx[1];
 	float* rho = calloc((size_t) (nx + 1) * (ny + 1), sizeof(float));
 	spec_deposit_charge(spec, rho);
+	if (zb_par_rank() != 0) { free(rho); return; }       /* one file per box: rank 0 writes it */
 	float* buf = malloc((size_t) nx * ny * sizeof(float));
 	for (int j = 0; j < ny; j++)
 		memcpy(buf + (size_t) j * nx, rho + (size_t) j * (nx + 1), nx * sizeof(float));
@@ -475,8 +505,19 @@ void spec_deposit_pha( const t_species *spec, const int rep_type,
 	{
 		zb_spec* e = zb_spec_of(spec, 0);
 		if (e && e->host_stale) {
+			if (!e->slab.on) {
+				zdev_spec2d_deposit_pha(zb_spec_dev(e), rep_type & 0x000F, (rep_type & 0x00F0) >> 4, pha_nx, pha_range,
+				                        spec->q, spec->dx[0], spec->dx[1], buf);
+				return;
+			}
+			/* slabs: every rank deposits its own particles (box coordinates), the grids are summed */
+			const size_t n = (size_t) pha_nx[0] * pha_nx[1];
+			float* part = calloc(n, sizeof(float));
 			zdev_spec2d_deposit_pha(zb_spec_dev(e), rep_type & 0x000F, (rep_type & 0x00F0) >> 4, pha_nx, pha_range,
-			                        spec->q, spec->dx[0], spec->dx[1], buf);
+			                        spec->q, spec->dx[0], spec->dx[1], part);
+			zb_par_allreduce_sum_f(part, n);
+			for (size_t k = 0; k < n; k++) buf[k] += part[k];
+			free(part);
 			return;
 		}
 	}
@@ -513,6 +554,7 @@ static void report_pha( const t_species *spec, const int rep_type,
 {
 	float* buf = calloc((size_t) pha_nx[0] * pha_nx[1], sizeof(float));
 	spec_deposit_pha(spec, rep_type, pha_nx, pha_range, buf);
+	if (zb_par_rank() != 0) { free(buf); return; }
 
 	const int q1 = rep_type & 0x000F, q2 = (rep_type & 0x00F0) >> 4;
 	static const char* ax_name[]  = { "x1", "x2", "x3", "u1", "u2", "u3" };
@@ -551,7 +593,7 @@ void spec_report( const t_species *spec, const int rep_type,
 		break;
 	case PARTICLES:
 		zb_spec_to_host(spec);
-		report_particles(spec);
+		if (zb_par_rank() == 0) report_particles(spec);
 		break;
 	}
 }

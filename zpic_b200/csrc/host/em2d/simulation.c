@@ -43,6 +43,7 @@ void sim_timings( t_simulation* sim, uint64_t t0, uint64_t t1 )
 void sim_new( t_simulation* sim, int nx[], float box[], float dt, float tmax, int ndump,
               t_species* species, int n_species )
 {
+	zb_par_init();       /* one process per GPU: join the job (no-op for a single process) */
 	sim->dt = dt;
 	sim->tmax = tmax;
 	sim->ndump = ndump;
@@ -105,7 +106,8 @@ void sim_report_energy( t_simulation* sim )
 	double tot_part = 0;
 	for (int i = 0; i < sim->n_species; i++) tot_part += sim->species[i].energy;
 
-	printf("Energy (fields | particles | total) = %e %e %e\n", tot_emf, tot_part, tot_emf + tot_part);
+	if (zb_par_rank() == 0)
+		printf("Energy (fields | particles | total) = %e %e %e\n", tot_emf, tot_part, tot_emf + tot_part);
 }
 
 void sim_delete( t_simulation* sim )

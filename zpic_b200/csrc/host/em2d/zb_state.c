@@ -6,6 +6,7 @@
 #include "zpic_b200.h"
 
 #define ZB_MAX 256
+#define ZB_MAX_RANKS_LOCAL 64
 static zb_grid grids[ZB_MAX];
 static int n_grids = 0;
 static zb_spec specs[ZB_MAX];
@@ -26,6 +27,29 @@ void zpic_b200_set_option( const char* name, int value ) {
 	else fprintf(stderr, "(*warning*) zpic_b200_set_option: unknown option %s\n", name);
 }
 
+zb_slab zb_slab_make( int nx, int window )
+{
+	zb_slab g;
+	memset(&g, 0, sizeof g);
+	const int n = zb_par_init();
+	g.rank = zb_par_rank(); g.nranks = n;
+	g.nxl = nx; g.x0 = 0; g.left = g.right = -1;
+	if (n <= 1) return g;
+	if (nx % n) {
+		fprintf(stderr, "(*error*) zpic-b200: %d cells along x cannot be cut into %d equal slabs\n", nx, n);
+		exit(-1);
+	}
+	g.on = 1;
+	g.nxl = nx / n; g.x0 = g.rank * g.nxl;
+	const int ring = !window;
+	g.left  = (ring || g.rank > 0)     ? (g.rank + n - 1) % n : -1;
+	g.right = (ring || g.rank < n - 1) ? (g.rank + 1) % n : -1;
+	g.is_last = g.rank == n - 1;
+	g.wrap_left = ring && g.rank == 0;
+	g.wrap_right = ring && g.rank == n - 1;
+	return g;
+}
+
 static zb_grid* grid_new( int nx, int ny ) {
 	if (n_grids == ZB_MAX) { fprintf(stderr, "(*error*) zpic-b200: too many live field objects\n"); exit(-1); }
 	zb_grid* e = &grids[n_grids++];
@@ -35,7 +59,12 @@ static zb_grid* grid_new( int nx, int ny ) {
 }
 
 zdev_grid2d* zb_dev( zb_grid* e ) {
-	if (!e->g) e->g = zdev_grid2d_create(e->nx, e->ny);
+	if (!e->g) {
+		const int window = (e->emf && e->emf->moving_window) || (e->cur && e->cur->moving_window);
+		e->slab = zb_slab_make(e->nx, window);
+		e->g = zdev_grid2d_create(e->slab.nxl, e->ny);
+		if (e->slab.on) zdev_grid2d_set_slab(e->g, e->slab.left, e->slab.right, e->slab.wrap_left, e->slab.wrap_right);
+	}
 	return e->g;
 }
 
@@ -95,7 +124,9 @@ zb_spec* zb_spec_of( const t_species* spec, int create ) {
 zdev_spec2d* zb_spec_dev( zb_spec* e ) {
 	if (!e->d) {
 		const t_species* spec = e->spec;
-		e->d = zdev_spec2d_create(spec->nx[0], spec->nx[1], spec->ppc[0] * spec->ppc[1], zb_opt_track_ids());
+		e->slab = zb_slab_make(spec->nx[0], spec->moving_window);
+		e->d = zdev_spec2d_create(e->slab.nxl, spec->nx[1], spec->ppc[0] * spec->ppc[1], e->slab.on ? 0 : zb_opt_track_ids());
+		if (e->slab.on) zdev_spec2d_set_slab(e->d, e->slab.left, e->slab.right, e->slab.x0, spec->nx[0]);
 	}
 	return e->d;
 }
@@ -116,12 +147,37 @@ static void zb_pin_emf( const t_emf* emf ) {
 	zdev_host_pin(emf->B_buf, bytes);
 }
 
+/* ---- slabs: the mirrors are global, the device grids are this rank's window of them ---- */
+
+static void grid_up( zb_grid* e, int which, const float3* host_buf, int nrow ) {
+	if (e->slab.on) zdev_grid2d_upload_window(zb_dev(e), which, (const float*) host_buf, nrow, e->slab.x0);
+	else zdev_grid2d_upload(zb_dev(e), which, (const float*) host_buf);
+}
+
+/* every rank's mirror ends up holding the whole box: own window from the device, the rest through the job's
+   shared scratch area (diagnostics path: reports, host-side field edits) */
+static void grid_down( zb_grid* e, int which, float3* host_buf, int nrow, int nrows ) {
+	if (!e->slab.on) { zdev_grid2d_download(zb_dev(e), which, (float*) host_buf); return; }
+	const zb_slab* g = &e->slab;
+	zdev_grid2d_download_window(zb_dev(e), which, (float*) host_buf, nrow, g->x0);
+	float3* all = zb_par_scratch((size_t) nrow * nrows * sizeof(float3));
+	/* buffer column c = cell c-1: the slab owns buffer columns [x0+1, x0+1+nxl); the box's own guard columns
+	   come from the first (column 0) and the last rank (the two upper ones) */
+	const int c0 = (g->rank == 0) ? 0 : g->x0 + 1;
+	const int c1 = g->is_last ? nrow : g->x0 + 1 + g->nxl;
+	for (int r = 0; r < nrows; r++)
+		memcpy(all + (size_t) r * nrow + c0, host_buf + (size_t) r * nrow + c0, (size_t) (c1 - c0) * sizeof(float3));
+	zb_par_barrier();
+	memcpy(host_buf, all, (size_t) nrow * nrows * sizeof(float3));
+	zb_par_barrier();
+}
+
 void zb_emf_to_device( t_emf* emf ) {
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	if (e->eb_dev_stale) {
 		zb_pin_emf(emf);
-		zdev_grid2d_upload(zb_dev(e), ZDEV_E, (const float*) emf->E_buf);
-		zdev_grid2d_upload(zb_dev(e), ZDEV_B, (const float*) emf->B_buf);
+		grid_up(e, ZDEV_E, emf->E_buf, emf->nrow);
+		grid_up(e, ZDEV_B, emf->B_buf, emf->nrow);
 		e->eb_dev_stale = 0;
 		e->eb_host_stale = 0;
 	}
@@ -130,17 +186,18 @@ void zb_emf_to_device( t_emf* emf ) {
 void zb_emf_to_host( const t_emf* emf ) {
 	zb_grid* e = zb_grid_of_emf(emf, 0);
 	if (!e) return;
+	const int nrows = emf->nx[1] + 3;
 	if (e->eb_host_stale) {
 		zb_pin_emf(emf);
-		zdev_grid2d_download(zb_dev(e), ZDEV_E, (float*) emf->E_buf);
-		zdev_grid2d_download(zb_dev(e), ZDEV_B, (float*) emf->B_buf);
+		grid_down(e, ZDEV_E, emf->E_buf, emf->nrow, nrows);
+		grid_down(e, ZDEV_B, emf->B_buf, emf->nrow, nrows);
 		e->eb_host_stale = 0;
 	}
 	if (e->part_host_stale) {
 		if (emf->ext_fld.E_type != EMF_FLD_TYPE_NONE && emf->ext_fld.E_part_buf)
-			zdev_grid2d_download(zb_dev(e), ZDEV_EPART, (float*) emf->ext_fld.E_part_buf);
+			grid_down(e, ZDEV_EPART, emf->ext_fld.E_part_buf, emf->nrow, nrows);
 		if (emf->ext_fld.B_type != EMF_FLD_TYPE_NONE && emf->ext_fld.B_part_buf)
-			zdev_grid2d_download(zb_dev(e), ZDEV_BPART, (float*) emf->ext_fld.B_part_buf);
+			grid_down(e, ZDEV_BPART, emf->ext_fld.B_part_buf, emf->nrow, nrows);
 		e->part_host_stale = 0;
 	}
 }
@@ -149,7 +206,7 @@ void zb_cur_to_host( const t_current* cur ) {
 	zb_grid* e = zb_grid_of_cur(cur, 0);
 	if (!e || !e->j_host_stale) return;
 	zdev_host_pin(cur->J_buf, (size_t) (cur->nx[0] + 3) * (cur->nx[1] + 3) * sizeof(float3));   /* unpinned by current_delete */
-	zdev_grid2d_download(zb_dev(e), ZDEV_J, (float*) cur->J_buf);
+	grid_down(e, ZDEV_J, cur->J_buf, cur->nrow, cur->nx[1] + 3);
 	e->j_host_stale = 0;
 }
 
@@ -165,7 +222,21 @@ void zb_spec_to_device( t_species* spec ) {
 	   mirror (the Python layer syncs first); take the host copy as the truth then */
 	if (!e->host_stale && (e->part_seen != spec->part || e->np_seen != spec->np)) e->dev_stale = 1;
 	if (e->dev_stale) {
-		zdev_spec2d_upload(zb_spec_dev(e), spec->part, spec->np);
+		zdev_spec2d* d = zb_spec_dev(e);
+		if (e->slab.on) {
+			/* the mirror holds the whole box on every rank: this rank takes the particles of its slab */
+			const int x0 = e->slab.x0, x1 = e->slab.x0 + e->slab.nxl;
+			int n = 0;
+			for (int i = 0; i < spec->np; i++) n += (spec->part[i].ix >= x0 && spec->part[i].ix < x1);
+			t_part* mine = malloc((size_t) (n > 0 ? n : 1) * sizeof(t_part));
+			n = 0;
+			for (int i = 0; i < spec->np; i++)
+				if (spec->part[i].ix >= x0 && spec->part[i].ix < x1) { mine[n] = spec->part[i]; mine[n].ix -= x0; n++; }
+			zdev_spec2d_upload(d, mine, n);
+			free(mine);
+		} else {
+			zdev_spec2d_upload(d, spec->part, spec->np);
+		}
 		e->dev_stale = 0; e->host_stale = 0;
 		e->part_seen = spec->part; e->np_seen = spec->np;
 	}
@@ -175,9 +246,31 @@ void zb_spec_to_host( const t_species* cspec ) {
 	t_species* spec = (t_species*) cspec;    /* the mirror is a cache of device state */
 	zb_spec* e = zb_spec_of(spec, 0);
 	if (!e || !e->host_stale) return;
-	int64_t np = zdev_spec2d_np(zb_spec_dev(e));
-	spec_grow_buffer(spec, (int) np);
-	spec->np = (int) zdev_spec2d_download(zb_spec_dev(e), spec->part, spec->np_max);
+	if (e->slab.on) {
+		/* every rank's mirror gets the whole population: own slab from the device (box coordinates), the
+		   others' through the shared scratch area, in rank order */
+		long long cnt[ZB_MAX_RANKS_LOCAL], mine = zdev_spec2d_np(zb_spec_dev(e));
+		zb_par_allgather(&mine, sizeof mine, cnt);
+		long long total = 0, off = 0;
+		for (int r = 0; r < e->slab.nranks; r++) { if (r < e->slab.rank) off += cnt[r]; total += cnt[r]; }
+		if (total > 0x7fffffffLL) {
+			fprintf(stderr, "(*error*) zpic-b200: %lld particles do not fit the int-sized host mirror of the reference API\n", total);
+			exit(-1);
+		}
+		t_part* all = zb_par_scratch((size_t) (total > 0 ? total : 1) * sizeof(t_part));
+		t_part* dst = all + off;
+		zdev_spec2d_download(zb_spec_dev(e), dst, mine);
+		for (long long i = 0; i < mine; i++) dst[i].ix += e->slab.x0;
+		zb_par_barrier();
+		spec_grow_buffer(spec, (int) total);
+		memcpy(spec->part, all, (size_t) total * sizeof(t_part));
+		spec->np = (int) total;
+		zb_par_barrier();
+	} else {
+		int64_t np = zdev_spec2d_np(zb_spec_dev(e));
+		spec_grow_buffer(spec, (int) np);
+		spec->np = (int) zdev_spec2d_download(zb_spec_dev(e), spec->part, spec->np_max);
+	}
 	e->host_stale = 0;
 	e->part_seen = spec->part; e->np_seen = spec->np;
 }

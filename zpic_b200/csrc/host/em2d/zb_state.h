@@ -11,6 +11,21 @@
 
 #include "zpic_dev.h"
 #include "simulation.h"
+#include "../common/zb_par.h"
+
+/* Slab decomposition along x (one process per GPU, zb_par.h).  The host objects of the API stay GLOBAL on every
+ * rank - same sizes, same mirrors, same random stream as a single-process run; the device twins are the rank's
+ * slab: columns [x0, x0 + nxl) with the reference's guard layout as halo.  Periodic boxes form a ring; under a
+ * moving window the slabs form an open chain whose two physical edges do nothing (em2d/emf.c:581, current.c:124). */
+typedef struct zb_slab {
+	int on;                    /* 0: single domain */
+	int rank, nranks;
+	int nxl, x0;               /* width and first column of this rank's slab */
+	int left, right;           /* neighbour ranks, -1: none */
+	int wrap_left, wrap_right; /* that edge is the periodic box boundary */
+	int is_last;
+} zb_slab;
+zb_slab zb_slab_make( int nx_global, int moving_window );
 
 /* E/B/J device grids shared by one t_emf and (after sim_new) one t_current */
 typedef struct zb_grid {
@@ -22,6 +37,7 @@ typedef struct zb_grid {
 	int eb_host_stale;         /* device advanced E/B after the last download */
 	int j_host_stale;          /* device J newer than host J_buf */
 	int part_host_stale;       /* device E_part/B_part newer than the host *_part_buf */
+	zb_slab slab;              /* fixed when the device object is created */
 } zb_grid;
 
 typedef struct zb_spec {
@@ -33,6 +49,7 @@ typedef struct zb_spec {
 	int host_stale;            /* device newer than host part[] */
 	const t_part* part_seen;   /* host buffer address / count at the last transfer: a change */
 	int np_seen;               /*   means host code touched the buffer (Species.add, realloc) */
+	zb_slab slab;              /* fixed when the device object is created */
 } zb_spec;
 
 zb_grid* zb_grid_of_emf( const t_emf* emf, int create );
