@@ -349,6 +349,142 @@ def run_ours(args):
     return out
 
 
+def _new_species(lib, A, n):
+    libc = C.CDLL(None)
+    libc.calloc.restype = C.c_void_p
+    libc.calloc.argtypes = [C.c_size_t, C.c_size_t]
+    return C.cast(libc.calloc(n, C.sizeof(A.Species)), C.POINTER(A.Species))
+
+
+def build_lwfa(lib, A, nx, ny):
+    """BASELINE configs[2]: the reference's em2d/input/lwfa-large.c geometry (dx = 0.01, 0.05) scaled to nx x ny cells,
+    4x4 particles per cell, plasma from x = 0.5 on (STEP), gaussian laser a0 = 3 launched 3 c/wp from the right edge,
+    moving window, compensated smoothing level 4 (input/lwfa.c:15-63 settings)"""
+    lib.set_rand_seed(12345, 67890)
+    cnx, box, dt = (C.c_int * 2)(nx, ny), (C.c_float * 2)(nx * 0.01, ny * 0.05), 0.009
+    species = _new_species(lib, A, 1)
+    dens = A.Density()
+    dens.type, dens.start = A.STEP, 0.5
+    lib.spec_new(C.byref(species[0]), b"electrons", -1.0, (C.c_int * 2)(4, 4), None, None, cnx, box, dt, C.byref(dens))
+    sim = A.Simulation()
+    lib.sim_new(C.byref(sim), cnx, box, dt, 1.0e9, 0, species, 1)
+    laser = A.Laser()
+    laser.type, laser.start, laser.fwhm, laser.a0, laser.omega0 = A.GAUSSIAN, box[0] - 3.0, 2.0, 3.0, 10.0
+    laser.W0, laser.focus, laser.axis, laser.polarization = 4.0, box[0] - 10.0, box[1] / 2, np.pi / 2
+    lib.sim_add_laser(C.byref(sim), C.byref(laser))
+    lib.sim_set_moving_window(C.byref(sim))
+    sm = A.Smooth(A.COMPENSATED, 0, 4, 0)
+    lib.sim_set_smooth(C.byref(sim), C.byref(sm))
+    return sim, species, 1, 16, dt, ()
+
+
+def build_kh(lib, A, n):
+    """BASELINE configs[3]: Kelvin-Helmholtz shear, n x n cells, two electron species that each fill one half of the box
+    in y through a CUSTOM density (0/1 step along y) and drift along +x / -x at 0.2 c, 8x4 particles per cell,
+    binomial smoothing level 1 along x and y, periodic"""
+    lib.set_rand_seed(12345, 67890)
+    cnx, box = (C.c_int * 2)(n, n), (C.c_float * 2)(n * CELL, n * CELL)
+    species = _new_species(lib, A, 2)
+    keep = []
+    for k, (name, lower, ux) in enumerate(((b"lower", True, 0.2), (b"upper", False, -0.2))):
+        fn = A.DENSITY_FN(lambda y, data, lower=lower, half=n * CELL / 2: 1.0 if ((y < half) == lower) else 0.0)
+        dens = A.Density()
+        dens.type, dens.custom_y = A.CUSTOM, fn
+        keep += [fn, dens]
+        lib.spec_new(C.byref(species[k]), name, -1.0, (C.c_int * 2)(8, 4), (C.c_float * 3)(ux, 0, 0), (C.c_float * 3)(0.01, 0.01, 0.01),
+                     cnx, box, DT, C.byref(dens))
+    sim = A.Simulation()
+    lib.sim_new(C.byref(sim), cnx, box, DT, 1.0e9, 0, species, 2)
+    sm = A.Smooth(A.BINOMIAL, A.BINOMIAL, 1, 1)
+    lib.sim_set_smooth(C.byref(sim), C.byref(sm))
+    return sim, species, 2, 32, DT, keep
+
+
+def run_deck(args):
+    """--workload lwfa | kh: BASELINE configs[2] / configs[3] through sim_new / sim_iter of the C API, slab-decomposed
+    over the ranks of the job (strong scaling: the box is the configuration's, whatever N), device-side
+    initialisation; one JSON line with the bench keys plus cell-updates/s.  Secondary lines: the driver's default
+    run is the Weibel configuration."""
+    from zpic_b200 import abi_em2d as A
+    from zpic_b200 import load
+    rank, world, local = (int(os.environ.get(k, "0" if k != "WORLD_SIZE" else "1")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        os.environ.setdefault("ZPIC_JOB", "bench" + os.environ.get("MASTER_PORT", "0"))
+    lib = load("em2d")
+    if lib.zdev_init(local) != 0:
+        raise SystemExit("bench.py: no CUDA device - the CUDA path is the only path")
+    lib.zpic_b200_set_option(b"device_init", 1)
+    lib.zpic_b200_set_option(b"lazy", 1)
+    K, W = args.steps, max(args.warmup, 3)
+    t0 = time.time()
+    if args.workload == "lwfa":
+        nx, ny = args.lwfa_nx, args.lwfa_ny
+        sim, species, nsp, ppc_total, dt, keep = build_lwfa(lib, A, nx, ny)
+        what = ("em2d LWFA %dx%d cells, 16 ppc, laser a0 3, moving window with host injection of the new column, "
+                "compensated smoothing level 4 (BASELINE configs[2])" % (nx, ny))
+    else:
+        nx = ny = args.kh_n
+        sim, species, nsp, ppc_total, dt, keep = build_kh(lib, A, nx)
+        what = ("em2d Kelvin-Helmholtz %dx%d cells, 2 species x 32 ppc (half box each), binomial smoothing x,y level 1, "
+                "periodic (BASELINE configs[3])" % (nx, ny))
+    for _ in range(W):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    t_init = time.time() - t0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.zdev_launch_count()
+    e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    lib.zdev_event_record(e0)
+    for _ in range(K):
+        lib.sim_iter(C.byref(sim))
+    lib.zdev_event_record(e1)
+    ms = lib.zdev_event_elapsed_ms(e0, e1)
+    lib.zdev_sync()
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.finish() if rank == 0 else None
+    launches = lib.zdev_launch_count() - launches0
+    # particles of the whole box after the run (collective: the count is summed over the slabs by the library)
+    lib.zpic_b200_set_option(b"lazy", 0)
+    lib.sim_iter(C.byref(sim))
+    npart = sum(int(species[k].np) for k in range(nsp))
+    if rank == 0:
+        peak, peak_src = peaks()
+        value = npart * K / (ms * 1e-3)
+        passes = 5 if args.workload == "lwfa" else 2
+        bytes_step = BYTES_PER_PUSH * npart + (BYTES_PER_CELL + 24.0 * passes) * nx * ny
+        gbs = bytes_step * K / (ms * 1e-3) / 1e9 / world
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": what, "particles": npart, "n_move": int(sim.emf.n_move), "dt": dt,
+                       "init": "device-side counter-based distribution; laser launch on the host (libm double precision)",
+                       "decomposition": "%d slabs along x, one process per GPU, through sim_new / sim_iter of the C API" % world,
+                       "init_and_warmup_s": round(t_init, 1)},
+            "cells": {"value": nx * ny * K / (ms * 1e-3), "unit": "cell-updates/s"},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "per GPU, algorithmic bytes of the whole step: 56 B per push + (72 + 24 per smoothing pass) B per cell"},
+            "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "cpu_baseline": None}))
+    lib.sim_delete(C.byref(sim))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_em1d(args, lib=None):
     """--workload em1d: BASELINE configs[4], the em1d two-stream deck scaled to 2^22 cells x 256 ppc x 2 beams
     (2^31 particles, 118 GB), driven through the device seam like scripts/quick_push_probe1d.py; one JSON line with
@@ -579,8 +715,12 @@ def main():
     ap.add_argument("--ppc", type=int, default=8, help="particles per cell per direction (8 -> 64 ppc)")
     ap.add_argument("--e2e-grid", type=int, default=1024, dest="e2e_n")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, dest="cpu_seconds")
-    ap.add_argument("--workload", default="em2d", choices=["em2d", "em1d"],
-                    help="em2d = BASELINE configs[1] (the default, what the driver runs); em1d = configs[4], one GPU")
+    ap.add_argument("--workload", default="em2d", choices=["em2d", "em1d", "lwfa", "kh"],
+                    help="em2d = BASELINE configs[1] (the default, what the driver runs); lwfa = configs[2], kh = configs[3] "
+                         "(slab-decomposed over the ranks of the job), em1d = configs[4] (one GPU)")
+    ap.add_argument("--lwfa-nx", type=int, default=16384, dest="lwfa_nx")
+    ap.add_argument("--lwfa-ny", type=int, default=1024, dest="lwfa_ny")
+    ap.add_argument("--kh-n", type=int, default=8192, dest="kh_n")
     ap.add_argument("--no-check", action="store_true", dest="no_check", help="N > 1: skip the slab-parity check")
     ap.add_argument("--log2-cells", type=int, default=22, dest="log2_cells", help="em1d: log2 of the cell count")
     ap.add_argument("--ppc1d", type=int, default=256, help="em1d: particles per cell per beam")
@@ -589,6 +729,8 @@ def main():
         run_reference(args)
     elif args.workload == "em1d":
         run_em1d(args)
+    elif args.workload in ("lwfa", "kh"):
+        run_deck(args)
     else:
         run_ours(args)
 

@@ -188,6 +188,13 @@ int64_t zdev_spec2d_np( zdev_spec2d* s );
  * throughput configurations whose host mirrors would not fit (hard part 5). */
 void zdev_spec2d_inject_uniform( zdev_spec2d* s, int ppcx, int ppcy,
                                  const float ufl[3], const float uth[3], uint64_t seed );
+/* the same in the cells [ix0, ix1) x [iy0, iy1) only (a plasma that starts at some x, a species that fills a band) */
+void zdev_spec2d_inject_rect( zdev_spec2d* s, int ppcx, int ppcy,
+                              const float ufl[3], const float uth[3], uint64_t seed, int ix0, int ix1, int iy0, int iy1 );
+/* the moving window's new column (cells ix, iy0 <= iy < iy1) generated the same way and appended on the device
+ * (species that were initialised on the device; the others take the host injector, em2d/particles.c:619-640) */
+void zdev_spec2d_inject_column( zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
+                                int ix, int iy0, int iy1, uint64_t column_number );
 /* the same in the rows iy0 <= iy < iy1 only (half-box species of a shear-flow deck) */
 void zdev_spec2d_inject_band( zdev_spec2d* s, int ppcx, int ppcy,
                               const float ufl[3], const float uth[3], uint64_t seed, int iy0, int iy1 );
@@ -222,6 +229,10 @@ void  zdev_spec2d_append_device( zdev_spec2d* s, const void* dev_part_aos, int64
  * of the push parameters are taken from the link.  gx0, gnx: the slab's first column in the whole box and the box
  * width (the device-side injector and the phasespace axis work in box coordinates). */
 void  zdev_spec2d_set_slab( zdev_spec2d* s, int left, int right, int gx0, int gnx );
+/* linked slabs: enqueue the (deferred) wait for the neighbours' particles + their append now; called at the end of a
+ * time step so that the transfer overlaps the current / field phase and the other species (anything that touches
+ * the species does it implicitly) */
+void  zdev_spec2d_flush_import( zdev_spec2d* s );
 /* the slab's own charge deposit: rho = (nx+1)*(ny+1) floats, overwritten, not folded */
 void  zdev_spec2d_deposit_charge_raw( zdev_spec2d* s, float q, float* rho );
 /* Device timing of the push kernel alone (k_push2d, not the migration pass): when enabled

@@ -22,7 +22,7 @@ def launch(name, cps, nranks, tmp_path, lazy=0, timeout=240):
     procs = []
     for r in range(nranks):
         env = dict(os.environ, ZPIC_RANK=str(r), ZPIC_NRANKS=str(nranks), ZPIC_JOB="t%d_%s" % (os.getpid(), name),
-                   ZPIC_TEST_LAZY=str(lazy), PYTHONPATH=REPO)
+                   ZPIC_TEST_LAZY=str(lazy), PYTHONPATH=REPO, ZPIC_DEVICE=str(r))      # one GPU each where the box has several
         env.pop("RANK", None)
         env.pop("WORLD_SIZE", None)
         procs.append(subprocess.Popen([sys.executable, os.path.join(REPO, "tests", "slab_worker.py"), name,

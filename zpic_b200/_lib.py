@@ -78,6 +78,7 @@ def _declare_dev(lib):
         "zdev_spec2d_np": (C.c_int64, [vp]),
         "zdev_spec2d_inject_uniform": (None, [vp, i, i, fp, fp, C.c_uint64]),
         "zdev_spec2d_inject_band": (None, [vp, i, i, fp, fp, C.c_uint64, i, i]),
+        "zdev_spec2d_inject_rect": (None, [vp, i, i, fp, fp, C.c_uint64, i, i, i, i]),
         "zdev_spec2d_advance": (None, [vp, vp, vp, C.POINTER(PushParams2D)]),
         "zdev_spec2d_fetch": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
         "zdev_spec2d_deposit_charge": (None, [vp, f, i, fp]),

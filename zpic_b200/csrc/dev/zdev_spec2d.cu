@@ -102,12 +102,18 @@ struct ctl2d {
 	unsigned int pad[2];
 };
 
+struct part_aos;
+// linked slabs (zdev_slab.cuh): where k_migrate2d announces its exports, and where k_slab_import finds the imports
+struct slab_pub { unsigned* ticket; unsigned* flag[2]; unsigned* count[2]; unsigned seq[2]; };
+struct slab_in { const unsigned* flag[2]; const unsigned* count[2]; const part_aos* rec[2]; unsigned seq[2]; };
+
 struct zdev_spec2d {
 	int nx, ny;
 	int TX, TY, ntx, nty, ntiles;
 	int ppc_hint, track_ids;
 	double slack;
-	int64_t cap_total;               // total SoA slots per buffer
+	int64_t cap_total;               // total SoA slots per buffer in use by the tile layout
+	int64_t alloc_total;             // slots allocated per buffer (headroom: tiles grow without reallocation)
 	int max_cap;                     // largest tile capacity (sizes perm[] in shared memory)
 	soa2d p, q;                      // current (A) and next (B) tile-binned buffers
 	int64_t* tile_off;               // device, ntiles+1
@@ -135,6 +141,10 @@ struct zdev_spec2d {
 	// neighbour's mailbox by k_migrate2d and appended there by k_slab_import
 	int slab; zdev_link link;
 	int gx0, gnx;                    // this slab's first column in the whole box, and the box width
+	// The import is DEFERRED: the message was sent by the step's k_migrate2d, but nothing in the rest of the step
+	// (current, fields, the other species) needs the arrivals, so the wait + append is enqueued at the end of the
+	// step (zdev_spec2d_flush_import, or whoever touches the species first): the transfer overlaps that work.
+	int import_pending; slab_in pending_in;
 	int ids_valid;                   // tags are a permutation of [0,np)
 	std::vector<int64_t>* h_off;     // host copy of tile_off
 	// optional device timing of the push kernel alone (bench roofline): ring of event pairs
@@ -252,7 +262,7 @@ static void mig_alloc(zdev_spec2d* s, int div) {
 	mig_free(s);
 	if (const char* e = getenv("ZPIC_MIG_DIV")) { const int v = atoi(e); if (v >= 1 && v < div) div = v; }
 	s->mig.div = div;
-	s->mig_cap = s->cap_total / div + 32;
+	s->mig_cap = s->alloc_total / div + 32;
 	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) s->mig_cap * sizeof(part_aos)));
 	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->mig.tag, (size_t) s->mig_cap * 4));
 	ZDEV_CHECK(cudaMalloc(&s->mig.np, (size_t) s->ntiles * sizeof(int)));
@@ -266,7 +276,7 @@ static void spec_free_particles(zdev_spec2d* s) {
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); }
 	mig_free(s);
 	cudaFree(s->ovf); cudaFree(s->ovf_tag); s->ovf = nullptr; s->ovf_tag = nullptr; s->ovf_cap = 0;
-	s->cap_total = 0;
+	s->cap_total = 0; s->alloc_total = 0;
 }
 
 extern "C" void zdev_spec2d_destroy(zdev_spec2d* s) {
@@ -335,8 +345,10 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	}
 	int64_t total = off[s->ntiles];
 	spec_free_particles(s);
-	soa_alloc(s->p, total, s->track_ids);
-	soa_alloc(s->q, total, s->track_ids);
+	// headroom for tiles that grow (a density spike): 1/8 of the layout, at most 64 M slots
+	s->alloc_total = (total + std::min<int64_t>(total / 8, (int64_t) 64 << 20) + 65536 + 31) & ~(int64_t) 31;
+	soa_alloc(s->p, s->alloc_total, s->track_ids);
+	soa_alloc(s->q, s->alloc_total, s->track_ids);
 	s->cap_total = total;
 	s->max_cap = (int) max_cap;
 	mig_alloc(s, 8);
@@ -392,7 +404,8 @@ static void spec_snapshot_ctl(zdev_spec2d* s) {
 	s->ctl_pending = 1;
 }
 // look at the last snapshot (waits for it if it is still in flight) and deal with full tiles
-static void spec_settle(zdev_spec2d* s) { if (s->ctl_pending) spec_resolve_overflow(s); }
+static void spec_flush_import(zdev_spec2d* s);
+static void spec_settle(zdev_spec2d* s) { spec_flush_import(s); if (s->ctl_pending) spec_resolve_overflow(s); }
 static void check_flags(zdev_spec2d* s, unsigned int flags) {
 	if (flags & 8u) {
 		fprintf(stderr, "(*error*) zpic-b200: more than %u particles found their tile full in one step (tile %dx%d cells); "
@@ -492,7 +505,6 @@ extern "C" void zdev_spec2d_upload(zdev_spec2d* s, const void* part, int64_t np)
 extern "C" void zdev_spec2d_append(zdev_spec2d* s, const void* part, int64_t np) {
 	if (np <= 0) return;
 	if (!s->cap_total) { zdev_spec2d_upload(s, part, np); return; }
-	spec_settle(s);
 	if (np > s->stage_cap) {
 		if (s->stage) { ZDEV_CHECK(cudaStreamSynchronize(zdev_strm)); cudaFree(s->stage); }
 		s->stage_cap = np + np / 2 + 1024;
@@ -650,8 +662,8 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		for (int t = 0; t < s->ntiles; t++) {
 			int64_t cap = off[t + 1] - off[t];
 			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			if (ovf_t[t] > 0 || need > cap - cap / 5) {          // full (double it), or above 80 %: it will be next
-				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 64;
+			if (ovf_t[t] > 0 || need > cap - cap / 4) {          // full (double it), or above 75 %: it will be next
+				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 256;
 				grown = (grown + 31) & ~(int64_t) 31;
 				if (grown > cap) cap = grown;
 			}
@@ -673,25 +685,35 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 			ZDEV_CHECK(cudaMalloc(&d_wait_tag, (size_t) n_ovf * 4));
 			ZDEV_CHECK(cudaMemcpyAsync(d_wait_tag, s->ovf_tag, (size_t) n_ovf * 4, cudaMemcpyDeviceToDevice, zdev_strm));
 		}
-		// population -> new layout (q is scratch between steps: release it first)
-		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		soa_free(s->q);
-		soa2d pn;
-		soa_alloc(pn, total, s->track_ids);
 		int64_t* d_off_new; ZDEV_CHECK(cudaMalloc(&d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
 		ZDEV_CHECK(cudaMemcpyAsync(d_off_new, off_new.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
-		ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, pn, d_off_new, s->tile_np);
-		ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
-		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(d_off_new);
-		soa_free(s->p);
-		s->p = pn;
-		soa_alloc(s->q, total, s->track_ids);
+		if (total <= s->alloc_total) {
+			// the new layout fits the allocation: population -> the other buffer (scratch between steps), swap
+			ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, s->q, d_off_new, s->tile_np);
+			ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
+			{ soa2d t = s->p; s->p = s->q; s->q = t; }
+			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+			cudaFree(d_off_new);
+		} else {
+			// population -> new, larger buffers (q is scratch between steps: release it first)
+			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+			soa_free(s->q);
+			s->alloc_total = (total + std::min<int64_t>(total / 8, (int64_t) 64 << 20) + 65536 + 31) & ~(int64_t) 31;
+			soa2d pn;
+			soa_alloc(pn, s->alloc_total, s->track_ids);
+			ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, pn, d_off_new, s->tile_np);
+			ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
+			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+			cudaFree(d_off_new);
+			soa_free(s->p);
+			s->p = pn;
+			soa_alloc(s->q, s->alloc_total, s->track_ids);
+			mig_alloc(s, s->mig.div);
+		}
 		*s->h_off = off_new;
 		s->cap_total = total;
 		s->max_cap = (int) max_cap;
 		spec_build_tile_lists(s);
-		mig_alloc(s, s->mig.div);
 		// clear the overflow state (energy, counts and export counters of the step stay) and append
 		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->n_ovf, 0, 2 * sizeof(unsigned int), zdev_strm));    // n_ovf, flags
 		spec_append_dev(s, d_wait, n_ovf, 0, d_wait_tag);
@@ -733,21 +755,23 @@ __device__ __forceinline__ void normal3(uint64_t seed, uint64_t gid, float& a, f
 }
 
 // one thread per cell: positions as spec_set_x's UNIFORM branch (particles.c:167-180,
-// 335-347), momenta as spec_set_u (thermal, minus the cell mean, plus fluid; :96-142)
+// 335-347), momenta as spec_set_u (thermal, minus the cell mean, plus fluid; :96-142).
+// Only the cells of the rectangle [ix0, ix1) x [iy0, iy1) get particles; a tile packs its part of it row by row
+// from its first slot.
 __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* tile_np,
                                  int nx, int ny, int TX, int TY, int ntx, int ppcx, int ppcy,
-                                 f3 ufl, f3 uth, uint64_t seed, int iy0, int iy1, int gx0, int gnx) {
+                                 f3 ufl, f3 uth, uint64_t seed, int ix0, int ix1, int iy0, int iy1, int gx0, int gnx) {
 	int64_t cell = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	if (cell >= (int64_t) nx * ny) return;
 	int iy = (int) (cell / nx), ix = (int) (cell - (int64_t) iy * nx);
-	if (iy < iy0 || iy >= iy1) return;                       // outside the band: no particles
+	if (iy < iy0 || iy >= iy1 || ix < ix0 || ix >= ix1) return;       // outside the rectangle: no particles
 	int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
 	int cx = (tx + 1) * TX <= nx ? TX : nx - tx * TX;
 	int lx = ix - tx * TX, ly = iy - ty * TY;
 	int npc = ppcx * ppcy;
-	// rows of the tile inside the band are packed from the tile's first slot
-	const int ly0 = max(iy0 - ty * TY, 0);
-	int64_t base = off[t] + (int64_t) (lx + (ly - ly0) * cx) * npc;
+	const int lx0 = max(ix0 - tx * TX, 0), ly0 = max(iy0 - ty * TY, 0);
+	const int w = min(tx * TX + cx, ix1) - max(tx * TX, ix0);          // cells of a tile row inside the rectangle
+	int64_t base = off[t] + (int64_t) ((lx - lx0) + (ly - ly0) * w) * npc;
 	uint64_t gid0 = ((uint64_t) (gx0 + ix) + (uint64_t) gnx * iy) * npc;     // numbered by cell of the WHOLE box
 	float sx = 0, sy = 0, sz = 0;
 	for (int k = 0; k < npc; k++) {
@@ -766,46 +790,111 @@ __global__ void k_inject_uniform(soa2d p, const int64_t* __restrict__ off, int* 
 		p.key[d] = (unsigned short) (lx + ly * TX);
 		if (p.tag) p.tag[d] = (int) (gid0 + k);
 	}
-	if (lx == 0 && ly == ly0) {
+	if (lx == lx0 && ly == ly0) {
 		int cy = (ty + 1) * TY <= ny ? TY : ny - ty * TY;
 		const int rows = min(ty * TY + cy, iy1) - max(ty * TY, iy0);
-		tile_np[t] = cx * rows * npc;
+		tile_np[t] = w * rows * npc;
 	}
 }
 
-// uniform plasma in the rows iy0 <= iy < iy1 only (e.g. the two half-box species of a shear-flow deck); tiles
-// outside the band get the minimum capacity (they grow on demand when particles arrive)
-extern "C" void zdev_spec2d_inject_band(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
-                                        int iy0, int iy1) {
+// uniform plasma in the cells [ix0, ix1) x [iy0, iy1) only (the half-box species of a shear-flow deck, a plasma
+// that starts at some x); tiles outside get the minimum capacity (they grow on demand when particles arrive)
+extern "C" void zdev_spec2d_inject_rect(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
+                                        int ix0, int ix1, int iy0, int iy1) {
 	int npc = ppcx * ppcy;
-	if (iy0 < 0) iy0 = 0;
-	if (iy1 > s->ny) iy1 = s->ny;
+	ix0 = std::max(ix0, 0); iy0 = std::max(iy0, 0);
+	ix1 = std::min(ix1, s->nx); iy1 = std::min(iy1, s->ny);
 	std::vector<int> cnt(s->ntiles);
 	int64_t np = 0;
 	for (int ty = 0; ty < s->nty; ty++) for (int tx = 0; tx < s->ntx; tx++) {
 		int cx = (tx + 1) * s->TX <= s->nx ? s->TX : s->nx - tx * s->TX;
 		int cy = (ty + 1) * s->TY <= s->ny ? s->TY : s->ny - ty * s->TY;
 		int rows = std::min(ty * s->TY + cy, iy1) - std::max(ty * s->TY, iy0);
+		int cols = std::min(tx * s->TX + cx, ix1) - std::max(tx * s->TX, ix0);
 		if (rows < 0) rows = 0;
-		cnt[tx + ty * s->ntx] = cx * rows * npc; np += (int64_t) cx * rows * npc;
+		if (cols < 0) cols = 0;
+		cnt[tx + ty * s->ntx] = cols * rows * npc; np += (int64_t) cols * rows * npc;
 	}
-	const bool band = iy0 > 0 || iy1 < s->ny;
+	// a species that fills only part of the box (a half-box beam) gets its capacity where it is, not the nominal
+	// fill everywhere; one that merely starts a little inside the box keeps the nominal layout (under a moving
+	// window the empty tiles fill up within a few steps, and growing tiles step after step is expensive)
+	const bool partial = (double) np < 0.9 * (double) s->nx * s->ny * npc;
 	const int hint = s->ppc_hint;
-	if (band) s->ppc_hint = 0;                  // capacities from the actual populations, not the nominal fill
+	if (partial) s->ppc_hint = 0;               // capacities from the actual populations, not the nominal fill
 	spec_layout(s, cnt, np);
 	s->ppc_hint = hint;
-	if (band) spec_build_tile_lists(s);
+	if (partial) spec_build_tile_lists(s);
 	f3 fl = {ufl[0], ufl[1], ufl[2]}, th = {uth[0], uth[1], uth[2]};
 	int64_t ncell = (int64_t) s->nx * s->ny;
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
-	ZDEV_LAUNCH(k_inject_uniform, zdev_div_up(ncell, 128), 128, 0, s->p, s->tile_off, s->tile_np,
-	            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed, iy0, iy1, s->gx0, s->gnx);
+	if (np > 0)
+		ZDEV_LAUNCH(k_inject_uniform, zdev_div_up(ncell, 128), 128, 0, s->p, s->tile_off, s->tile_np,
+		            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, th, seed, ix0, ix1, iy0, iy1, s->gx0, s->gnx);
 	s->np_host = np; s->np_known = 1;
 	s->ids_valid = s->track_ids && np < 0x7fffffff;
 }
 
+extern "C" void zdev_spec2d_inject_band(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
+                                        int iy0, int iy1) {
+	zdev_spec2d_inject_rect(s, ppcx, ppcy, ufl, uth, seed, 0, s->nx, iy0, iy1);
+}
+
 extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed) {
-	zdev_spec2d_inject_band(s, ppcx, ppcy, ufl, uth, seed, 0, s->ny);
+	zdev_spec2d_inject_rect(s, ppcx, ppcy, ufl, uth, seed, 0, s->nx, 0, s->ny);
+}
+
+// The moving window's new column (cells ix, iy0 <= iy < iy1) generated on the device like k_inject_uniform does and
+// appended to its tiles: one thread per cell reserves the cell's slots with one atomic.  `col` numbers the column
+// (cells that ever entered the box get distinct particle numbers).
+__global__ void k_inject_column(soa2d p, const int64_t* __restrict__ off, int* tile_np, ctl2d* ctl, int TX, int TY, int ntx,
+                                int ppcx, int ppcy, f3 ufl, f3 uth, uint64_t seed, int ix, int iy0, int iy1, uint64_t col,
+                                part_aos* ovf, int* ovf_tag, unsigned int ovf_cap) {
+	const int iy = iy0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (iy >= iy1) return;
+	const int npc = ppcx * ppcy;
+	const uint64_t gid0 = (col * 0x100000ull + (uint64_t) iy) * npc + 0x4000000000000000ull;
+	float sx = 0, sy = 0, sz = 0;
+	for (int k = 0; k < npc; k++) {
+		float a, b, c; normal3(seed, gid0 + k, a, b, c);
+		sx += uth.x * a; sy += uth.y * b; sz += uth.z * c;
+	}
+	const float norm = 1.0f / npc;
+	sx *= norm; sy *= norm; sz *= norm;
+	const int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
+	const int lx = ix - tx * TX, ly = iy - ty * TY;
+	const int slot0 = atomicAdd(&tile_np[t], npc);
+	const float dpcx = 1.0f / ppcx, dpcy = 1.0f / ppcy;
+	const int64_t room = off[t + 1] - off[t];
+	int parked = 0;
+	for (int k = 0; k < npc; k++) {
+		float a, b, c; normal3(seed, gid0 + k, a, b, c);
+		const int kx = k % ppcx, ky = k / ppcx;
+		const float x = (float) (dpcx * (kx + 0.5)), y = (float) (dpcy * (ky + 0.5));
+		const float ux = uth.x * a + (ufl.x - sx), uy = uth.y * b + (ufl.y - sy), uz = uth.z * c + (ufl.z - sz);
+		if (slot0 + k < room) {
+			const int64_t d = off[t] + slot0 + k;
+			rec_store(p.rec, d, x, y, ux, uy, uz);
+			p.key[d] = (unsigned short) (lx + ly * TX);
+			if (p.tag) p.tag[d] = 0;
+		} else {
+			part_aos r; r.ix = ix; r.iy = iy; r.x = x; r.y = y; r.ux = ux; r.uy = uy; r.uz = uz;
+			ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, 0);
+			parked++;
+		}
+	}
+	if (parked) atomicSub(&tile_np[t], parked);      // (the tile is full: nobody else got a slot behind ours)
+}
+
+extern "C" void zdev_spec2d_inject_column(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3], uint64_t seed,
+                                          int ix, int iy0, int iy1, uint64_t column_number) {
+	if (!s->cap_total || iy1 <= iy0) return;
+	f3 fl = {ufl[0], ufl[1], ufl[2]}, th = {uth[0], uth[1], uth[2]};
+	ZDEV_LAUNCH(k_inject_column, zdev_div_up(iy1 - iy0, 128), 128, 0, s->p, s->tile_off, s->tile_np, s->ctl, s->TX, s->TY, s->ntx,
+	            ppcx, ppcy, fl, th, seed, ix, iy0, iy1, column_number, s->ovf, s->ovf_tag, s->ovf_cap);
+	s->appended = 1;
+	s->np_host += (int64_t) (iy1 - iy0) * ppcx * ppcy;
+	s->ids_valid = 0;
+	spec_snapshot_ctl(s);
 }
 
 // ------------------------------------------------------------------ the push
@@ -1303,10 +1392,6 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	}
 }
 
-// linked slabs (zdev_slab.cuh): where k_migrate2d announces its exports, and where k_slab_import finds the imports
-struct slab_pub { unsigned* ticket; unsigned* flag[2]; unsigned* count[2]; unsigned seq[2]; };
-struct slab_in { const unsigned* flag[2]; const unsigned* count[2]; const part_aos* rec[2]; unsigned seq[2]; };
-
 // Boundary conditions for the particles that left their tile (reference particles.c:1237-1259: periodic y
 // always; x periodic, absorbing under a moving window, or handed to the neighbour slab), then append them
 // to their destination tiles.  One warp per tile segment.
@@ -1486,12 +1571,19 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 	ZDEV_LAUNCH(k_migrate2d, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
 	            s->TX, s->TY, s->ntx, s->ntiles, s->nx, s->ny, prm->moving_window, prm->slab_left, prm->slab_right,
 	            exp_l, exp_r, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap, pub);
-	if (s->slab)
-		ZDEV_LAUNCH(k_slab_import, dim3(2 * zdev_num_sm, 2), 256, 0, s->p, s->tile_off, s->tile_np, s->ctl, s->TX, s->TY, s->ntx,
-		            in, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap);
-	spec_snapshot_ctl(s);
+	if (s->slab) { s->pending_in = in; s->import_pending = 1; }      // the snapshot follows the import
+	else spec_snapshot_ctl(s);
 	if (prm->moving_window || prm->slab_left || prm->slab_right) s->ids_valid = 0;
 }
+
+static void spec_flush_import(zdev_spec2d* s) {
+	if (!s->import_pending) return;
+	s->import_pending = 0;
+	ZDEV_LAUNCH(k_slab_import, dim3(2 * zdev_num_sm, 2), 256, 0, s->p, s->tile_off, s->tile_np, s->ctl, s->TX, s->TY, s->ntx,
+	            s->pending_in, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap);
+	spec_snapshot_ctl(s);
+}
+extern "C" void zdev_spec2d_flush_import(zdev_spec2d* s) { spec_flush_import(s); }
 
 extern "C" void zdev_spec2d_fetch(zdev_spec2d* s, double* energy_sum, int64_t* np) {
 	// the overflow check at the end of the advance has already brought the step's control block to the host;

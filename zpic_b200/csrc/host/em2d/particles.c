@@ -237,6 +237,41 @@ void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int*
 	draw_momenta(spec, *buf, first, *np - 1);
 }
 
+/* the cells [ix0, ix1) x [iy0, iy1) a density profile fills completely, if it is of that kind (device-side
+   initialisation only handles those): whole cells, decided at the cell centre */
+static int device_init_rect( const t_species* spec, int rect[4] )
+{
+	const t_density* d = &spec->density;
+	const int nx = spec->nx[0], ny = spec->nx[1];
+	rect[0] = 0; rect[1] = nx; rect[2] = 0; rect[3] = ny;
+	switch (d->type) {
+	case UNIFORM: return 1;
+	case STEP:
+	case SLAB: {
+		int i0 = 0, i1 = nx;
+		while (i0 < nx && (i0 + 0.5f) * spec->dx[0] < d->start) i0++;
+		if (d->type == SLAB) { i1 = i0; while (i1 < nx && (i1 + 0.5f) * spec->dx[0] < d->end) i1++; }
+		rect[0] = i0; rect[1] = i1;
+		return 1;
+	}
+	case CUSTOM: {
+		if (d->custom_x && d->custom_x != &density_one) return 0;
+		if (!d->custom_y) return 1;
+		int j0 = -1, j1 = -1;
+		for (int j = 0; j < ny; j++) {
+			const float v = d->custom_y((j + 0.5f) * spec->dx[1], d->custom_data_y);
+			if (v != 0.0f && v != 1.0f) return 0;              /* a real profile: the host injector */
+			if (v == 1.0f) { if (j0 < 0) j0 = j; else if (j1 >= 0) return 0; }     /* a second band */
+			else if (j0 >= 0 && j1 < 0) j1 = j;
+		}
+		if (j0 < 0) { rect[2] = rect[3] = 0; return 1; }
+		rect[2] = j0; rect[3] = (j1 < 0) ? ny : j1;
+		return 1;
+	}
+	default: return 0;
+	}
+}
+
 void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
                const float *ufl, const float *uth,
                const int nx[], float box[], const float dt, t_density* density )
@@ -284,14 +319,18 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
 
 	spec->np = 0;
 	const int range[][2] = { {0, nx[0]-1}, {0, nx[1]-1} };
-	if (zb_opt_device_init() && spec->density.type == UNIFORM) {
-		/* opt-in for populations too large for a host mirror: same distribution, generated by a
-		   counter-based generator on the device at the first step (one draw of the host stream
-		   seeds it, so runs stay reproducible and species differ) */
+	int rect[4];
+	if (zb_opt_device_init() && device_init_rect(spec, rect)) {
+		/* opt-in for populations too large for a host mirror: the plasma fills a rectangle of cells at the nominal
+		   particles per cell (whole box; from a STEP / inside a SLAB along x; the band a 0/1 CUSTOM profile along
+		   y selects), generated by a counter-based generator on the device at the first step (one draw of the
+		   host stream seeds it, so runs stay reproducible and species differ) - same distribution as
+		   spec_set_x / spec_set_u, not the reference random stream */
 		zb_spec* e = zb_spec_of(spec, 1);
 		e->device_init = 1;
 		e->device_seed = ((uint64_t) rand_uint32() << 32) | rand_uint32();
-		long long total = (long long) nx[0] * nx[1] * npc;
+		memcpy(e->dev_rect, rect, sizeof rect);
+		long long total = (long long) (rect[1] - rect[0]) * (rect[3] - rect[2]) * npc;
 		spec->np = (total > 0x7fffffffLL) ? 0x7fffffff : (int) total;
 	} else {
 		spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
@@ -360,16 +399,29 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		/* new plasma enters through the right edge: host injector (global random stream),
 		   then the column is appended to the device tiles */
 		spec->n_move++;
-		const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
-		t_part* col = NULL; int ncol = 0, ncol_max = 0;
-		spec_inject_into(spec, range, &col, &ncol, &ncol_max);
-		if (!s->slab.on) zdev_spec2d_append(zb_spec_dev(s), col, ncol);
-		else if (s->slab.is_last) {
-			/* every rank runs the injector (the global random stream stays in step); the column belongs to the last slab */
-			for (int i = 0; i < ncol; i++) col[i].ix -= s->slab.x0;
-			zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+		if (s->device_made) {
+			/* a species that was generated on the device: so is its new column, wherever the profile (whole cells,
+			   decided at the cell centre like the initial fill) has plasma at the window's right edge */
+			const float xc = (spec->n_move + spec->nx[0] - 1 + 0.5f) * spec->dx[0];
+			const t_density* d = &spec->density;
+			const int in = (d->type == UNIFORM || d->type == CUSTOM) || (d->type == STEP && xc >= d->start) ||
+			               (d->type == SLAB && xc >= d->start && xc < d->end);
+			if (in && (!s->slab.on || s->slab.is_last))
+				zdev_spec2d_inject_column(zb_spec_dev(s), spec->ppc[0], spec->ppc[1], spec->ufl, spec->uth, s->device_seed,
+				                          s->slab.nxl - 1, s->dev_rect[2], s->dev_rect[3],
+				                          (uint64_t) (spec->n_move + spec->nx[0] - 1));
+		} else {
+			const int range[][2] = { {spec->nx[0]-1, spec->nx[0]-1}, {0, spec->nx[1]-1} };
+			t_part* col = NULL; int ncol = 0, ncol_max = 0;
+			spec_inject_into(spec, range, &col, &ncol, &ncol_max);
+			if (!s->slab.on) zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+			else if (s->slab.is_last) {
+				/* every rank runs the injector (the global random stream stays in step); the column belongs to the last slab */
+				for (int i = 0; i < ncol; i++) col[i].ix -= s->slab.x0;
+				zdev_spec2d_append(zb_spec_dev(s), col, ncol);
+			}
+			free(col);
 		}
-		free(col);
 	}
 
 	if (!zb_opt_lazy()) {

@@ -21,6 +21,12 @@ void sim_iter( t_simulation* sim )
 		spec_advance( &sim->species[i], &sim->emf, &sim->current );
 	current_update( &sim->current );
 	emf_advance( &sim->emf, &sim->current );
+	/* slabs: the particles the neighbour slabs sent during spec_advance are waited for and appended only now -
+	   their transfer ran behind the other species' push and the current / field phase */
+	for (int i = 0; i < sim->n_species; i++) {
+		zb_spec* e = zb_spec_of(&sim->species[i], 0);
+		if (e && e->d && e->slab.on) zdev_spec2d_flush_import(e->d);
+	}
 
 	if (zb_opt_coherent()) zpic_b200_sync_host(sim);     /* and refresh every mirror */
 }

@@ -214,8 +214,10 @@ void zb_spec_to_device( t_species* spec ) {
 	zb_spec* e = zb_spec_of(spec, 1);
 	if (e->device_init) {
 		/* throughput configurations: the population never existed on the host */
-		zdev_spec2d_inject_uniform(zb_spec_dev(e), spec->ppc[0], spec->ppc[1], spec->ufl, spec->uth, e->device_seed);
-		e->device_init = 0; e->dev_stale = 0; e->host_stale = 1;
+		zdev_spec2d* d = zb_spec_dev(e);
+		zdev_spec2d_inject_rect(d, spec->ppc[0], spec->ppc[1], spec->ufl, spec->uth, e->device_seed,
+		                        e->dev_rect[0] - e->slab.x0, e->dev_rect[1] - e->slab.x0, e->dev_rect[2], e->dev_rect[3]);
+		e->device_init = 0; e->device_made = 1; e->dev_stale = 0; e->host_stale = 1;
 		return;
 	}
 	/* host code that appended particles or reallocated the buffer did so on a current

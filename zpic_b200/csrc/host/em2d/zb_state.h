@@ -44,7 +44,9 @@ typedef struct zb_spec {
 	const t_species* spec;
 	zdev_spec2d* d;            /* NULL until first device use: see zb_spec_dev() */
 	int device_init;           /* population is generated on the device at first use (no host mirror yet) */
+	int device_made;           /* ... and was: the moving window's new columns are generated on the device too */
 	uint64_t device_seed;
+	int dev_rect[4];           /*   ... in the cells [0,1) x [2,3) of the box */
 	int dev_stale;             /* host part[] newer than the device copy (or never uploaded) */
 	int host_stale;            /* device newer than host part[] */
 	const t_part* part_seen;   /* host buffer address / count at the last transfer: a change */
