@@ -323,7 +323,11 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	double slack = s->slack;
 	// perm[] costs 4 bytes of shared memory per slot of capacity: tiles whose nominal fill is large keep 25 % of
 	// room (two push CTAs + 92 KB of L1 per SM), small ones 100 %; full tiles grow on demand either way
-	if (slack <= 0.0) slack = ((int64_t) s->TX * s->TY * s->ppc_hint > 4500 || np > (int64_t) 200000000) ? 1.25 : 2.0;
+	if (slack <= 0.0) {
+		int64_t fill = (int64_t) s->TX * s->TY * s->ppc_hint;
+		for (int t = 0; t < s->ntiles; t++) if (cnt[t] > fill) fill = cnt[t];
+		slack = (fill > 4500 || np > (int64_t) 200000000) ? 1.25 : 2.0;
+	}
 	std::vector<int64_t>& off = *s->h_off;
 	off.assign(s->ntiles + 1, 0);
 	int64_t max_cap = 0;
