@@ -556,22 +556,15 @@ def run_em1d(args, lib=None):
     return out
 
 
-def run_e2e(lib, A, args, n_full):
-    """The metric through the public C API as a caller uses it (reference em2d/main.c:53-59 and the
-    Weibel deck's sim_report, input/weibel.c:44-57): the species are created on the HOST by spec_new
-    (reference random stream), uploaded once, then every timed step is sim_iter + the energy
-    diagnostics (host scalars in; per-species energy / particle count and the six field energies
-    out), and every `ndump`=10 steps the deck's report set is brought back to host buffers (B, J,
-    the two charge densities).  Bounded to a grid whose host-side injection takes seconds.
-
-    `coherent` is the same loop with NO state kept on the device: every sim_iter uploads all
-    particles + E,B from the host mirrors and downloads particles + E,B,J again."""
-    n = min(n_full, args.e2e_n)
+def _e2e_leg(lib, A, args, n, device_init, steps):
+    """sim_iter + per-step diagnostics + the deck's report set every 10 steps, wall clock, host buffers"""
     ppc = (args.ppc, args.ppc)
-    lib.zpic_b200_set_option(b"device_init", 0)
+    lib.zpic_b200_set_option(b"device_init", int(device_init))
     lib.zpic_b200_set_option(b"lazy", 0)
     lib.zpic_b200_set_option(b"coherent", 0)
+    t0 = time.perf_counter()
     sim, species, _ = build_weibel(lib, A, n, n, ppc)
+    t_build = time.perf_counter() - t0
     np_total = 2 * n * n * args.ppc * args.ppc
     grid_b = (n + 3) * (n + 3) * 12
     rho = [np.zeros((n + 1, n + 1), dtype=np.float32) for _ in range(2)]
@@ -580,26 +573,60 @@ def run_e2e(lib, A, args, n_full):
     def one_step(k):
         lib.sim_iter(C.byref(sim))
         lib.emf_get_energy(C.byref(sim.emf), en6)
-        if (k + 1) % 10 == 0:                      # the deck's report cadence
+        if (k + 1) % 10 == 0:                      # the deck's report cadence (input/weibel.c:44-57, ndump = 10)
             lib.zpic_b200_sync_emf(C.byref(sim.emf))
             lib.zpic_b200_sync_current(C.byref(sim.current))
             for s in range(2):
                 rho[s][...] = 0
                 lib.spec_deposit_charge(C.byref(species[s]), rho[s].ctypes.data_as(C.POINTER(C.c_float)))
 
-    for k in range(7, 10):                         # warm-up: three steps, the last one with the report set
+    t0 = time.perf_counter()
+    one_step(7)                                    # first step: the one-off upload (host-initialised) / generation
+    lib.zdev_sync()
+    t_first = time.perf_counter() - t0
+    for k in range(8, 10):                         # warm-up, the last one with the report set
         one_step(k)                                # (first use page-locks the E, B, J mirrors)
     lib.zdev_sync()
-    steps = max(args.steps, 10)
     t0 = time.perf_counter()
     for k in range(steps):
         one_step(k)
     lib.zdev_sync()
     dt_res = time.perf_counter() - t0
     reports = steps // 10
-    h2d_res = 2 * 32 + reports * 2 * (n + 1) * (n + 1) * 4 / steps
-    d2h_res = 2 * 24 + 48 + reports * (3 * grid_b + 2 * (n + 1) * (n + 1) * 4) / steps
+    leg = {"value": np_total * steps / dt_res, "unit": UNIT,
+           "h2d_bytes_per_step": int(2 * 32 + reports * 2 * (n + 1) * (n + 1) * 4 / steps),
+           "d2h_bytes_per_step": int(2 * 48 + 48 + reports * (3 * grid_b + 2 * (n + 1) * (n + 1) * 4) / steps),
+           "workload": "em2d Weibel %dx%d, 2 x %d ppc" % (n, n, args.ppc ** 2), "steps": steps, "wall_clock": True,
+           "ms_per_step": dt_res / steps * 1e3,
+           "one_off": {"spec_new_sim_new_s": round(t_build, 3), "first_step_s": round(t_first, 3),
+                       "upload_bytes": 0 if device_init else np_total * 28 + 2 * grid_b,
+                       "note": "not in `value`: building the deck, and the first sim_iter with the one-off "
+                               + ("generation of the particles on the device" if device_init else "upload of the host-initialised particles and fields")}}
+    return leg, sim, species
 
+
+def run_e2e(lib, A, args, n_full):
+    """The metric through the public C API as a caller uses it (reference em2d/main.c:53-59 and the Weibel deck's
+    sim_report, input/weibel.c:44-57) on the HEADLINE configuration: sim_new, then every timed step is sim_iter
+    followed by the energy diagnostics read back to the host (per-species kinetic energy and particle count, the six
+    field energies; this synchronises every step), and every `ndump` = 10 steps the deck's report set arrives in
+    host buffers (E, B, J mirrors and the two charge densities).  Wall clock around the loop.
+    `host_initialised`: the same loop with the species created on the HOST by spec_new (the reference random
+    stream) and uploaded once, at the largest size whose host initialisation takes seconds.
+    `coherent`: NO state kept on the device - every sim_iter uploads all particles + E, B from the host mirrors and
+    downloads particles + E, B, J again."""
+    steps = max(args.steps, 10)
+    main, sim, species = _e2e_leg(lib, A, args, n_full, True, steps)
+    lib.sim_delete(C.byref(sim))
+    main["mode"] = ("public C API on BASELINE configs[1] (device-side initialisation): every step sim_iter + energy "
+                    "diagnostics read back (a stream synchronisation per step); every 10 steps the deck's report set "
+                    "(E, B, J, 2 charge grids) synchronised to host buffers")
+    n = min(n_full, args.e2e_n)
+    host, sim, species = _e2e_leg(lib, A, args, n, False, steps)
+    host["mode"] = "the same loop, species created on the host by spec_new (reference random stream) and uploaded once"
+    main["host_initialised"] = host
+    np_total = 2 * n * n * args.ppc * args.ppc
+    grid_b = (n + 3) * (n + 3) * 12
     # strict host-buffer round trip
     lib.zpic_b200_set_option(b"coherent", 1)
     lib.sim_iter(C.byref(sim))
@@ -612,17 +639,12 @@ def run_e2e(lib, A, args, n_full):
     dt_coh = time.perf_counter() - t0
     lib.zpic_b200_set_option(b"coherent", 0)
     lib.sim_delete(C.byref(sim))
-    return {"value": np_total * steps / dt_res, "unit": UNIT,
-            "h2d_bytes_per_step": int(h2d_res), "d2h_bytes_per_step": int(d2h_res),
-            "mode": "public C API (spec_new on the host with the reference random stream, sim_new, sim_iter); state "
-                    "uploaded once and kept in HBM; every step: sim_iter + energy diagnostics read back; every 10 "
-                    "steps the deck's report set (B, J, 2 charge grids) synchronised to host buffers",
-            "workload": "em2d Weibel %dx%d, 2 x %d ppc (largest size whose HOST initialisation takes seconds)" % (n, n, args.ppc ** 2),
-            "steps": steps, "wall_clock": True,
-            "coherent": {"value": np_total * csteps / dt_coh, "unit": UNIT, "steps": csteps,
-                         "h2d_bytes_per_step": np_total * 28 + 2 * grid_b, "d2h_bytes_per_step": np_total * 28 + 3 * grid_b,
-                         "note": "ZPIC_COHERENT=1: no state kept on the device between calls - every sim_iter uploads all "
-                                 "particles + E,B from pageable host buffers and downloads particles + E,B,J"}}
+    main["coherent"] = {"value": np_total * csteps / dt_coh, "unit": UNIT, "steps": csteps,
+                        "workload": host["workload"],
+                        "h2d_bytes_per_step": np_total * 28 + 2 * grid_b, "d2h_bytes_per_step": np_total * 28 + 3 * grid_b,
+                        "note": "ZPIC_COHERENT=1: no state kept on the device between calls - every sim_iter uploads all "
+                                "particles + E,B from pageable host buffers and downloads particles + E,B,J"}
+    return main
 
 
 # ------------------------------------------------------------------------------------------

@@ -33,6 +33,16 @@ void zpic_b200_touch_emf( struct EMF* emf );
  * every step).  Also settable through ZPIC_LAZY / ZPIC_TRACK_IDS / ZPIC_COHERENT. */
 void zpic_b200_set_option( const char* name, int value );
 
+/* A custom-field callback (t_emf_ext_fld / t_emf_init_fld: E_custom, B_custom with *_custom_data) for callers that
+ * cannot hand over a C function - Python through ctypes cannot return a struct from a callback: `data` points at a
+ * zpic_b200_field_table whose values the caller computed for every cell of the buffer, guards included
+ * (value of cell (ix, iy) at table[3 * ((ix + 1) + (iy + 1) * nrow)], nrow = nx + 3; the em1d library exports the same
+ * name with the em1d callback signature (int ix, float dx, void* data), value of cell ix at table[3 * (ix + 1)]). */
+typedef struct zpic_b200_field_table { int nrow; const float* table; } zpic_b200_field_table;
+#ifdef ZPIC_B200_WITH_FLOAT3          /* (declared where the reference's float3 is known: include/em2d/zpic.h) */
+float3 zpic_b200_table_field( int ix, float dx, int iy, float dy, void* data );
+#endif
+
 /* opaque device handles (zdev_spec2d* / zdev_grid2d* of include/zpic_dev.h) behind a host object */
 void* zpic_b200_species_handle( struct Species* spec );
 void* zpic_b200_grid_handle( struct EMF* emf );

@@ -25,12 +25,23 @@ sys.path.insert(0, REPO)
 from zpic_b200 import zdf  # noqa: E402
 
 
-def run(exe, where):
+def run(exe, where, nranks=1):
+    """nranks > 1: the SAME program started once per slab (ZPIC_RANK / ZPIC_NRANKS / ZPIC_DEVICE), all in one directory;
+    the library decomposes the box, rank 0 writes the files"""
     t0 = time.time()
-    r = subprocess.run([exe], cwd=where, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise SystemExit("%s failed (%d):\n%s" % (exe, r.returncode, r.stdout[-2000:]))
-    return time.time() - t0, r.stdout
+    if nranks <= 1:
+        r = subprocess.run([exe], cwd=where, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise SystemExit("%s failed (%d):\n%s" % (exe, r.returncode, r.stdout[-2000:]))
+        return time.time() - t0, r.stdout
+    procs = []
+    for k in range(nranks):
+        env = dict(os.environ, ZPIC_RANK=str(k), ZPIC_NRANKS=str(nranks), ZPIC_DEVICE=str(k), ZPIC_JOB="deck%d" % os.getpid())
+        procs.append(subprocess.Popen([exe], cwd=where, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate()[0] for p in procs]
+    if any(p.returncode != 0 for p in procs):
+        raise SystemExit("%s x %d failed:\n%s" % (exe, nranks, "\n".join(o[-1500:] for o in outs)))
+    return time.time() - t0, outs[0]
 
 
 def files(root):
@@ -42,11 +53,11 @@ def files(root):
     return out
 
 
-def distances(exe_a, exe_b, upto):
+def distances(exe_a, exe_b, upto, nranks=1):
     """run two builds of the program and compare every ZDF file of iterations <= upto.
     Returns (at_upto, worst, worst_component, n_files, n_compared, seconds_a, seconds_b, log_a)."""
     with tempfile.TemporaryDirectory() as ta, tempfile.TemporaryDirectory() as tb:
-        t_a, log = run(exe_a, ta)
+        t_a, log = run(exe_a, ta, nranks)
         t_b, _ = run(exe_b, tb)
         fa, fb = files(ta), files(tb)
         assert set(fa) == set(fb), sorted(set(fa) ^ set(fb))[:10]
@@ -91,7 +102,7 @@ def distances(exe_a, exe_b, upto):
     return at_end, worst, worst_comp, len(fb), n_cmp, t_a, t_b, log
 
 
-def compare(code, upto=100, tol=1e-5, ours=None, self_check=False, noise=True, noise_factor=4.0):
+def compare(code, upto=100, tol=1e-5, ours=None, self_check=False, noise=True, noise_factor=4.0, nranks=1):
     """The bar: at iteration `upto` every field family (EMF, CURRENT, CHARGE, PHASESPACE) of the CUDA build is
     within `tol` (relative L2) of the strict reference build - or, where the deck amplifies rounding noise past
     that (the cold two-stream instability of the shipped em1d deck: the reference's OWN -Ofast and strict builds
@@ -104,14 +115,14 @@ def compare(code, upto=100, tol=1e-5, ours=None, self_check=False, noise=True, n
     for e in (ref_exe, our_exe):
         if not os.path.exists(e):
             raise SystemExit("%s missing: run `make -C oracle decks` where the reference tree exists" % e)
-    at_end, worst, worst_comp, n_files, n_cmp, t_ours, t_ref, log = distances(our_exe, ref_exe, upto)
+    at_end, worst, worst_comp, n_files, n_cmp, t_ours, t_ref, log = distances(our_exe, ref_exe, upto, nranks)
     floor = {}
     if noise and os.path.exists(fast_exe):
         floor = distances(fast_exe, ref_exe, upto)[0]
     # the bar is stated at a given number of steps (fields that have grown out of the noise): judged on the dumps
     # of iteration `upto`; the worst over all earlier dumps (tiny fields, relative noise) is reported beside it
     ok = bool(at_end) and all(v <= max(tol, noise_factor * floor.get(k, 0.0)) for k, v in at_end.items())
-    return {"code": code, "files": n_files, "compared": n_cmp, "upto": upto, "tol": tol, "rel_err_at_upto": at_end,
+    return {"code": code, "slabs": nranks, "files": n_files, "compared": n_cmp, "upto": upto, "tol": tol, "rel_err_at_upto": at_end,
             "reference_fast_vs_strict_at_upto": floor, "noise_factor": noise_factor,
             "worst_rel_err_upto": worst, "worst_single_component": worst_comp,
             "seconds_ours": round(t_ours, 2), "seconds_reference": round(t_ref, 2), "ok": ok,
@@ -125,8 +136,9 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-5)
     ap.add_argument("--self-check", action="store_true")
     ap.add_argument("--ours", default=None, help="another executable to put in place of <code>_ours")
+    ap.add_argument("--gpus", type=int, default=1, help="em2d: run the program as this many slabs (one process each)")
     a = ap.parse_args()
-    res = compare(a.code, a.upto, a.tol, a.ours, a.self_check)
+    res = compare(a.code, a.upto, a.tol, a.ours, a.self_check, nranks=a.gpus)
     print(json.dumps(res))
     return 0 if res["ok"] else 1
 

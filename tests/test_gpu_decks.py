@@ -12,12 +12,12 @@ sys.path.insert(0, os.path.join(REPO, "scripts"))
 pytestmark = pytest.mark.gpu
 
 
-def _run(code):
+def _run(code, nranks=1):
     import gpu_decks
     d = os.path.join(REPO, "oracle", "_ref", "decks")
     if not all(os.path.exists(os.path.join(d, code + s)) for s in ("_ref", "_ours")):
         pytest.skip("oracle/_ref/decks not built")
-    return gpu_decks.compare(code, upto=100, tol=1e-5)
+    return gpu_decks.compare(code, upto=100, tol=1e-5, nranks=nranks)
 
 
 def test_em2d_weibel_program_matches_the_reference_program():
@@ -36,3 +36,11 @@ def test_em1d_twostream_program_matches_the_reference_program():
     # which does not feed back that fast, still meets 1e-5
     assert res["rel_err_at_upto"]["CHARGE"] <= 1e-5, res
     assert res["ok"], res
+
+
+def test_em2d_weibel_program_as_two_slabs():
+    """the same unmodified program started twice (ZPIC_RANK = 0, 1): the library cuts the box into two slabs (on two GPUs
+    where the box has them), rank 0 writes the reference's 255 files"""
+    res = _run("em2d", nranks=2)
+    assert res["files"] == 255 and res["compared"] == 55
+    assert all(v <= 1e-5 for v in res["rel_err_at_upto"].values()), res

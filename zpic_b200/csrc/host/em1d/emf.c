@@ -7,6 +7,7 @@
 #include <string.h>
 #include <math.h>
 #include "zb_state.h"
+#include "zpic_b200.h"
 #include "timer.h"
 #include "zdf.h"
 
@@ -164,6 +165,16 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	if (ge || gb) zdev_emf1d_set_ext_grid(zb_dev(e), (const float*) ge, (const float*) gb);
 	free(ge); free(gb);
 	e->part_host_stale = 1;
+}
+
+/* custom-field callback that reads a table the caller filled (zpic_b200.h; the em1d form: value of cell ix at
+   table[3 * (ix + 1)]) */
+float3 zpic_b200_table_field( int ix, float dx, void* data )
+{
+	const zpic_b200_field_table* t = (const zpic_b200_field_table*) data;
+	const float* v = t->table + 3 * (size_t) (ix + 1);
+	(void) dx;
+	return (float3) { v[0], v[1], v[2] };
 }
 
 void emf_advance( t_emf *emf, const t_current *current )

@@ -163,8 +163,15 @@ def _fld_type(name):
     return {"none": A.EMF_FLD_TYPE_NONE, "uniform": A.EMF_FLD_TYPE_UNIFORM, "custom": A.EMF_FLD_TYPE_CUSTOM}[name]
 
 
+class _FieldTable(C.Structure):          # include/zpic_b200.h zpic_b200_field_table
+    _fields_ = [("nrow", C.c_int), ("table", C.POINTER(C.c_float))]
+
+
 class _FieldSpec:
-    """common part of ExternalField / InitialField (em2d.pyx:481-878)"""
+    """common part of ExternalField / InitialField (em2d.pyx:481-878).  Custom fields are Python callables
+    f(ix, dx, iy, dy) -> (fx, fy, fz) like in the reference; ctypes cannot return a struct from a callback, so they
+    are evaluated once for every cell of the buffer (the reference calls them with exactly these arguments,
+    em2d/emf.c:862-863, 924-980) and handed to the C side as a table read by zpic_b200_table_field."""
     _struct = None
 
     def __init__(self, *, E_type="none", B_type="none", E_0=(0., 0., 0.), B_0=(0., 0., 0.),
@@ -174,15 +181,24 @@ class _FieldSpec:
         self._c.B_type = _fld_type(B_type)
         self._c.E_0 = A.Float3(*E_0)
         self._c.B_0 = A.Float3(*B_0)
+        self._fns = {"E": E_custom, "B": B_custom}
         self._keep = []
-        for name, fn in (("E_custom", E_custom), ("B_custom", B_custom)):
-            if fn:
-                def tramp(ix, dx, iy, dy, data, _fn=fn):
-                    v = _fn(ix, dx, iy, dy)
-                    return A.Float3(v[0], v[1], v[2])
-                cb = A.FIELD_FN(tramp)
-                self._keep.append(cb)
-                setattr(self._c, name, cb)
+
+    def _bind(self, nx, ny, dx, dy):
+        """evaluate the custom callables on the grid of the simulation this object is being attached to"""
+        self._keep = []
+        tramp = C.cast(_L().zpic_b200_table_field, A.FIELD_FN)
+        for f, fn in self._fns.items():
+            if not fn or getattr(self._c, f + "_type") != A.EMF_FLD_TYPE_CUSTOM:
+                continue
+            tab = np.empty((ny + 3, nx + 3, 3), dtype=np.float32)
+            for j in range(-1, ny + 2):
+                for i in range(-1, nx + 2):
+                    tab[j + 1, i + 1] = fn(i, dx, j, dy)
+            desc = _FieldTable(nx + 3, tab.ctypes.data_as(C.POINTER(C.c_float)))
+            self._keep += [tab, desc]
+            setattr(self._c, f + "_custom", tramp)
+            setattr(self._c, f + "_custom_data", C.cast(C.pointer(desc), C.c_void_p))
 
 
 class ExternalField(_FieldSpec):
@@ -212,10 +228,14 @@ class EMF:
         return np.array(e[:])
 
     def init_fld(self, init_fld):
+        e = self._e
+        init_fld._bind(e.nx[0], e.nx[1], e.dx[0], e.dx[1])
         _L().emf_init_fld(self._p, C.byref(init_fld._c))
 
     def set_ext_fld(self, ext_fld):
         self._ext = ext_fld
+        e = self._e
+        ext_fld._bind(e.nx[0], e.nx[1], e.dx[0], e.dx[1])
         _L().emf_set_ext_fld(self._p, C.byref(ext_fld._c))
 
     nx = property(lambda s: np.array(s._e.nx[:], dtype=np.int32))
