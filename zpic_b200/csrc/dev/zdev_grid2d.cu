@@ -362,157 +362,18 @@ k_yee_fused(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__
 	}
 }
 
-// ---- mode 2 (ZPIC_FUSED_YEE=2, UNMEASURED, prepared for an A/B): the same kernel with the tile classified once.
-// k_yee_fused spends 16 warp-instructions per cell, mostly on the masks and index arithmetic that only tiles on
-// the rim of the buffer need (profiles/r01_yee_fused_summary.txt: IADD3 + ISETP + BRA + BSSY/BSYNC are 40 % of
-// the instruction stream).  A tile whose whole neighbourhood lies inside every loop range - A >= 1,
-// A + W + 1 <= nrow - 2 and the same for the rows - runs the body with EDGE = false, where every mask is true at
-// compile time and the copies walk row pointers; all other tiles run the masked body, EDGE = true, which is
-// k_yee_fused's.  Same arithmetic on the same inputs in both: bit-identical by construction.
-template <bool EDGE>
-__device__ __forceinline__ void yee_fused_tile(f3* sE, f3* sB, f3* sJ, f3* __restrict__ Eout, f3* __restrict__ Bout,
-                                               const f3* __restrict__ E, const f3* __restrict__ B, const f3* __restrict__ J,
-                                               int nrow, int nrows, float hdt_dx, float hdt_dy, float dt_dx, float dt_dy, float dt) {
-	const int A = blockIdx.x * YF_W, R = blockIdx.y * YF_H;
-	const int tx = threadIdx.x, ty = threadIdx.y;
-	{
-		const int tid = ty * YF_W + tx;
-		const long rowf = (long) nrow * 3;
-		const float* gE = reinterpret_cast<const float*>(E);
-		const float* gB = reinterpret_cast<const float*>(B);
-		const float* gJ = reinterpret_cast<const float*>(J);
-		float* fE = reinterpret_cast<float*>(sE);
-		float* fB = reinterpret_cast<float*>(sB);
-		float* fJ = reinterpret_cast<float*>(sJ);
-		if (!EDGE) {
-			// everything is inside the buffer: one pointer per array, advanced by a buffer row per tile row
-			const long o0 = (long) (R - 1) * rowf + (long) (A - 1) * 3;
-			for (int f = tid; f < YF_EW * 3; f += YF_THREADS) {
-				const float* pe = gE + o0 + f;
-				const float* pb = gB + o0 + f;
-				const bool inb = f < YF_BW * 3;
-				#pragma unroll
-				for (int r = 0; r < YF_EH; r++) {
-					yf_cp4(fE + r * (YF_EW * 3) + f, pe, true);
-					if (r < YF_BH && inb) yf_cp4(fB + r * (YF_BW * 3) + f, pb, true);
-					pe += rowf; pb += rowf;
-				}
-			}
-			for (int f = tid; f < YF_JW * 3; f += YF_THREADS) {
-				const float* pj = gJ + (long) R * rowf + (long) A * 3 + f;
-				#pragma unroll
-				for (int r = 0; r < YF_JH; r++) { yf_cp4(fJ + r * (YF_JW * 3) + f, pj, true); pj += rowf; }
-			}
-		} else {
-			#pragma unroll 1
-			for (int r = 0; r < YF_EH; r++) {
-				const int bj = R - 1 + r;
-				const bool rok = bj >= 0 && bj < nrows;
-				for (int f = tid; f < YF_EW * 3; f += YF_THREADS) {
-					const long fo = (long) (A - 1) * 3 + f;
-					const bool ok = rok && fo >= 0 && fo < rowf;
-					const long go = ok ? (long) bj * rowf + fo : 0;
-					yf_cp4(fE + r * (YF_EW * 3) + f, gE + go, ok);
-					if (r < YF_BH && f < YF_BW * 3) yf_cp4(fB + r * (YF_BW * 3) + f, gB + go, ok);
-				}
-			}
-			#pragma unroll 1
-			for (int r = 0; r < YF_JH; r++) {
-				const int bj = R + r;
-				for (int f = tid; f < YF_JW * 3; f += YF_THREADS) {
-					const long fo = (long) A * 3 + f;
-					const bool ok = bj < nrows && fo < rowf;
-					yf_cp4(fJ + r * (YF_JW * 3) + f, gJ + (ok ? (long) bj * rowf + fo : 0), ok);
-				}
-			}
-		}
-		asm volatile("cp.async.wait_all;" ::: "memory");
-	}
-	__syncthreads();
-	#pragma unroll
-	for (int r = ty; r < YF_BH; r += YF_TY) {
-		const int bj = R - 1 + r;
-		const bool rok = !EDGE || (bj >= 0 && bj <= nrows - 2);
-		#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int c = h ? YF_W + tx : tx;
-			if (h && tx >= 2) break;
-			const int bi = A - 1 + c;
-			if (rok && (!EDGE || (bi >= 0 && bi <= nrow - 2))) {
-				f3 b = sB[r * YF_BW + c];
-				yf_b(b, sE[r * YF_EW + c], sE[r * YF_EW + c + 1], sE[(r + 1) * YF_EW + c], hdt_dx, hdt_dy);
-				sB[r * YF_BW + c] = b;
-			}
-		}
-	}
-	__syncthreads();
-	#pragma unroll
-	for (int rr = ty; rr < YF_JH; rr += YF_TY) {
-		const int bj = R + rr;
-		const bool rok = !EDGE || (bj >= 1 && bj <= nrows - 1);
-		#pragma unroll
-		for (int h = 0; h < 2; h++) {
-			const int cc = h ? YF_W : tx;
-			if (h && tx >= 1) break;
-			const int bi = A + cc;
-			if (rok && (!EDGE || (bi >= 1 && bi <= nrow - 1))) {
-				const int r = rr + 1, c = cc + 1;
-				const f3 b = sB[r * YF_BW + c], bx = sB[r * YF_BW + c - 1], by = sB[(r - 1) * YF_BW + c];
-				const f3 jc = sJ[rr * YF_JW + cc];
-				f3 e = sE[r * YF_EW + c];
-				e.x += ( + dt_dy * ( b.z - by.z ) ) - dt * jc.x;
-				e.y += ( - dt_dx * ( b.z - bx.z ) ) - dt * jc.y;
-				e.z += ( + dt_dx * ( b.y - bx.y ) - dt_dy * ( b.x - by.x ) ) - dt * jc.z;
-				sE[r * YF_EW + c] = e;
-			}
-		}
-	}
-	__syncthreads();
-	#pragma unroll
-	for (int rr = ty; rr < YF_H; rr += YF_TY) {
-		const int bi = A + tx, bj = R + rr;
-		if (!EDGE || (bi < nrow && bj < nrows)) {
-			const int r = rr + 1, c = tx + 1;
-			const f3 e = sE[r * YF_EW + c];
-			f3 b = sB[r * YF_BW + c];
-			if (!EDGE || (bi <= nrow - 2 && bj <= nrows - 2))
-				yf_b(b, e, sE[r * YF_EW + c + 1], sE[(r + 1) * YF_EW + c], hdt_dx, hdt_dy);
-			const long o = (long) bj * nrow + bi;
-			Eout[o] = e;
-			Bout[o] = b;
-		}
-	}
-}
-
-__global__ void __launch_bounds__(YF_THREADS)
-k_yee_fused2(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__ E, const f3* __restrict__ B,
-             const f3* __restrict__ J, int nrow, int nrows, float hdt_dx, float hdt_dy, float dt_dx, float dt_dy, float dt) {
-	__shared__ f3 sE[YF_EH * YF_EW];
-	__shared__ f3 sB[YF_BH * YF_BW];
-	__shared__ f3 sJ[YF_JH * YF_JW];
-	const int A = blockIdx.x * YF_W, R = blockIdx.y * YF_H;
-	const bool inner = A >= 1 && A + YF_W + 1 <= nrow - 2 && R >= 1 && R + YF_H + 1 <= nrows - 2;    // block-uniform
-	if (inner) yee_fused_tile<false>(sE, sB, sJ, Eout, Bout, E, B, J, nrow, nrows, hdt_dx, hdt_dy, dt_dx, dt_dy, dt);
-	else       yee_fused_tile<true>(sE, sB, sJ, Eout, Bout, E, B, J, nrow, nrows, hdt_dx, hdt_dy, dt_dx, dt_dy, dt);
-}
-
-// ZPIC_FUSED_YEE=0 (or zdev_yee_set_fused(0)) keeps the three separate stencil kernels
 static int fused_yee = -1;
 static int fused_yee_on() {
-	if (fused_yee < 0) { const char* e = getenv("ZPIC_FUSED_YEE"); fused_yee = !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)); }
+	if (fused_yee < 0) { const char* e = getenv("ZPIC_FUSED_YEE"); fused_yee = !e ? 1 : (e[0] == '0' ? 0 : 1); }
 	return fused_yee;
 }
-extern "C" void zdev_yee_set_fused(int on) { fused_yee = on == 2 ? 2 : (on ? 1 : 0); }
+extern "C" void zdev_yee_set_fused(int on) { fused_yee = on ? 1 : 0; }
 static void yee_fused(zdev_grid2d* g, zdev_grid2d* gj, float dt, float dx, float dy) {
 	need_EB(g); need_J(gj); check_same_shape(g, gj); need_tmp(g); need_tmp2(g);
 	const float dtb = dt / 2.0f;
 	const int alias_e = (g->Epart == g->E), alias_b = (g->Bpart == g->B);
 	dim3 grd(zdev_div_up(g->nrow, YF_W), zdev_div_up(g->nrows, YF_H));
-	if (fused_yee_on() == 2)
-		ZDEV_LAUNCH(k_yee_fused2, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
-		            dtb / dx, dtb / dy, dt / dx, dt / dy, dt);
-	else
-		ZDEV_LAUNCH(k_yee_fused, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
+	ZDEV_LAUNCH(k_yee_fused, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
 		            dtb / dx, dtb / dy, dt / dx, dt / dy, dt);
 	{ f3* t = g->E; g->E = g->tmp; g->tmp = t; }
 	{ f3* t = g->B; g->B = g->tmp2; g->tmp2 = t; }
