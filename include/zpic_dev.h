@@ -199,6 +199,27 @@ void zdev_spec2d_inject_column( zdev_spec2d* s, int ppcx, int ppcy, const float 
 void zdev_spec2d_inject_band( zdev_spec2d* s, int ppcx, int ppcy,
                               const float ufl[3], const float uth[3], uint64_t seed, int iy0, int iy1 );
 
+/* The reference's OWN random stream continued on the device (em2d/random.c:48-101: the two multiply-with-carry
+ * generators by modular jump-ahead, the polar Box-Muller rejections by a prefix sum over the acceptance flags).
+ * (z, w, have_spare, spare) are the variables m_z, m_w, iset, gset of random.c:16-17, 69-70; on return they are
+ * what `count` calls of rand_norm() would have left.  d_out (device memory, `count` floats; NULL: advance the
+ * state only) receives (float) (scale[m % 3] * deviate m), the narrowing of spec_set_u (em2d/particles.c:97-101).
+ * Returns 1 without doing anything when the state is outside the generators' linear range (a seed word of
+ * a 2^16 - 1 or more): the caller then draws on the host. */
+int zdev_ref_normals( uint32_t* z, uint32_t* w, int* have_spare, double* spare, long long count,
+                      const float scale[3], float* d_out );
+/* host half of the above alone: the generators' state after `draws` calls of rand_uint32() (random.c:48-53) */
+int zdev_ref_jump( uint32_t* z, uint32_t* w, unsigned long long draws );
+/* Initial population of a lattice profile (UNIFORM / STEP / SLAB, em2d/particles.c:167-180, 335-347) generated
+ * on the device on the reference random stream: the in-cell x positions kx_lo[i] <= kx < kx_hi[i] of box column
+ * i carry plasma (host arrays, one entry per column of the WHOLE box), every row alike; injection order,
+ * positions, thermal momenta, per-cell mean removal and fluid momentum as spec_set_x / spec_set_u produce them
+ * (:96-142; the cell means are those of a square box or a cold plasma - the reference's accumulator index uses
+ * nx[1] as its stride).  The stream state is advanced like zdev_ref_normals does. */
+int zdev_spec2d_inject_lattice( zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3],
+                                const int* kx_lo, const int* kx_hi,
+                                uint32_t* z, uint32_t* w, int* have_spare, double* spare );
+
 /* spec_advance minus the host bookkeeping (em2d/particles.c:1125-1259):
  * interpolate_fld (:1029-1071) + Boris push (:1146-1207) + dep_current_zamb
  * (:773-924) into g_cur's J, then boundaries / window shift and tile re-binning.

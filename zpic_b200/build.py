@@ -36,11 +36,11 @@ CC_FLAGS = ["-O2", "-std=gnu99", "-ffp-contract=off", "-fPIC", "-Wall", "-Wno-un
 
 CODES = {
     "em2d": {
-        "dev": ["zdev_runtime.cu", "zdev_grid2d.cu", "zdev_spec2d.cu"],
+        "dev": ["zdev_runtime.cu", "zdev_refrng.cu", "zdev_grid2d.cu", "zdev_spec2d.cu"],
         "host_dir": "em2d",
     },
     "em1d": {
-        "dev": ["zdev_runtime.cu", "zdev_grid1d.cu", "zdev_spec1d.cu"],
+        "dev": ["zdev_runtime.cu", "zdev_refrng.cu", "zdev_grid1d.cu", "zdev_spec1d.cu"],
         "host_dir": "em1d",
     },
 }

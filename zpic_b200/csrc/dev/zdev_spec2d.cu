@@ -847,6 +847,111 @@ extern "C" void zdev_spec2d_inject_uniform(zdev_spec2d* s, int ppcx, int ppcy, c
 	zdev_spec2d_inject_rect(s, ppcx, ppcy, ufl, uth, seed, 0, s->nx, 0, s->ny);
 }
 
+// ---- the same population as the reference's host injector, on the reference random stream (zdev_refrng.cu)
+// One thread per cell of the rows [j0, j1).  Column i of the box holds the in-cell x positions kx_lo <= kx < kx_hi
+// (STEP / SLAB clip them, particles.c:335-347), pre[] = particles per row in the columns before i, R per row; the
+// cell's particles are numbered (iy R + pre[i] + ky w + kx - kx_lo) like spec_set_x's loops order them, and
+// th[] holds the three thermal components of the rows' particles in that order (null: a cold plasma).
+__global__ void k_inject_lattice(soa2d p, const int64_t* __restrict__ off, int* tile_np, int nx, int ny, int TX, int TY, int ntx,
+                                 int ppcx, int ppcy, f3 ufl, const int* __restrict__ kx_lo, const int* __restrict__ kx_hi,
+                                 const int* __restrict__ pre, int gx0, int64_t R, int j0, int j1, const float* __restrict__ th) {
+	const int64_t c = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= (int64_t) nx * (j1 - j0)) return;
+	const int iy = j0 + (int) (c / nx), ix = (int) (c % nx), g = gx0 + ix;
+	const int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
+	const int cxw = (tx + 1) * TX <= nx ? TX : nx - tx * TX, cyw = (ty + 1) * TY <= ny ? TY : ny - ty * TY;
+	const int lx = ix - tx * TX, ly = iy - ty * TY;
+	const int gt0 = gx0 + tx * TX;
+	const int rowcnt = pre[gt0 + cxw] - pre[gt0];
+	if (lx == 0 && ly == 0) tile_np[t] = rowcnt * cyw;
+	const int lo = kx_lo[g], w = kx_hi[g] - lo;
+	if (w <= 0) return;
+	const int cnt = w * ppcy;
+	const int64_t base = off[t] + (int64_t) ly * rowcnt + (pre[g] - pre[gt0]);
+	const int64_t n0 = (int64_t) iy * R + pre[g];                    // injection index of the cell's first particle
+	const float* q = th ? th + 3 * ((int64_t) (iy - j0) * R + pre[g]) : nullptr;
+	float sx = 0, sy = 0, sz = 0;
+	if (q) {
+		for (int k = 0; k < cnt; k++) { sx += q[3 * k]; sy += q[3 * k + 1]; sz += q[3 * k + 2]; }
+		const float norm = 1.0f / cnt;
+		sx *= norm; sy *= norm; sz *= norm;
+	}
+	const float dpcx = 1.0f / ppcx, dpcy = 1.0f / ppcy;
+	for (int k = 0; k < cnt; k++) {
+		const int ky = k / w, kx = lo + k - ky * w;
+		const float tx_ = q ? q[3 * k] : 0.0f, ty_ = q ? q[3 * k + 1] : 0.0f, tz_ = q ? q[3 * k + 2] : 0.0f;
+		const int64_t d = base + k;
+		rec_store(p.rec, d, (float) (dpcx * (kx + 0.5)), (float) (dpcy * (ky + 0.5)),
+		          tx_ + (ufl.x - sx), ty_ + (ufl.y - sy), tz_ + (ufl.z - sz));
+		p.key[d] = (unsigned short) (lx + ly * TX);
+		if (p.tag) p.tag[d] = (int) (n0 + k);
+	}
+}
+
+extern "C" int zdev_spec2d_inject_lattice(zdev_spec2d* s, int ppcx, int ppcy, const float ufl[3], const float uth[3],
+                                          const int* kx_lo, const int* kx_hi,
+                                          uint32_t* z, uint32_t* w, int* have_spare, double* spare) {
+	const int gnx = s->gnx > 0 ? s->gnx : s->nx, gx0 = s->gnx > 0 ? s->gx0 : 0;
+	std::vector<int> pre(gnx + 1, 0);
+	for (int i = 0; i < gnx; i++) pre[i + 1] = pre[i] + std::max(kx_hi[i] - kx_lo[i], 0) * ppcy;
+	const int64_t R = pre[gnx];
+	const int64_t total = R * s->ny;                               // the whole box: the stream is the whole box's
+	const bool cold = uth[0] == 0.0f && uth[1] == 0.0f && uth[2] == 0.0f;
+	{	// the state must be usable before anything is laid out
+		uint32_t zz = *z, ww = *w;
+		if (zdev_ref_jump(&zz, &ww, 0)) return 1;
+	}
+	std::vector<int> cnt(s->ntiles);
+	int64_t np = 0;
+	for (int ty = 0; ty < s->nty; ty++) for (int tx = 0; tx < s->ntx; tx++) {
+		const int cx = (tx + 1) * s->TX <= s->nx ? s->TX : s->nx - tx * s->TX;
+		const int cy = (ty + 1) * s->TY <= s->ny ? s->TY : s->ny - ty * s->TY;
+		const int64_t c = (int64_t) (pre[gx0 + tx * s->TX + cx] - pre[gx0 + tx * s->TX]) * cy;
+		cnt[tx + ty * s->ntx] = (int) c; np += c;
+	}
+	const bool partial = (double) np < 0.9 * (double) s->nx * s->ny * ppcx * ppcy;
+	const int hint = s->ppc_hint;
+	if (partial) s->ppc_hint = 0;
+	spec_layout(s, cnt, np);
+	s->ppc_hint = hint;
+	if (partial) spec_build_tile_lists(s);
+	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+	int *d_lo, *d_hi, *d_pre;
+	ZDEV_CHECK(cudaMalloc(&d_lo, (size_t) gnx * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&d_hi, (size_t) gnx * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&d_pre, (size_t) (gnx + 1) * sizeof(int)));
+	ZDEV_CHECK(cudaMemcpyAsync(d_lo, kx_lo, (size_t) gnx * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaMemcpyAsync(d_hi, kx_hi, (size_t) gnx * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaMemcpyAsync(d_pre, pre.data(), (size_t) (gnx + 1) * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	const f3 fl = {ufl[0], ufl[1], ufl[2]};
+	if (cold || R == 0) {
+		// 0 * deviate: only the stream position matters (3 deviates per particle all the same, particles.c:97-101)
+		zdev_ref_normals(z, w, have_spare, spare, 3 * total, uth, nullptr);
+		if (np > 0)
+			ZDEV_LAUNCH(k_inject_lattice, zdev_div_up((int64_t) s->nx * s->ny, 128), 128, 0, s->p, s->tile_off, s->tile_np,
+			            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, d_lo, d_hi, d_pre, gx0, R, 0, s->ny, (const float*) nullptr);
+	} else {
+		// bands of rows: the thermal components of a band are generated into a staging array, then placed
+		const int rows = (int) std::max<int64_t>(1, std::min<int64_t>(s->ny, ((int64_t) 1 << 26) / R));
+		float* d_th;
+		ZDEV_CHECK(cudaMalloc(&d_th, (size_t) rows * R * 3 * sizeof(float)));
+		for (int j0 = 0; j0 < s->ny; j0 += rows) {
+			const int j1 = std::min(j0 + rows, s->ny);
+			zdev_ref_normals(z, w, have_spare, spare, 3 * R * (j1 - j0), uth, d_th);
+			if (np > 0)
+				ZDEV_LAUNCH(k_inject_lattice, zdev_div_up((int64_t) s->nx * (j1 - j0), 128), 128, 0, s->p, s->tile_off, s->tile_np,
+				            s->nx, s->ny, s->TX, s->TY, s->ntx, ppcx, ppcy, fl, d_lo, d_hi, d_pre, gx0, R, j0, j1, (const float*) d_th);
+		}
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		ZDEV_CHECK(cudaFree(d_th));
+	}
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	ZDEV_CHECK(cudaFree(d_lo)); ZDEV_CHECK(cudaFree(d_hi)); ZDEV_CHECK(cudaFree(d_pre));
+	s->np_host = np; s->np_known = 1;
+	s->ids_valid = s->track_ids && total < 0x7fffffff && np == total;
+	return 0;
+}
+
 // The moving window's new column (cells ix, iy0 <= iy < iy1) generated on the device like k_inject_uniform does and
 // appended to its tiles: one thread per cell reserves the cell's slots with one atomic.  `col` numbers the column
 // (cells that ever entered the box get distinct particle numbers).
@@ -1572,7 +1677,7 @@ extern "C" void zdev_spec2d_advance(zdev_spec2d* s, zdev_grid2d* grid, zdev_grid
 			in.rec[side] = (const part_aos*) zdev_link_in(K, side, seq);
 		}
 	}
-	ZDEV_LAUNCH(k_migrate2d, 4 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
+	ZDEV_LAUNCH(k_migrate2d, 8 * zdev_num_sm, 256, 0, s->p, s->tile_off, s->tile_np, s->mig, s->ctl,
 	            s->TX, s->TY, s->ntx, s->ntiles, s->nx, s->ny, prm->moving_window, prm->slab_left, prm->slab_right,
 	            exp_l, exp_r, s->exp_cap, s->ovf, s->ovf_tag, s->ovf_cap, pub);
 	if (s->slab) { s->pending_in = in; s->import_pending = 1; }      // the snapshot follows the import

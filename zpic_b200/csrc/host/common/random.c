@@ -18,6 +18,17 @@ void set_rand_seed( uint32_t first, uint32_t second )
 	mwc_z = second;
 }
 
+/* the stream's state, for the device-side continuation of the stream (zdev_ref_normals, zpic_dev.h) */
+void zb_rand_get_state( uint32_t* z, uint32_t* w, int* have, double* value )
+{
+	*z = mwc_z; *w = mwc_w; *have = have_spare; *value = spare;
+}
+
+void zb_rand_set_state( uint32_t z, uint32_t w, int have, double value )
+{
+	mwc_z = z; mwc_w = w; have_spare = have; spare = value;
+}
+
 uint32_t rand_uint32( void )
 {
 	mwc_z = 36969u * (mwc_z & 0xffffu) + (mwc_z >> 16);

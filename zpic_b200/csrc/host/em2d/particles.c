@@ -13,6 +13,7 @@
 #include <math.h>
 #include "zb_state.h"
 #include "random.h"
+#include "../common/zb_rand.h"
 #include "timer.h"
 #include "zdf.h"
 
@@ -272,6 +273,40 @@ static int device_init_rect( const t_species* spec, int rect[4] )
 	}
 }
 
+/* Lattice profiles (UNIFORM / STEP / SLAB): the in-cell x positions kx with lo[i] <= kx < hi[i] of column i carry
+   plasma - the clip of place_particles() evaluated with the same float expressions; every row is alike.  Returns
+   the particles per row, or -1 when the reference-stream device injector does not cover the species (CUSTOM
+   profiles; a warm plasma in a box with nx[0] != nx[1], whose cell means mix cells - SURVEY.md App. B 5). */
+static long long lattice_columns( const t_species* spec, int** lo_out, int** hi_out )
+{
+	const enum density_type type = spec->density.type;
+	if (type != UNIFORM && type != STEP && type != SLAB) return -1;
+	const int warm = spec->uth[0] != 0 || spec->uth[1] != 0 || spec->uth[2] != 0;
+	if (warm && spec->nx[0] != spec->nx[1]) return -1;
+	const int nx = spec->nx[0], ppcx = spec->ppc[0];
+	const float dpcx = 1.0f / ppcx;
+	float lo = 0, hi = 0;
+	if (type == STEP || type == SLAB) lo = spec->density.start / spec->dx[0] - spec->n_move;
+	if (type == SLAB) hi = spec->density.end / spec->dx[0] - spec->n_move;
+	int* klo = malloc((size_t) nx * sizeof(int)); int* khi = malloc((size_t) nx * sizeof(int));
+	long long per_row = 0;
+	for (int i = 0; i < nx; i++) {
+		int a = ppcx, b = 0;                     /* first and one-past-last passing position (they form a range) */
+		for (int k = 0; k < ppcx; k++) {
+			const float cx = dpcx * ( k + 0.5 );
+			int in = 1;
+			if (type == STEP) in = ( i + cx > lo );
+			if (type == SLAB) in = ( i + cx > lo && i + cx < hi );
+			if (in) { if (k < a) a = k; b = k + 1; }
+		}
+		if (b <= a) { a = 0; b = 0; }
+		klo[i] = a; khi[i] = b;
+		per_row += (long long) (b - a) * spec->ppc[1];
+	}
+	*lo_out = klo; *hi_out = khi;
+	return per_row;
+}
+
 void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
                const float *ufl, const float *uth,
                const int nx[], float box[], const float dt, t_density* density )
@@ -320,7 +355,32 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc[],
 	spec->np = 0;
 	const int range[][2] = { {0, nx[0]-1}, {0, nx[1]-1} };
 	int rect[4];
-	if (zb_opt_device_init() && device_init_rect(spec, rect)) {
+	int *lat_lo = NULL, *lat_hi = NULL;
+	long long per_row = -1;
+	if (zb_opt_device_init() == 2) per_row = lattice_columns(spec, &lat_lo, &lat_hi);
+	if (per_row >= 0) {
+		/* device_init = 2: the reference's own initial population - same positions, same injection order, momenta
+		   from the same global random stream - generated on the device at the first step (zdev_refrng.cu).  The
+		   host stream is moved past this species' 3 deviates per particle NOW, so whatever is created next (the
+		   second species, a window column) draws what it would have drawn in the reference. */
+		zb_spec* e = zb_spec_of(spec, 1);
+		zb_rand_get_state(&e->rs_z, &e->rs_w, &e->rs_have, &e->rs_spare);
+		uint32_t z = e->rs_z, w = e->rs_w; int have = e->rs_have; double spare = e->rs_spare;
+		const long long total = per_row * nx[1];
+		if (zdev_ref_normals(&z, &w, &have, &spare, 3 * total, spec->uth, NULL) == 0) {
+			zb_rand_set_state(z, w, have, spare);
+			e->device_init = 2;
+			e->lat_lo = lat_lo; e->lat_hi = lat_hi;
+			spec->np = (total > 0x7fffffffLL) ? 0x7fffffff : (int) total;
+		} else {
+			/* seeds outside the generators' linear range: the host injector */
+			free(lat_lo); free(lat_hi);
+			per_row = -1;
+		}
+	}
+	if (per_row >= 0) {
+		/* done above */
+	} else if (zb_opt_device_init() == 1 && device_init_rect(spec, rect)) {
 		/* opt-in for populations too large for a host mirror: the plasma fills a rectangle of cells at the nominal
 		   particles per cell (whole box; from a STEP / inside a SLAB along x; the band a 0/1 CUSTOM profile along
 		   y selects), generated by a counter-based generator on the device at the first step (one draw of the

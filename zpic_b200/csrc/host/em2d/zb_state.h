@@ -43,7 +43,10 @@ typedef struct zb_grid {
 typedef struct zb_spec {
 	const t_species* spec;
 	zdev_spec2d* d;            /* NULL until first device use: see zb_spec_dev() */
-	int device_init;           /* population is generated on the device at first use (no host mirror yet) */
+	int device_init;           /* population is generated on the device at first use (no host mirror yet): 1 with a
+	                              counter-based generator, 2 on the reference random stream (lattice profiles) */
+	int* lat_lo; int* lat_hi;  /*   2: in-cell x positions [lo, hi) of every box column that carry plasma */
+	uint32_t rs_z, rs_w; int rs_have; double rs_spare;   /* 2: the stream's state where this species' draws begin */
 	int device_made;           /* ... and was: the moving window's new columns are generated on the device too */
 	uint64_t device_seed;
 	int dev_rect[4];           /*   ... in the cells [0,1) x [2,3) of the box */
@@ -78,7 +81,8 @@ void zb_spec_to_host( const t_species* spec );
 int zb_opt_lazy( void );        /* 1: do not fetch energy / np after every spec_advance */
 int zb_opt_track_ids( void );   /* 1: keep injection order recoverable in the host mirror */
 int zb_opt_coherent( void );    /* 1: host mirrors are refreshed before and after every sim_iter */
-int zb_opt_device_init( void ); /* 1: uniform species are initialised on the device (not the reference random stream) */
+int zb_opt_device_init( void ); /* species are initialised on the device: 1 counter-based generator (not the reference
+                                   random stream), 2 the reference random stream (lattice profiles; others on the host) */
 
 void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max );
 
