@@ -43,12 +43,14 @@ def test_module_builds_a_simulation_on_the_host(ours):
 
 
 @pytest.mark.gpu
-def test_module_steps_like_the_reference(ours, ref):
-    """the unmodified module on the CUDA library (ZPIC_COHERENT semantics: host mirrors refreshed around every
-    sim_iter) against the reference build driven through ctypes: same deck, 10 steps"""
+@pytest.mark.parametrize("coherent", [0, 1])
+def test_module_steps_like_the_reference(ours, ref, coherent):
+    """the unmodified module on the CUDA library against the reference build driven through ctypes: same deck, 10
+    steps.  coherent = 0: the module's numpy views are guarded mirrors (zb_guard.h) - what it reads is downloaded
+    when it reads it; coherent = 1: ZPIC_COHERENT semantics, every mirror refreshed around every sim_iter"""
     em2d = _load("em2d")
     assert ours.zdev_init(-1) == 0
-    ours.zpic_b200_set_option(b"coherent", 1)
+    ours.zpic_b200_set_option(b"coherent", coherent)
     ours.zpic_b200_set_option(b"lazy", 0)
     try:
         sim, sp = _weibel(em2d)

@@ -21,8 +21,9 @@ void current_new( t_current *current, int nx[], float box[], float dt )
 	}
 	current->nrow = nx[0] + 3;
 	size_t ncell = (size_t) (nx[0] + 3) * (nx[1] + 3);
-	current->J_buf = calloc(ncell, sizeof(float3));
+	current->J_buf = zb_guard_alloc(ncell * sizeof(float3));
 	if (!current->J_buf) { fprintf(stderr, "(*error*) current_new: out of memory\n"); exit(-1); }
+	zb_guard_bind_cur(current);
 	current->J = current->J_buf + 1 + current->nrow;
 
 	current->smooth = (t_smooth) { .xtype = NONE, .ytype = NONE, .xlevel = 0, .ylevel = 0 };
@@ -37,7 +38,7 @@ void current_delete( t_current *current )
 {
 	zb_grid_drop_cur(current);
 	if (zdev_ready()) zdev_host_unpin(current->J_buf);
-	free(current->J_buf);
+	zb_guard_free(current->J_buf);
 	current->J_buf = NULL;
 }
 
@@ -46,6 +47,7 @@ void current_zero( t_current *current )
 	zb_grid* e = zb_grid_of_cur(current, 1);
 	zdev_current_zero(zb_dev(e));
 	e->j_host_stale = 1;
+	zb_guard_refresh();
 }
 
 void current_update( t_current *current )
@@ -58,6 +60,7 @@ void current_update( t_current *current )
 	                    current->smooth.xlevel, current->smooth.ylevel);
 	e->j_host_stale = 1;
 	current->iter++;
+	zb_guard_refresh();
 }
 
 void current_report( const t_current *current, const int jc )
@@ -67,7 +70,7 @@ void current_report( const t_current *current, const int jc )
 		return;
 	}
 	zb_cur_to_host(current);
-	if (zb_par_rank() != 0) return;          /* one file per box: rank 0 writes it */
+	if (zb_par_rank() != 0) { zb_guard_refresh(); return; }          /* one file per box: rank 0 writes it */
 
 	const int nx = current->nx[0], ny = current->nx[1];
 	float* buf = malloc((size_t) nx * ny * sizeof(float));
@@ -92,4 +95,5 @@ void current_report( const t_current *current, const int jc )
 	                         .t = current->iter * current->dt, .time_units = "1/\\omega_p" };
 	zdf_save_grid(buf, zdf_float32, &info, &iter, "CURRENT");
 	free(buf);
+	zb_guard_refresh();
 }

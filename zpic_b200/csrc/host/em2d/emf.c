@@ -36,9 +36,10 @@ void emf_new( t_emf *emf, int nx[], float box[], const float dt )
 	}
 	emf->nrow = nx[0] + 3;
 	size_t n = emf_ncell(emf);
-	emf->E_buf = calloc(n, sizeof(float3));
-	emf->B_buf = calloc(n, sizeof(float3));
+	emf->E_buf = zb_guard_alloc(n * sizeof(float3));       /* guarded mirrors: ../common/zb_guard.h */
+	emf->B_buf = zb_guard_alloc(n * sizeof(float3));
 	if (!emf->E_buf || !emf->B_buf) { fprintf(stderr, "(*error*) emf_new: out of memory\n"); exit(-1); }
+	zb_guard_bind_emf(emf);
 	emf->E = emf->E_buf + 1 + emf->nrow;
 	emf->B = emf->B_buf + 1 + emf->nrow;
 
@@ -61,10 +62,10 @@ void emf_delete( t_emf *emf )
 {
 	zb_grid_drop_emf(emf);
 	if (zdev_ready()) { zdev_host_unpin(emf->E_buf); zdev_host_unpin(emf->B_buf); }
-	free(emf->E_buf); free(emf->B_buf);
+	zb_guard_free(emf->E_buf); zb_guard_free(emf->B_buf);
 	emf->E_buf = emf->B_buf = NULL;
-	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.E_part_buf);
-	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.B_part_buf);
+	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.E_part_buf);
+	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.B_part_buf);
 	emf->E_part = emf->B_part = NULL;
 }
 
@@ -238,8 +239,8 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	const size_t bytes = emf_ncell(emf) * sizeof(float3);
 
-	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.E_part_buf);
-	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.B_part_buf);
+	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.E_part_buf);
+	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.B_part_buf);
 
 	emf->ext_fld.E_type = ext_fld->E_type;
 	emf->ext_fld.B_type = ext_fld->B_type;
@@ -253,14 +254,14 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	else {
 		emf->ext_fld.E_0 = ext_fld->E_0;
 		emf->ext_fld.E_custom = ext_fld->E_custom; emf->ext_fld.E_custom_data = ext_fld->E_custom_data;
-		emf->ext_fld.E_part_buf = malloc(bytes);
+		emf->ext_fld.E_part_buf = zb_guard_alloc(bytes);
 		emf->E_part = emf->ext_fld.E_part_buf + 1 + emf->nrow;
 	}
 	if (ext_fld->B_type == EMF_FLD_TYPE_NONE) { emf->B_part = emf->B; emf->ext_fld.B_part_buf = NULL; }
 	else {
 		emf->ext_fld.B_0 = ext_fld->B_0;
 		emf->ext_fld.B_custom = ext_fld->B_custom; emf->ext_fld.B_custom_data = ext_fld->B_custom_data;
-		emf->ext_fld.B_part_buf = malloc(bytes);
+		emf->ext_fld.B_part_buf = zb_guard_alloc(bytes);
 		emf->B_part = emf->ext_fld.B_part_buf + 1 + emf->nrow;
 	}
 
@@ -287,6 +288,8 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	if (ge || gb) zdev_emf_set_ext_grid(zb_dev(e), (const float*) ge, (const float*) gb);
 	free(ge); free(gb);
 	e->part_host_stale = 1;
+	zb_guard_bind_emf(emf);
+	zb_guard_refresh();
 }
 
 /* custom-field callback that reads a table the caller filled (zpic_b200.h) */
@@ -322,6 +325,7 @@ void emf_advance( t_emf *emf, const t_current *current )
 	if (shift) emf->n_move++;
 
 	if (!zb_opt_lazy()) zdev_sync();
+	zb_guard_refresh();
 	emf_seconds += timer_interval_seconds(t0, timer_ticks());
 }
 
@@ -343,7 +347,7 @@ void emf_report( const t_emf *emf, const char field, const int fc )
 		return;
 	}
 	zb_emf_to_host(emf);
-	if (zb_par_rank() != 0) return;          /* one file per box: rank 0 writes it */
+	if (zb_par_rank() != 0) { zb_guard_refresh(); return; }          /* one file per box: rank 0 writes it */
 
 	char name[16], label[16];
 	const float3* f;
@@ -376,4 +380,5 @@ void emf_report( const t_emf *emf, const char field, const int fc )
 	                         .t = emf->iter * emf->dt, .time_units = "1/\\omega_p" };
 	zdf_save_grid(buf, zdf_float32, &info, &iter, "EMF");
 	free(buf);
+	zb_guard_refresh();
 }

@@ -28,19 +28,37 @@ double   spec_perf( void )  { return (push_count > 0) ? push_seconds / push_coun
 
 static float density_one( float x, void* data ) { (void) x; (void) data; return 1.0; }
 
-static void grow( t_part** buf, int* np_max, int size )
+/* `mirror`: the buffer is a species' host mirror (a guarded mapping, ../common/zb_guard.h; `keep` particles of it
+   are worth copying), otherwise a scratch buffer from the C allocator */
+static void grow( t_part** buf, int* np_max, int size, const t_species* mirror, int keep )
 {
 	if (size > *np_max) {
 		*np_max = ( size/1024 + 1 ) * 1024;       /* 1024-particle chunks (reference particles.c:463) */
-		*buf = realloc(*buf, (size_t) *np_max * sizeof(t_part));
+		if (mirror) {
+			*buf = zb_guard_realloc(*buf, (size_t) *np_max * sizeof(t_part), (size_t) keep * sizeof(t_part));
+			zb_guard_bind_spec(mirror, *buf);
+		} else *buf = realloc(*buf, (size_t) *np_max * sizeof(t_part));
 		if (!*buf) { fprintf(stderr, "(*error*) species buffer: out of memory\n"); exit(-1); }
 	}
 }
 
+/* room for `size` particles in the mirror; what it holds is NOT preserved (it is about to be overwritten) */
+void zb_spec_reserve( t_species* spec, const int size )
+{
+	if (size <= spec->np_max) return;
+	if (spec->part && zdev_ready()) zdev_host_forget(spec->part);
+	/* a growing population (moving window) asks again and again: a quarter of headroom */
+	const long long want = (long long) spec->np_max + spec->np_max / 4;
+	grow(&spec->part, &spec->np_max, (want > size && want < 0x7ffffc00LL) ? (int) want : size, spec, 0);
+}
+
 void spec_grow_buffer( t_species* spec, const int size )
 {
-	if (size > spec->np_max && spec->part && zdev_ready()) zdev_host_forget(spec->part);   /* realloc may move it */
-	grow(&spec->part, &spec->np_max, size);
+	if (size <= spec->np_max) return;
+	/* callers (Species.add of the Python module, em2d.pyx:253) append to what the buffer holds: make it current */
+	zb_spec_to_host(spec);
+	if (spec->part && zdev_ready()) zdev_host_forget(spec->part);   /* the buffer may move */
+	grow(&spec->part, &spec->np_max, size, spec, spec->np);
 }
 
 /* upper bound of the number of particles the profile puts in `range`
@@ -233,7 +251,8 @@ static void draw_momenta( t_species* spec, t_part* part, int first, int last )
 void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max )
 {
 	const int first = *np;
-	grow(buf, np_max, *np + count_upper_bound(spec, range));
+	const int is_mirror = (buf == &spec->part);
+	grow(buf, np_max, *np + count_upper_bound(spec, range), is_mirror ? spec : NULL, *np);
 	*np = place_particles(spec, range, *buf, *np);
 	draw_momenta(spec, *buf, first, *np - 1);
 }
@@ -403,7 +422,7 @@ void spec_delete( t_species* spec )
 {
 	zb_spec_drop(spec);
 	if (spec->part && zdev_ready()) zdev_host_forget(spec->part);
-	free(spec->part);
+	zb_guard_free(spec->part);
 	spec->part = NULL;
 	spec->np = -1;
 }
@@ -421,6 +440,7 @@ void spec_move_window( t_species *spec )
 		spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
 		zb_spec* e = zb_spec_of(spec, 1);
 		e->dev_stale = 1;
+		zb_guard_refresh();
 	}
 }
 
@@ -498,9 +518,13 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		spec->np = (np > 0x7fffffffLL) ? 0x7fffffff : (int) np;
 		s->np_seen = spec->np;
 		push_count += spec->np;
+		/* a guarded mirror is filled from inside a fault handler, where the buffer cannot move: make room now */
+		if (zb_guard_enabled() && spec->np > spec->np_max && spec->np < 0x7ff00000 && zb_par_init() <= 1)
+			zb_spec_reserve(spec, spec->np);
 	} else {
 		push_count += spec->np;      /* population estimate; exact after the next sync */
 	}
+	zb_guard_refresh();
 	push_seconds += timer_interval_seconds(t0, timer_ticks());
 }
 
@@ -708,4 +732,5 @@ void spec_report( const t_species *spec, const int rep_type,
 		if (zb_par_rank() == 0) report_particles(spec);
 		break;
 	}
+	zb_guard_refresh();
 }

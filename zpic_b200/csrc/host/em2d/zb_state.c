@@ -191,6 +191,9 @@ void zb_emf_to_host( const t_emf* emf ) {
 	zb_grid* e = zb_grid_of_emf(emf, 0);
 	if (!e) return;
 	const int nrows = emf->nx[1] + 3;
+	/* the library is about to write (and its callers may go on writing): open the mirrors */
+	zb_guard_set(emf->E_buf, ZB_G_RW); zb_guard_set(emf->B_buf, ZB_G_RW);
+	zb_guard_set(emf->ext_fld.E_part_buf, ZB_G_RW); zb_guard_set(emf->ext_fld.B_part_buf, ZB_G_RW);
 	if (e->eb_host_stale) {
 		zb_pin_emf(emf);
 		grid_down(e, ZDEV_E, emf->E_buf, emf->nrow, nrows);
@@ -208,6 +211,7 @@ void zb_emf_to_host( const t_emf* emf ) {
 
 void zb_cur_to_host( const t_current* cur ) {
 	zb_grid* e = zb_grid_of_cur(cur, 0);
+	zb_guard_set(cur->J_buf, ZB_G_RW);
 	if (!e || !e->j_host_stale) return;
 	zdev_host_pin(cur->J_buf, (size_t) (cur->nx[0] + 3) * (cur->nx[1] + 3) * sizeof(float3));   /* unpinned by current_delete */
 	grid_down(e, ZDEV_J, cur->J_buf, cur->nrow, cur->nx[1] + 3);
@@ -265,6 +269,7 @@ void zb_spec_to_host( const t_species* cspec ) {
 	t_species* spec = (t_species*) cspec;    /* the mirror is a cache of device state */
 	zb_spec* e = zb_spec_of(spec, 0);
 	if (e && e->device_init) zb_spec_to_device(spec);      /* never materialised yet: generate it, then mirror it */
+	zb_guard_set(spec->part, ZB_G_RW);
 	if (!e || !e->host_stale) return;
 	if (e->slab.on) {
 		/* every rank's mirror gets the whole population: own slab from the device (box coordinates), the
@@ -282,17 +287,76 @@ void zb_spec_to_host( const t_species* cspec ) {
 		zdev_spec2d_download(zb_spec_dev(e), dst, mine);
 		for (long long i = 0; i < mine; i++) dst[i].ix += e->slab.x0;
 		zb_par_barrier();
-		spec_grow_buffer(spec, (int) total);
+		zb_spec_reserve(spec, (int) total);
 		memcpy(spec->part, all, (size_t) total * sizeof(t_part));
 		spec->np = (int) total;
 		zb_par_barrier();
 	} else {
 		int64_t np = zdev_spec2d_np(zb_spec_dev(e));
-		spec_grow_buffer(spec, (int) np);
+		zb_spec_reserve(spec, (int) np);
 		spec->np = (int) zdev_spec2d_download(zb_spec_dev(e), spec->part, spec->np_max);
 	}
 	e->host_stale = 0;
 	e->part_seen = spec->part; e->np_seen = spec->np;
+}
+
+/* ---------------------------------------------------------------- guarded mirrors */
+
+enum { ZB_K_E, ZB_K_B, ZB_K_EPART, ZB_K_BPART, ZB_K_J, ZB_K_PART };
+
+/* a stale mirror was touched by host code (we are inside the fault handler): bring it over.  E and B travel
+   together, like in zb_emf_to_host. */
+static void guard_fill( void* owner, int kind ) {
+	switch (kind) {
+	case ZB_K_E: case ZB_K_B: case ZB_K_EPART: case ZB_K_BPART: zb_emf_to_host((const t_emf*) owner); break;
+	case ZB_K_J: zb_cur_to_host((const t_current*) owner); break;
+	case ZB_K_PART: zb_spec_to_host((const t_species*) owner); break;
+	}
+	zb_guard_refresh();
+}
+
+/* first host write to a mirror that was in sync: it goes up before the next device step */
+static void guard_dirty( void* owner, int kind ) {
+	if (kind == ZB_K_E || kind == ZB_K_B) { zb_grid* e = zb_grid_of_emf((const t_emf*) owner, 0); if (e) e->eb_dev_stale = 1; }
+	else if (kind == ZB_K_PART) { zb_spec* e = zb_spec_of((const t_species*) owner, 0); if (e) e->dev_stale = 1; }
+}
+
+void zb_guard_bind_emf( const t_emf* emf ) {
+	zb_guard_bind(emf->E_buf, (void*) emf, ZB_K_E, guard_fill, guard_dirty);
+	zb_guard_bind(emf->B_buf, (void*) emf, ZB_K_B, guard_fill, guard_dirty);
+	zb_guard_bind(emf->ext_fld.E_part_buf, (void*) emf, ZB_K_EPART, guard_fill, guard_dirty);
+	zb_guard_bind(emf->ext_fld.B_part_buf, (void*) emf, ZB_K_BPART, guard_fill, guard_dirty);
+}
+void zb_guard_bind_cur( const t_current* cur ) { zb_guard_bind(cur->J_buf, (void*) cur, ZB_K_J, guard_fill, guard_dirty); }
+void zb_guard_bind_spec( const t_species* spec, void* buf ) { zb_guard_bind(buf, (void*) spec, ZB_K_PART, guard_fill, guard_dirty); }
+
+/* protection of every mirror from the coherence flags: device newer -> no access; in sync -> read only (a write
+   is noticed); host newer -> open.  J is never uploaded, so it is simply open once it is current.  Particle
+   mirrors are guarded only when the particle count is known after every step (not in lazy mode: the handler
+   cannot move a buffer that turns out too small). */
+void zb_guard_refresh( void ) {
+	if (!zb_guard_enabled()) return;
+	/* slabs: refreshing a mirror is a collective of the job (every rank's mirror holds the whole box), which a
+	   page fault on one rank cannot start - the mirrors stay open and callers use the explicit sync calls */
+	if (zb_par_init() > 1) return;
+	for (int i = 0; i < n_grids; i++) {
+		zb_grid* e = &grids[i];
+		if (e->emf) {
+			const int st = e->eb_host_stale ? ZB_G_NONE : (e->eb_dev_stale ? ZB_G_RW : ZB_G_READ);
+			zb_guard_set(e->emf->E_buf, st); zb_guard_set(e->emf->B_buf, st);
+			const int sp = e->part_host_stale ? ZB_G_NONE : ZB_G_READ;
+			if (e->emf->ext_fld.E_type != EMF_FLD_TYPE_NONE) zb_guard_set(e->emf->ext_fld.E_part_buf, sp);
+			if (e->emf->ext_fld.B_type != EMF_FLD_TYPE_NONE) zb_guard_set(e->emf->ext_fld.B_part_buf, sp);
+		}
+		if (e->cur) zb_guard_set(e->cur->J_buf, e->j_host_stale ? ZB_G_NONE : ZB_G_RW);
+	}
+	const int lazy = zb_opt_lazy();
+	for (int i = 0; i < n_specs; i++) {
+		zb_spec* e = &specs[i];
+		if (!e->spec->part) continue;
+		const int st = lazy ? ZB_G_RW : (e->host_stale ? ZB_G_NONE : (e->dev_stale ? ZB_G_RW : ZB_G_READ));
+		zb_guard_set(e->spec->part, st);
+	}
 }
 
 /* ---------------------------------------------------------------- public extras */
@@ -301,6 +365,7 @@ void zpic_b200_sync_host( t_simulation* sim ) {
 	zb_emf_to_host(&sim->emf);
 	zb_cur_to_host(&sim->current);
 	for (int i = 0; i < sim->n_species; i++) zb_spec_to_host(&sim->species[i]);
+	zb_guard_refresh();
 }
 
 void zpic_b200_touch_host( t_simulation* sim ) {
@@ -312,17 +377,19 @@ void zpic_b200_touch_emf( t_emf* emf ) {
 	zb_emf_to_host(emf);
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	e->eb_dev_stale = 1;
+	zb_guard_refresh();
 }
 
 void zpic_b200_touch_species( t_species* spec ) {
 	zb_spec_to_host(spec);
 	zb_spec* e = zb_spec_of(spec, 1);
 	e->dev_stale = 1;
+	zb_guard_refresh();
 }
 
-void zpic_b200_sync_species( t_species* spec ) { zb_spec_to_host(spec); }
-void zpic_b200_sync_emf( t_emf* emf ) { zb_emf_to_host(emf); }
-void zpic_b200_sync_current( t_current* cur ) { zb_cur_to_host(cur); }
+void zpic_b200_sync_species( t_species* spec ) { zb_spec_to_host(spec); zb_guard_refresh(); }
+void zpic_b200_sync_emf( t_emf* emf ) { zb_emf_to_host(emf); zb_guard_refresh(); }
+void zpic_b200_sync_current( t_current* cur ) { zb_cur_to_host(cur); zb_guard_refresh(); }
 
 /* device handles of the twins (zpic_dev.h objects), for tools that drive or time the
    device seam directly (bench.py) */

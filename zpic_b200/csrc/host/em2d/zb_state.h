@@ -12,6 +12,7 @@
 #include "zpic_dev.h"
 #include "simulation.h"
 #include "../common/zb_par.h"
+#include "../common/zb_guard.h"
 
 /* Slab decomposition along x (one process per GPU, zb_par.h).  The host objects of the API stay GLOBAL on every
  * rank - same sizes, same mirrors, same random stream as a single-process run; the device twins are the rank's
@@ -85,5 +86,13 @@ int zb_opt_device_init( void ); /* species are initialised on the device: 1 coun
                                    random stream), 2 the reference random stream (lattice profiles; others on the host) */
 
 void spec_inject_into( t_species* spec, const int range[][2], t_part** buf, int* np, int* np_max );
+void zb_spec_reserve( t_species* spec, const int size );
+
+/* guarded mirrors (../common/zb_guard.h): tell the guard who owns a mirror, and bring every mirror's protection
+   in line with the coherence flags (called where a public entry point returns to the caller) */
+void zb_guard_bind_emf( const t_emf* emf );
+void zb_guard_bind_cur( const t_current* cur );
+void zb_guard_bind_spec( const t_species* spec, void* buf );
+void zb_guard_refresh( void );
 
 #endif
