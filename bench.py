@@ -235,11 +235,19 @@ def run_ours(args):
     #      GPU inside spec_advance / current_update / emf_advance (csrc/dev/zdev_slab.cuh).  torch.distributed
     #      (NCCL) only carries the barrier and the max-over-ranks of the timing.
     n, free_b = fit_grid(lib, args.n, args.ppc * args.ppc)
-    lib.zpic_b200_set_option(b"device_init", 1)
+    # initial state: at N = 1 the reference's own (its random stream continued on the device, zdev_refrng.cu: the
+    # particles are those spec_new of the reference creates for this deck and seed); at N > 1 the box is not square
+    # and a warm plasma there takes the reference's cell-mixing means: counter-based generator
+    init_mode = args.init if args.init else (2 if world == 1 else 1)
+    lib.zpic_b200_set_option(b"device_init", init_mode)
     lib.zpic_b200_set_option(b"lazy", 1)
     lib.zpic_b200_set_option(b"coherent", 0)
     lib.zdev_set_push_timing(1)
+    t_init0 = time.perf_counter()
     sim, species, _ = build_weibel(lib, A, n * world, n, ppc)
+    lib.sim_iter(C.byref(sim))
+    lib.zdev_sync()
+    t_init = time.perf_counter() - t_init0
     np_total = 2 * n * n * args.ppc * args.ppc            # per GPU
     for _ in range(max(W, 1)):
         lib.sim_iter(C.byref(sim))
@@ -315,8 +323,11 @@ def run_ours(args):
                                    % (n * world, n, " (%d per GPU along x)" % n if world > 1 else "", args.ppc * args.ppc,
                                       "" if n == 4096 else ", grid reduced to fit memory"),
                        "particles_per_gpu": np_total, "dt": DT, "dx": CELL,
-                       "init": "device-side counter-based thermal+fluid distribution",
-                       "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (np_total * 52 / 1e9),
+                       "init": ("the reference's initial state: spec_new's particles for this deck and seed, generated on the device "
+                                "from the reference's random stream (multiply-with-carry jump-ahead + scan over the Box-Muller "
+                                "rejections)" if init_mode == 2 else "device-side counter-based thermal+fluid distribution"),
+                       "init_s": round(t_init, 2),
+                       "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (np_total * 48 / 1e9),
                        "decomposition": ("%d slabs along x, one process per GPU, through sim_new / sim_iter of the C API; J guard "
                                          "columns (add), E/B halos and migrating particles are written by the sending kernels "
                                          "straight into the neighbour GPU's memory over NVLink (CUDA IPC mailboxes + flags, no "
@@ -616,9 +627,9 @@ def run_e2e(lib, A, args, n_full):
     `coherent`: NO state kept on the device - every sim_iter uploads all particles + E, B from the host mirrors and
     downloads particles + E, B, J again."""
     steps = max(args.steps, 10)
-    main, sim, species = _e2e_leg(lib, A, args, n_full, True, steps)
+    main, sim, species = _e2e_leg(lib, A, args, n_full, 2, steps)
     lib.sim_delete(C.byref(sim))
-    main["mode"] = ("public C API on BASELINE configs[1] (device-side initialisation): every step sim_iter + energy "
+    main["mode"] = ("public C API on BASELINE configs[1] (the reference's initial state, generated on the device): every step sim_iter + energy "
                     "diagnostics read back (a stream synchronisation per step); every 10 steps the deck's report set "
                     "(E, B, J, 2 charge grids) synchronised to host buffers")
     n = min(n_full, args.e2e_n)
@@ -627,6 +638,24 @@ def run_e2e(lib, A, args, n_full):
     main["host_initialised"] = host
     np_total = 2 * n * n * args.ppc * args.ppc
     grid_b = (n + 3) * (n + 3) * 12
+    # a caller written for the reference: no zpic_b200_* call anywhere, it just reads a raw buffer of the API after
+    # every step (what the reference's Cython module does when a notebook looks at sim.emf.Ez): the mirrors are
+    # guarded mappings (csrc/host/common/zb_guard.c), the read faults once per step and pulls E and B over
+    lib.zb_guard_fills.restype = C.c_ulong
+    E = A.grid_view(sim.emf.E_buf, n, n)
+    fills0, acc = lib.zb_guard_fills(), 0.0
+    lib.sim_iter(C.byref(sim))
+    acc += float(E[1:-2, 1:-2, 2].max())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lib.sim_iter(C.byref(sim))
+        acc += float(E[1:-2, 1:-2, 2].max())
+    dt_raw = time.perf_counter() - t0
+    main["unmodified_caller"] = {"value": np_total * steps / dt_raw, "unit": UNIT, "steps": steps, "workload": host["workload"],
+                                 "h2d_bytes_per_step": 2 * 32, "d2h_bytes_per_step": 2 * grid_b + 2 * 48,
+                                 "mirror_fills": int(lib.zb_guard_fills() - fills0),
+                                 "note": "sim_iter + a numpy reduction over the raw E buffer of the API every step, no "
+                                         "zpic_b200_* call: the stale mirror faults, the handler downloads E and B"}
     # strict host-buffer round trip
     lib.zpic_b200_set_option(b"coherent", 1)
     lib.sim_iter(C.byref(sim))
@@ -744,6 +773,8 @@ def main():
     ap.add_argument("--lwfa-ny", type=int, default=1024, dest="lwfa_ny")
     ap.add_argument("--kh-n", type=int, default=8192, dest="kh_n")
     ap.add_argument("--no-check", action="store_true", dest="no_check", help="N > 1: skip the slab-parity check")
+    ap.add_argument("--init", type=int, default=0, help="device-side initialisation: 2 = the reference random stream "
+                    "(default at N = 1), 1 = counter-based generator (default at N > 1)")
     ap.add_argument("--log2-cells", type=int, default=22, dest="log2_cells", help="em1d: log2 of the cell count")
     ap.add_argument("--ppc1d", type=int, default=256, help="em1d: particles per cell per beam")
     args = ap.parse_args()

@@ -94,3 +94,87 @@ def test_window_run_with_a_growing_population(ours, ref):
     assert a.species[0].np > 0
     a.delete()
     b.delete()
+
+
+# ------------------------------------------------------------------ em1d
+
+@pytest.fixture(scope="module")
+def ours1():
+    from zpic_b200 import load
+    return load("em1d")
+
+
+@pytest.fixture(scope="module")
+def ref1():
+    from tests import helpers1d as H1
+    lib = H1.load_ref()
+    if lib is None:
+        pytest.skip("oracle/_ref not built")
+    return lib
+
+
+def test_em1d_raw_buffers_and_in_place_edits(ours1, ref1):
+    """the em1d twin: the two-stream deck read and edited through the raw buffers of the API, no sync calls"""
+    from tests import helpers1d as H1
+    assert ours1.zdev_init(-1) == 0
+    ours1.zpic_b200_set_option(b"lazy", 0)
+    ours1.zpic_b200_set_option(b"coherent", 0)
+    a, b = H1.twostream(ours1, nx=120, ppc=64, n_sort=0), H1.twostream(ref1, nx=120, ppc=64, n_sort=0)
+    # the two beams' currents cancel: E and J are summation-order noise on the scale of one beam (0.2), see
+    # tests/test_gpu_em1d.py::test_twostream_shipped_deck_100_steps
+    for chunk in range(3):
+        a.iter(5)
+        b.iter(5)
+        t = 0.1 * 5 * (chunk + 1)
+        assert np.abs(a.J() - b.J()).max() < 1e-5 * 0.2
+        assert np.abs(a.E() - b.E()).max() < 1e-5 * 0.2 * t
+        assert np.abs(a.B() - b.B()).max() < 1e-5 * 0.2 * t
+        for k in range(2):
+            pa, pb = a.parts(k).copy(), b.parts(k).copy()
+            assert len(pa) == len(pb) and np.array_equal(np.sort(pa["ix"]), np.sort(pb["ix"]))
+    for d in (a, b):
+        d.E()[:, 0] += np.float32(0.01)
+        p = d.parts(0)
+        p["ux"] += np.float32(0.05)
+    a.iter(5)
+    b.iter(5)
+    assert H.rel_l2(a.E(), b.E()) < 1e-5               # now a real field: the 0.01 offset and the kicked beam's current
+    for k in range(2):
+        pa, pb = a.parts(k).copy(), b.parts(k).copy()
+        assert np.array_equal(np.sort(pa["ix"]), np.sort(pb["ix"]))
+        assert abs(float(pa["ux"].astype(np.float64).sum()) - float(pb["ux"].astype(np.float64).sum())) < 1e-3
+    a.delete()
+    b.delete()
+
+
+def test_em1d_cython_module_steps_like_the_reference(ours1, ref1):
+    """the reference's unmodified em1d.pyx linked to the CUDA library (never run on a GPU before): two-stream deck,
+    50 steps, its numpy views against the reference build"""
+    import glob
+    import importlib.util
+    import os
+    from tests import helpers1d as H1
+    hits = glob.glob(os.path.join(H.REPO, "zpic_b200", "cython", "_build", "em1d.*.so"))
+    if not hits:
+        pytest.skip("Cython module not built (python -m zpic_b200.cython.build_modules)")
+    spec = importlib.util.spec_from_file_location("em1d", hits[0])
+    em1d = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em1d)
+    assert ours1.zdev_init(-1) == 0
+    ours1.zpic_b200_set_option(b"lazy", 0)
+    ours1.zpic_b200_set_option(b"coherent", 0)
+    nx, box = 120, float(np.float32(4 * np.pi))
+    sp = [em1d.Species("right", -1.0, 64, ufl=[0.2, 0.0, 0.0], uth=[0.001, 0.001, 0.001], n_sort=0),
+          em1d.Species("left", -1.0, 64, ufl=[-0.2, 0.0, 0.0], uth=[0.001, 0.001, 0.001], n_sort=0)]
+    sim = em1d.Simulation(nx, box, 0.1, species=sp)
+    b = H1.twostream(ref1, nx=nx, ppc=64, n_sort=0)
+    for chunk in range(5):
+        for _ in range(10):
+            sim.iter()
+        b.iter(10)
+        got, want = np.asarray(sim.emf.Ex), b.E()[1:-2, 0]
+        assert np.abs(got - want).max() <= 1e-5 * 0.2 * (chunk + 1), chunk      # (cancelling beams: the scale is one beam's)
+        for k in range(2):
+            pa, pb = np.asarray(sp[k].particles), b.parts(k)
+            assert len(pa) == len(pb) and np.array_equal(np.sort(pa["ix"]), np.sort(pb["ix"]))
+    assert sim.n == 50

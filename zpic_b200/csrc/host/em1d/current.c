@@ -9,7 +9,7 @@ void current_new( t_current *current, int nx, float box, float dt )
 	zb_grid_drop_cur(current);
 	current->nx = nx;
 	current->gc[0] = 1; current->gc[1] = 2;           /* reference current.c:33 */
-	current->J_buf = calloc((size_t) nx + 3, sizeof(float3));
+	current->J_buf = zb_guard_alloc(((size_t) nx + 3) * sizeof(float3));
 	if (!current->J_buf) { fprintf(stderr, "(*error*) current_new: out of memory\n"); exit(-1); }
 	current->J = current->J_buf + 1;
 	current->box = box;
@@ -19,12 +19,13 @@ void current_new( t_current *current, int nx, float box, float dt )
 	current->dt = dt;
 	current->bc_type = CURRENT_BC_PERIODIC;
 	zb_grid_of_cur(current, 1);
+	zb_guard_bind_cur(current);
 }
 
 void current_delete( t_current *current )
 {
 	zb_grid_drop_cur(current);
-	free(current->J_buf);
+	zb_guard_free(current->J_buf);
 	current->J_buf = NULL;
 }
 
@@ -33,6 +34,7 @@ void current_zero( t_current *current )
 	zb_grid* e = zb_grid_of_cur(current, 1);
 	zdev_current1d_zero(zb_dev(e));
 	e->j_host_stale = 1;
+	zb_guard_refresh();
 }
 
 void current_update( t_current *current )
@@ -42,6 +44,7 @@ void current_update( t_current *current )
 	                      (int) current->smooth.xtype, current->smooth.xlevel);
 	e->j_host_stale = 1;
 	current->iter++;
+	zb_guard_refresh();
 }
 
 void current_report( const t_current *current, const int jc )
@@ -64,4 +67,5 @@ void current_report( const t_current *current, const int jc )
 	t_zdf_iteration iter = { .name = "ITERATION", .n = current->iter, .t = current->iter * current->dt, .time_units = "1/\\omega_p" };
 	zdf_save_grid(buf, zdf_float32, &info, &iter, "CURRENT");
 	free(buf);
+	zb_guard_refresh();
 }

@@ -19,8 +19,8 @@ void emf_new( t_emf *emf, int nx, float box, const float dt )
 	zb_grid_drop_emf(emf);
 	emf->nx = nx;
 	emf->gc[0] = 1; emf->gc[1] = 2;                     /* reference emf.c:41 */
-	emf->E_buf = calloc((size_t) nx + 3, sizeof(float3));
-	emf->B_buf = calloc((size_t) nx + 3, sizeof(float3));
+	emf->E_buf = zb_guard_alloc(((size_t) nx + 3) * sizeof(float3));       /* guarded mirrors: ../common/zb_guard.h */
+	emf->B_buf = zb_guard_alloc(((size_t) nx + 3) * sizeof(float3));
 	if (!emf->E_buf || !emf->B_buf) { fprintf(stderr, "(*error*) emf_new: out of memory\n"); exit(-1); }
 	emf->E = emf->E_buf + 1;
 	emf->B = emf->B_buf + 1;
@@ -38,15 +38,16 @@ void emf_new( t_emf *emf, int nx, float box, const float dt )
 	emf->B_part = emf->B;
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	e->eb_dev_stale = 0;
+	zb_guard_bind_emf(emf);
 }
 
 void emf_delete( t_emf *emf )
 {
 	zb_grid_drop_emf(emf);
-	free(emf->E_buf); free(emf->B_buf);
+	zb_guard_free(emf->E_buf); zb_guard_free(emf->B_buf);
 	emf->E_buf = emf->B_buf = NULL;
-	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.E_part_buf);
-	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.B_part_buf);
+	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.E_part_buf);
+	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.B_part_buf);
 	emf->E_part = emf->B_part = NULL;
 }
 
@@ -134,8 +135,8 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	zb_emf_to_device(emf);
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	const size_t bytes = ((size_t) emf->nx + 3) * sizeof(float3);
-	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.E_part_buf);
-	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) free(emf->ext_fld.B_part_buf);
+	if (emf->ext_fld.E_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.E_part_buf);
+	if (emf->ext_fld.B_type > EMF_FLD_TYPE_NONE) zb_guard_free(emf->ext_fld.B_part_buf);
 	if ((unsigned) ext_fld->E_type > EMF_FLD_TYPE_CUSTOM || (unsigned) ext_fld->B_type > EMF_FLD_TYPE_CUSTOM) {
 		fprintf(stderr, "Invalid external field type, aborting.\n");
 		exit(-1);
@@ -146,14 +147,14 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	else {
 		emf->ext_fld.E_0 = ext_fld->E_0;
 		emf->ext_fld.E_custom = ext_fld->E_custom; emf->ext_fld.E_custom_data = ext_fld->E_custom_data;
-		emf->ext_fld.E_part_buf = malloc(bytes);
+		emf->ext_fld.E_part_buf = zb_guard_alloc(bytes);
 		emf->E_part = emf->ext_fld.E_part_buf + 1;
 	}
 	if (ext_fld->B_type == EMF_FLD_TYPE_NONE) { emf->B_part = emf->B; emf->ext_fld.B_part_buf = NULL; }
 	else {
 		emf->ext_fld.B_0 = ext_fld->B_0;
 		emf->ext_fld.B_custom = ext_fld->B_custom; emf->ext_fld.B_custom_data = ext_fld->B_custom_data;
-		emf->ext_fld.B_part_buf = malloc(bytes);
+		emf->ext_fld.B_part_buf = zb_guard_alloc(bytes);
 		emf->B_part = emf->ext_fld.B_part_buf + 1;
 	}
 	float e0[3] = { ext_fld->E_0.x, ext_fld->E_0.y, ext_fld->E_0.z };
@@ -165,6 +166,8 @@ void emf_set_ext_fld( t_emf* const emf, t_emf_ext_fld* ext_fld )
 	if (ge || gb) zdev_emf1d_set_ext_grid(zb_dev(e), (const float*) ge, (const float*) gb);
 	free(ge); free(gb);
 	e->part_host_stale = 1;
+	zb_guard_bind_emf(emf);
+	zb_guard_refresh();
 }
 
 /* custom-field callback that reads a table the caller filled (zpic_b200.h; the em1d form: value of cell ix at
@@ -192,6 +195,7 @@ void emf_advance( t_emf *emf, const t_current *current )
 	emf->iter += 1;
 	if (shift) emf->n_move++;
 	if (!zb_opt_lazy()) zdev_sync();
+	zb_guard_refresh();
 	emf_seconds += timer_interval_seconds(t0, timer_ticks());
 }
 
@@ -230,4 +234,5 @@ void emf_report( const t_emf *emf, const char field, const int fc )
 	t_zdf_iteration iter = { .name = "ITERATION", .n = emf->iter, .t = emf->iter * emf->dt, .time_units = "1/\\omega_p" };
 	zdf_save_grid(buf, zdf_float32, &info, &iter, "EMF");
 	free(buf);
+	zb_guard_refresh();
 }

@@ -19,15 +19,32 @@ double   spec_perf( void )  { return (push_count > 0) ? push_seconds / push_coun
 
 /* ------------------------------------------------------------------ injection (host) */
 
-static void grow( t_part** buf, int* np_max, int size )
+/* `mirror`: the buffer is a species' host mirror (a guarded mapping, ../common/zb_guard.h; `keep` particles of it
+   are worth copying), otherwise a scratch buffer from the C allocator */
+static void grow( t_part** buf, int* np_max, int size, const t_species* mirror, int keep )
 {
 	if (size > *np_max) {
 		*np_max = ( size/1024 + 1 ) * 1024;
-		*buf = realloc(*buf, (size_t) *np_max * sizeof(t_part));
+		if (mirror) {
+			*buf = zb_guard_realloc(*buf, (size_t) *np_max * sizeof(t_part), (size_t) keep * sizeof(t_part));
+			zb_guard_bind_spec(mirror, *buf);
+		} else *buf = realloc(*buf, (size_t) *np_max * sizeof(t_part));
 		if (!*buf) { fprintf(stderr, "(*error*) species buffer: out of memory\n"); exit(-1); }
 	}
 }
-void spec_grow_buffer( t_species* spec, const int size ) { grow(&spec->part, &spec->np_max, size); }
+/* room for `size` particles in the mirror; what it holds is NOT preserved (it is about to be overwritten) */
+void zb_spec_reserve( t_species* spec, const int size )
+{
+	if (size <= spec->np_max) return;
+	const long long want = (long long) spec->np_max + spec->np_max / 4;
+	grow(&spec->part, &spec->np_max, (want > size && want < 0x7ffffc00LL) ? (int) want : size, spec, 0);
+}
+void spec_grow_buffer( t_species* spec, const int size )
+{
+	if (size <= spec->np_max) return;
+	zb_spec_to_host(spec);        /* callers append to what the buffer holds (Species.add, em1d.pyx): make it current */
+	grow(&spec->part, &spec->np_max, size, spec, spec->np);
+}
 
 /* upper bound of the particles the profile puts in cells range[0]..range[1]
  * (reference spec_np_inj, em1d/particles.c:147-232) */
@@ -182,7 +199,7 @@ static void draw_momenta( t_species* spec, t_part* part, int first, int last )
 void spec_inject_into( t_species* spec, const int range[], t_part** buf, int* np, int* np_max )
 {
 	const int first = *np;
-	grow(buf, np_max, *np + count_upper_bound(spec, range));
+	grow(buf, np_max, *np + count_upper_bound(spec, range), (buf == &spec->part) ? spec : NULL, *np);
 	*np = place_particles(spec, range, *buf, *np);
 	draw_momenta(spec, *buf, first, *np - 1);
 }
@@ -238,7 +255,7 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc,
 void spec_delete( t_species* spec )
 {
 	zb_spec_drop(spec);
-	free(spec->part);
+	zb_guard_free(spec->part);
 	spec->part = NULL;
 	spec->np = -1;
 }
@@ -253,6 +270,7 @@ void spec_move_window( t_species *spec )
 		const int range[2] = { spec->nx - 1, spec->nx - 1 };
 		spec_inject_into(spec, range, &spec->part, &spec->np, &spec->np_max);
 		zb_spec_of(spec, 1)->dev_stale = 1;
+		zb_guard_refresh();
 	}
 }
 
@@ -295,7 +313,10 @@ void spec_advance( t_species* spec, t_emf* emf, t_current* current )
 		/* the count is taken after the append: the injected column is already in it */
 		spec->np = (np > 0x7fffffffLL) ? 0x7fffffff : (int) np;
 		s->np_seen = spec->np;
+		/* a guarded mirror is filled from inside a fault handler, where the buffer cannot move: make room now */
+		if (zb_guard_enabled() && spec->np > spec->np_max && spec->np < 0x7ff00000) zb_spec_reserve(spec, spec->np);
 	}
+	zb_guard_refresh();
 	push_count += spec->np;
 	push_seconds += timer_interval_seconds(t0, timer_ticks());
 }
@@ -425,4 +446,5 @@ void spec_report( const t_species *spec, const int rep_type, const int pha_nx[],
 	case PHA: report_pha(spec, rep_type, pha_nx, pha_range); break;
 	case PARTICLES: zb_spec_to_host(spec); report_particles(spec); break;
 	}
+	zb_guard_refresh();
 }

@@ -109,6 +109,8 @@ void zb_emf_to_host( const t_emf* cemf ) {
 	t_emf* emf = (t_emf*) cemf;
 	zb_grid* e = zb_grid_of_emf(emf, 0);
 	if (!e) return;
+	zb_guard_set(emf->E_buf, ZB_G_RW); zb_guard_set(emf->B_buf, ZB_G_RW);
+	zb_guard_set(emf->ext_fld.E_part_buf, ZB_G_RW); zb_guard_set(emf->ext_fld.B_part_buf, ZB_G_RW);
 	if (e->eb_host_stale) {
 		zdev_grid1d_download(zb_dev(e), ZDEV_E, (float*) emf->E_buf);
 		zdev_grid1d_download(zb_dev(e), ZDEV_B, (float*) emf->B_buf);
@@ -128,6 +130,7 @@ void zb_emf_to_host( const t_emf* cemf ) {
 }
 void zb_cur_to_host( const t_current* cur ) {
 	zb_grid* e = zb_grid_of_cur(cur, 0);
+	zb_guard_set(cur->J_buf, ZB_G_RW);
 	if (!e || !e->j_host_stale) return;
 	zdev_grid1d_download(zb_dev(e), ZDEV_J, (float*) cur->J_buf);
 	e->j_host_stale = 0;
@@ -149,34 +152,84 @@ void zb_spec_to_device( t_species* spec ) {
 void zb_spec_to_host( const t_species* cspec ) {
 	t_species* spec = (t_species*) cspec;
 	zb_spec* e = zb_spec_of(spec, 0);
+	if (e && e->device_init) zb_spec_to_device(spec);      /* never materialised yet: generate it, then mirror it */
+	zb_guard_set(spec->part, ZB_G_RW);
 	if (!e || !e->host_stale) return;
 	int64_t np = zdev_spec1d_np(zb_spec_dev(e));
-	spec_grow_buffer(spec, (int) np);
+	zb_spec_reserve(spec, (int) np);
 	spec->np = (int) zdev_spec1d_download(zb_spec_dev(e), spec->part, spec->np_max);
 	e->host_stale = 0;
 	e->part_seen = spec->part; e->np_seen = spec->np;
+}
+
+/* ---- guarded mirrors: see csrc/host/em2d/zb_state.c */
+enum { ZB_K_E, ZB_K_B, ZB_K_EPART, ZB_K_BPART, ZB_K_J, ZB_K_PART };
+
+static void guard_fill( void* owner, int kind ) {
+	switch (kind) {
+	case ZB_K_E: case ZB_K_B: case ZB_K_EPART: case ZB_K_BPART: zb_emf_to_host((const t_emf*) owner); break;
+	case ZB_K_J: zb_cur_to_host((const t_current*) owner); break;
+	case ZB_K_PART: zb_spec_to_host((const t_species*) owner); break;
+	}
+	zb_guard_refresh();
+}
+static void guard_dirty( void* owner, int kind ) {
+	if (kind == ZB_K_E || kind == ZB_K_B) { zb_grid* e = zb_grid_of_emf((const t_emf*) owner, 0); if (e) e->eb_dev_stale = 1; }
+	else if (kind == ZB_K_PART) { zb_spec* e = zb_spec_of((const t_species*) owner, 0); if (e) e->dev_stale = 1; }
+}
+void zb_guard_bind_emf( const t_emf* emf ) {
+	zb_guard_bind(emf->E_buf, (void*) emf, ZB_K_E, guard_fill, guard_dirty);
+	zb_guard_bind(emf->B_buf, (void*) emf, ZB_K_B, guard_fill, guard_dirty);
+	zb_guard_bind(emf->ext_fld.E_part_buf, (void*) emf, ZB_K_EPART, guard_fill, guard_dirty);
+	zb_guard_bind(emf->ext_fld.B_part_buf, (void*) emf, ZB_K_BPART, guard_fill, guard_dirty);
+}
+void zb_guard_bind_cur( const t_current* cur ) { zb_guard_bind(cur->J_buf, (void*) cur, ZB_K_J, guard_fill, guard_dirty); }
+void zb_guard_bind_spec( const t_species* spec, void* buf ) { zb_guard_bind(buf, (void*) spec, ZB_K_PART, guard_fill, guard_dirty); }
+
+void zb_guard_refresh( void ) {
+	if (!zb_guard_enabled()) return;
+	for (int i = 0; i < n_grids; i++) {
+		zb_grid* e = &grids[i];
+		if (e->emf) {
+			const int st = e->eb_host_stale ? ZB_G_NONE : (e->eb_dev_stale ? ZB_G_RW : ZB_G_READ);
+			zb_guard_set(e->emf->E_buf, st); zb_guard_set(e->emf->B_buf, st);
+			const int sp = e->part_host_stale ? ZB_G_NONE : ZB_G_READ;
+			if (e->emf->ext_fld.E_type != EMF_FLD_TYPE_NONE) zb_guard_set(e->emf->ext_fld.E_part_buf, sp);
+			if (e->emf->ext_fld.B_type != EMF_FLD_TYPE_NONE) zb_guard_set(e->emf->ext_fld.B_part_buf, sp);
+		}
+		if (e->cur) zb_guard_set(e->cur->J_buf, e->j_host_stale ? ZB_G_NONE : ZB_G_RW);
+	}
+	const int lazy = zb_opt_lazy();
+	for (int i = 0; i < n_specs; i++) {
+		zb_spec* e = &specs[i];
+		if (!e->spec->part) continue;
+		zb_guard_set(e->spec->part, lazy ? ZB_G_RW : (e->host_stale ? ZB_G_NONE : (e->dev_stale ? ZB_G_RW : ZB_G_READ)));
+	}
 }
 
 void zpic_b200_sync_host( t_simulation* sim ) {
 	zb_emf_to_host(&sim->emf);
 	zb_cur_to_host(&sim->current);
 	for (int i = 0; i < sim->n_species; i++) zb_spec_to_host(&sim->species[i]);
+	zb_guard_refresh();
 }
 void zpic_b200_touch_emf( t_emf* emf ) {
 	zb_emf_to_host(emf);
 	zb_grid* e = zb_grid_of_emf(emf, 1);
 	e->eb_dev_stale = 1; e->mur_dev_stale = 1;
+	zb_guard_refresh();
 }
 void zpic_b200_touch_species( t_species* spec ) {
 	zb_spec_to_host(spec);
 	zb_spec_of(spec, 1)->dev_stale = 1;
+	zb_guard_refresh();
 }
 void zpic_b200_touch_host( t_simulation* sim ) {
 	zpic_b200_touch_emf(&sim->emf);
 	for (int i = 0; i < sim->n_species; i++) zpic_b200_touch_species(&sim->species[i]);
 }
-void zpic_b200_sync_species( t_species* spec ) { zb_spec_to_host(spec); }
-void zpic_b200_sync_emf( t_emf* emf ) { zb_emf_to_host(emf); }
-void zpic_b200_sync_current( t_current* cur ) { zb_cur_to_host(cur); }
+void zpic_b200_sync_species( t_species* spec ) { zb_spec_to_host(spec); zb_guard_refresh(); }
+void zpic_b200_sync_emf( t_emf* emf ) { zb_emf_to_host(emf); zb_guard_refresh(); }
+void zpic_b200_sync_current( t_current* cur ) { zb_cur_to_host(cur); zb_guard_refresh(); }
 void* zpic_b200_species_handle( t_species* spec ) { zb_spec_to_device(spec); return zb_spec_dev(zb_spec_of(spec, 1)); }
 void* zpic_b200_grid_handle( t_emf* emf ) { return zb_dev(zb_grid_of_emf(emf, 1)); }

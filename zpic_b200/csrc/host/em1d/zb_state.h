@@ -5,6 +5,7 @@
 
 #include "zpic_dev.h"
 #include "simulation.h"
+#include "../common/zb_guard.h"
 
 typedef struct zb_grid {
 	const t_emf* emf;
@@ -47,5 +48,12 @@ int zb_opt_coherent( void );
 int zb_opt_device_init( void );
 
 void spec_inject_into( t_species* spec, const int range[], t_part** buf, int* np, int* np_max );
+void zb_spec_reserve( t_species* spec, const int size );
+
+/* guarded mirrors (../common/zb_guard.h), as in the em2d layer */
+void zb_guard_bind_emf( const t_emf* emf );
+void zb_guard_bind_cur( const t_current* cur );
+void zb_guard_bind_spec( const t_species* spec, void* buf );
+void zb_guard_refresh( void );
 
 #endif
