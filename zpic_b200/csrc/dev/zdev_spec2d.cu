@@ -1158,6 +1158,12 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
+	// an empty tile (the other half of the box of a half-box species, vacuum ahead of a plasma edge) has nothing to
+	// stage, sort or push: it only reports that it stays empty
+	if (n == 0) {
+		if (threadIdx.x == 0) { mig.np[t] = 0; tile_np_out[t] = 0; }
+		return;
+	}
 
 	// ---- the tile's keys: one bulk copy, in flight while the fields are staged
 	if (threadIdx.x == 0) {
