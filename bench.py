@@ -512,15 +512,23 @@ def run_em1d(args, lib=None):
     dt = np.float32(0.1)
     g = lib.zdev_grid1d_create(n)
     specs = []
+    # initial state: the reference's own for this deck - its random stream (default seeds, em1d/random.c:16-17)
+    # continued on the device through both beams, species after species like spec_new draws them
+    z, w, have, spare = C.c_uint32(67890), C.c_uint32(12345), C.c_int(0), C.c_double(0.0)
+    klo_a, khi_a = np.zeros(n, dtype=np.int32), np.full(n, ppc, dtype=np.int32)
+    klo, khi = klo_a.ctypes.data_as(C.POINTER(C.c_int)), khi_a.ctypes.data_as(C.POINTER(C.c_int))
+    t_init0 = time.perf_counter()
     for k, sign in enumerate((1.0, -1.0)):
         sp = lib.zdev_spec1d_create(n, ppc, 0)
         ufl = (C.c_float * 3)(0.2 * sign, 0, 0)
         uth = (C.c_float * 3)(0.001, 0.001, 0.001)
-        lib.zdev_spec1d_inject_uniform(sp, ppc, ufl, uth, 4321 + k)
+        rc = lib.zdev_spec1d_inject_lattice(sp, ppc, ufl, uth, klo, khi, C.byref(z), C.byref(w), C.byref(have), C.byref(spare))
+        assert rc == 0
         q = np.float32(-1.0) / np.float32(ppc)
         prm = PushParams1D(float(np.float32(0.5 * float(dt) / -1.0)), float(dt / dx), float(q * dx / dt), float(q), 0, 0)
         specs.append((sp, prm))
     lib.zdev_sync()
+    t_init = time.perf_counter() - t_init0
     npart = 2 * n * ppc
 
     def step():
@@ -554,7 +562,8 @@ def run_em1d(args, lib=None):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "em1d two-stream 2^%d cells x %d ppc x 2 beams, periodic (BASELINE configs[4])" % (args.log2_cells, ppc),
                       "particles_per_gpu": npart, "dt": float(dt), "dx": float(dx),
-                      "init": "device-side counter-based thermal+fluid distribution",
+                      "init": "the reference's initial state for this deck and seed, generated on the device from the reference's random stream",
+                      "init_s": round(t_init, 2),
                       "cache": "working set %.1f GB per step >> 126 MB L2, no flush needed" % (npart * 44 / 1e9)},
            "roofline": {"bound": "hbm", "kernel": "k_push1d", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": 40.0,

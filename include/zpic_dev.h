@@ -118,8 +118,7 @@ void zdev_emf_set_ext_grid( zdev_grid2d* g, const float* host_ext_e, const float
 void zdev_emf_advance( zdev_grid2d* g, zdev_grid2d* g_cur, float dt, float dx, float dy,
                        int moving_window, int shift_window );
 /* The three stencils of emf_advance run as ONE kernel by default (60 B instead of 132 B of traffic per cell,
- * bit-identical results); 0 selects the three separate kernels below, 2 an experimental form of the one-pass
- * kernel that classifies its tiles as interior / rim once ($ZPIC_FUSED_YEE=0 / 2 do the same). */
+ * bit-identical results); 0 selects the three separate kernels below ($ZPIC_FUSED_YEE=0 does the same). */
 void zdev_yee_set_fused( int on );
 /* pieces, for kernel-level parity tests */
 void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c:500-522 */
@@ -315,6 +314,11 @@ int64_t zdev_spec1d_np( zdev_spec1d* s );
 /* slots allocated per buffer (grows when tiles fill up) */
 int64_t zdev_spec1d_capacity( zdev_spec1d* s );
 void zdev_spec1d_inject_uniform( zdev_spec1d* s, int ppc, const float ufl[3], const float uth[3], uint64_t seed );
+/* the 1-D twin of zdev_spec2d_inject_lattice: UNIFORM / STEP / SLAB plasma (em1d/particles.c:245-262) generated on
+ * the device on the reference random stream; the in-cell positions klo[i] <= k < khi[i] of cell i carry plasma */
+int zdev_spec1d_inject_lattice( zdev_spec1d* s, int ppc, const float ufl[3], const float uth[3],
+                                const int* klo, const int* khi,
+                                uint32_t* z, uint32_t* w, int* have_spare, double* spare );
 /* spec_advance minus host bookkeeping (em1d/particles.c:936-1062): interpolate_fld (:864-886), Boris,
  * dep_current_zamb (:707-779), boundaries / window shift, per-step re-binning */
 void zdev_spec1d_advance( zdev_spec1d* s, zdev_grid1d* g, zdev_grid1d* g_cur, const zdev_push1d_params* p );

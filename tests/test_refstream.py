@@ -180,3 +180,84 @@ def test_warm_plasma_in_a_non_square_box_takes_the_host_injector(ours, ref):
         b.delete()
     finally:
         ours.zpic_b200_set_option(b"device_init", 0)
+
+
+# ------------------------------------------------------------------ em1d
+
+@pytest.fixture(scope="module")
+def ours1():
+    from zpic_b200 import load
+    return load("em1d")
+
+
+@pytest.fixture(scope="module")
+def ref1():
+    from tests import helpers1d as H1
+    lib = H1.load_ref()
+    if lib is None:
+        pytest.skip("oracle/_ref not built")
+    return lib
+
+
+@pytest.mark.gpu
+def test_em1d_twostream_beams_generated_on_the_device_equal_the_reference(ours1, ref1):
+    """em1d/input/twostream.c: both beams (2 x 30 000 warm particles) bit-identical to the reference's host injector,
+    stream position equal afterwards, still bit-identical after one step"""
+    from tests import helpers1d as H1
+    assert ours1.zdev_init(-1) == 0
+    ours1.zpic_b200_set_option(b"device_init", 2)
+    ours1.zpic_b200_set_option(b"lazy", 0)
+    try:
+        a, b = H1.twostream(ours1, nx=120, ppc=250, n_sort=0), H1.twostream(ref1, nx=120, ppc=250, n_sort=0)
+        for k in range(2):
+            assert a.species[k].np == b.species[k].np and not a.species[k].part
+        ours1.rand_uint32.restype = ref1.rand_uint32.restype = C.c_uint32
+        assert ours1.rand_uint32() == ref1.rand_uint32()
+        a.sync()
+        order = ["ix", "x", "ux", "uy", "uz"]
+        for k in range(2):
+            pa, pb = np.sort(a.parts(k).copy(), order=order), np.sort(b.parts(k).copy(), order=order)
+            assert np.array_equal(pa.view(np.uint8), pb.view(np.uint8))
+        a.iter(1)
+        b.iter(1)
+        a.sync()
+        for k in range(2):
+            pa, pb = np.sort(a.parts(k).copy(), order=order), np.sort(b.parts(k).copy(), order=order)
+            assert np.array_equal(pa.view(np.uint8), pb.view(np.uint8))
+        a.delete()
+        b.delete()
+    finally:
+        ours1.zpic_b200_set_option(b"device_init", 0)
+
+
+@pytest.mark.gpu
+def test_em1d_clipped_plasma_under_a_moving_window(ours1, ref1):
+    """em1d/input/movwindow.c pattern: a STEP plasma that starts inside a cell, window columns from the host injector"""
+    from tests import helpers1d as H1
+    from zpic_b200 import abi_em1d as A1
+    assert ours1.zdev_init(-1) == 0
+    ours1.zpic_b200_set_option(b"device_init", 2)
+    ours1.zpic_b200_set_option(b"lazy", 0)
+    try:
+        decks = []
+        for lib in (ours1, ref1):
+            sp = dict(name="electrons", m_q=-1.0, ppc=32, density=dict(type=A1.STEP, start=20.013), n_sort=0)
+            d = H1.Deck1D(lib, 512, 41.0, 0.07, [sp], tmax=300.0, ndump=50)
+            d.add_laser(start=25.0, fwhm=7.0, a0=0.5, omega0=10.0, polarization=np.pi / 2)
+            d.set_moving_window()
+            decks.append(d)
+        a, b = decks
+        assert a.species[0].np == b.species[0].np and not a.species[0].part
+        a.iter(60)
+        b.iter(60)
+        a.sync()
+        assert a.species[0].np == b.species[0].np and a.sim.emf.n_move == b.sim.emf.n_move > 3
+        pa, pb = np.sort(a.parts(0).copy(), order=["ix", "x", "ux"]), np.sort(b.parts(0).copy(), order=["ix", "x", "ux"])
+        assert np.array_equal(pa["ix"], pb["ix"])
+        assert H.rel_l2(a.E(), b.E()) < 1e-5
+        ours1.rand_uint32.restype = ref1.rand_uint32.restype = C.c_uint32
+        assert ours1.rand_uint32() == ref1.rand_uint32()
+        a.delete()
+        b.delete()
+    finally:
+        ours1.zpic_b200_set_option(b"device_init", 0)

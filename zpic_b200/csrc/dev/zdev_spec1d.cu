@@ -500,6 +500,89 @@ extern "C" void zdev_spec1d_inject_uniform(zdev_spec1d* s, int ppc, const float 
 	s->ids_valid = s->track_ids && np < 0x7fffffff;
 }
 
+// ---- the same population as the reference's host injector, on the reference random stream (zdev_refrng.cu; the
+// 1-D twin of k_inject_lattice in zdev_spec2d.cu).  One thread per cell of [i0, i1): the in-cell positions
+// klo <= k < khi of cell i carry plasma (STEP / SLAB clip them, em1d/particles.c:245-262), pre[] = particles in
+// the cells before i; th[] holds the three thermal components of the band's particles in injection order (null:
+// a cold plasma).  Cell means are summed in particle order like spec_set_u does (em1d/particles.c:88-130).
+__global__ void k1_inject_lattice(buf1d p, const int64_t* __restrict__ off, int* tile_np, int nx, int TX, int ppc, f3 ufl,
+                                  const int* __restrict__ klo, const int* __restrict__ khi, const int64_t* __restrict__ pre,
+                                  int i0, int i1, const float* __restrict__ th) {
+	const int cell = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (cell >= i1) return;
+	const int t = cell / TX, lc = cell - t * TX, gt0 = t * TX;
+	const int cxw = (t + 1) * TX <= nx ? TX : nx - t * TX;
+	if (lc == 0) tile_np[t] = (int) (pre[gt0 + cxw] - pre[gt0]);
+	const int lo = klo[cell], cnt = khi[cell] - lo;
+	if (cnt <= 0) return;
+	const int64_t base = off[t] + (pre[cell] - pre[gt0]);
+	const float* q = th ? th + 3 * (pre[cell] - pre[i0]) : nullptr;
+	float sx = 0, sy = 0, sz = 0;
+	if (q) {
+		for (int k = 0; k < cnt; k++) { sx += q[3 * k]; sy += q[3 * k + 1]; sz += q[3 * k + 2]; }
+		const float norm = 1.0f / cnt;
+		sx *= norm; sy *= norm; sz *= norm;
+	}
+	for (int k = 0; k < cnt; k++) {
+		const float a = q ? q[3 * k] : 0.0f, b = q ? q[3 * k + 1] : 0.0f, c = q ? q[3 * k + 2] : 0.0f;
+		rec20 v = { (float) ((lo + k + 0.5) / ppc), a + (ufl.x - sx), b + (ufl.y - sy), c + (ufl.z - sz), lc };
+		rec1_store(p.rec, base + k, v); p.key[base + k] = key1_of(lc, v.x);
+		if (p.tag) p.tag[base + k] = (int) (pre[cell] + k);
+	}
+}
+
+extern "C" int zdev_spec1d_inject_lattice(zdev_spec1d* s, int ppc, const float ufl[3], const float uth[3],
+                                          const int* klo, const int* khi,
+                                          uint32_t* z, uint32_t* w, int* have_spare, double* spare) {
+	{ uint32_t zz = *z, ww = *w; if (zdev_ref_jump(&zz, &ww, 0)) return 1; }
+	const int nx = s->nx;
+	std::vector<int64_t> pre(nx + 1, 0);
+	for (int i = 0; i < nx; i++) pre[i + 1] = pre[i] + std::max(khi[i] - klo[i], 0);
+	const int64_t total = pre[nx];
+	std::vector<int> cnt(s->ntiles);
+	for (int t = 0; t < s->ntiles; t++) {
+		const int cx = (t + 1) * s->TX <= nx ? s->TX : nx - t * s->TX;
+		cnt[t] = (int) (pre[t * s->TX + cx] - pre[t * s->TX]);
+	}
+	layout(s, cnt, total);
+	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
+	int *d_lo, *d_hi; int64_t* d_pre;
+	ZDEV_CHECK(cudaMalloc(&d_lo, (size_t) nx * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&d_hi, (size_t) nx * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&d_pre, (size_t) (nx + 1) * sizeof(int64_t)));
+	ZDEV_CHECK(cudaMemcpyAsync(d_lo, klo, (size_t) nx * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaMemcpyAsync(d_hi, khi, (size_t) nx * sizeof(int), cudaMemcpyHostToDevice, zdev_strm));
+	ZDEV_CHECK(cudaMemcpyAsync(d_pre, pre.data(), (size_t) (nx + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
+	const f3 fl = {ufl[0], ufl[1], ufl[2]};
+	const bool cold = uth[0] == 0.0f && uth[1] == 0.0f && uth[2] == 0.0f;
+	if (cold || total == 0) {
+		zdev_ref_normals(z, w, have_spare, spare, 3 * total, uth, nullptr);
+		if (total > 0)
+			ZDEV_LAUNCH(k1_inject_lattice, zdev_div_up(nx, 128), 128, 0, s->p, s->tile_off, s->tile_np, nx, s->TX, ppc, fl,
+			            d_lo, d_hi, d_pre, 0, nx, (const float*) nullptr);
+	} else {
+		// bands of cells holding at most 2^26 particles: their thermal components are generated, then placed
+		const int64_t band = (int64_t) 1 << 26;
+		float* d_th;
+		ZDEV_CHECK(cudaMalloc(&d_th, (size_t) std::min<int64_t>(total, band + ppc) * 3 * sizeof(float)));
+		for (int i0 = 0; i0 < nx; ) {
+			int i1 = i0 + 1;
+			while (i1 < nx && pre[i1 + 1] - pre[i0] <= band) i1++;
+			zdev_ref_normals(z, w, have_spare, spare, 3 * (pre[i1] - pre[i0]), uth, d_th);
+			ZDEV_LAUNCH(k1_inject_lattice, zdev_div_up(i1 - i0, 128), 128, 0, s->p, s->tile_off, s->tile_np, nx, s->TX, ppc, fl,
+			            d_lo, d_hi, d_pre, i0, i1, (const float*) d_th);
+			i0 = i1;
+		}
+		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+		ZDEV_CHECK(cudaFree(d_th));
+	}
+	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
+	ZDEV_CHECK(cudaFree(d_lo)); ZDEV_CHECK(cudaFree(d_hi)); ZDEV_CHECK(cudaFree(d_pre));
+	s->np_host = total;
+	s->ids_valid = s->track_ids && total < 0x7fffffff;
+	return 0;
+}
+
 // ------------------------------------------------------------------ the push
 
 // one queued remainder of a cell-crossing move (a single in-cell segment, already in the frame of the cell

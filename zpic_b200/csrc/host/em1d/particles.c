@@ -8,6 +8,7 @@
 #include <math.h>
 #include "zb_state.h"
 #include "random.h"
+#include "../common/zb_rand.h"
 #include "timer.h"
 #include "zdf.h"
 
@@ -204,6 +205,41 @@ void spec_inject_into( t_species* spec, const int range[], t_part** buf, int* np
 	draw_momenta(spec, *buf, first, *np - 1);
 }
 
+/* Lattice profiles (UNIFORM / STEP / SLAB): the in-cell positions k with lo[i] <= k < hi[i] of cell i carry plasma -
+   the clip of place_particles() evaluated with the same float expressions.  Returns the particle count, or -1 when
+   the reference-stream device injector does not cover the profile (RAMP, CUSTOM). */
+static long long lattice_cells( const t_species* spec, int** lo_out, int** hi_out )
+{
+	const enum density_type type = spec->density.type;
+	if (type != UNIFORM && type != STEP && type != SLAB) return -1;
+	const int nx = spec->nx, npc = spec->ppc;
+	float* pos = malloc((size_t) npc * sizeof(float));
+	for (int i = 0; i < npc; i++) pos[i] = ( i + 0.5 ) / npc;
+	float lo = 0, hi = 0;
+	if (type == STEP || type == SLAB) lo = spec->density.start / spec->dx - spec->n_move;
+	if (type == SLAB) hi = spec->density.end / spec->dx - spec->n_move;
+	int* klo = malloc((size_t) nx * sizeof(int)); int* khi = malloc((size_t) nx * sizeof(int));
+	long long total = 0;
+	for (int i = 0; i < nx; i++) {
+		int a = 0, b = npc;
+		if (type != UNIFORM) {
+			a = npc; b = 0;
+			for (int k = 0; k < npc; k++) {
+				int in = 1;
+				if (type == STEP) in = ( i + pos[k] > lo );
+				if (type == SLAB) in = ( i + pos[k] > lo && i + pos[k] < hi );
+				if (in) { if (k < a) a = k; b = k + 1; }
+			}
+			if (b <= a) { a = 0; b = 0; }
+		}
+		klo[i] = a; khi[i] = b;
+		total += b - a;
+	}
+	free(pos);
+	*lo_out = klo; *hi_out = khi;
+	return total;
+}
+
 void spec_new( t_species* spec, char name[], const float m_q, const int ppc,
                const float *ufl, const float *uth,
                const int nx, float box, const float dt, t_density* density )
@@ -239,7 +275,29 @@ void spec_new( t_species* spec, char name[], const float m_q, const int ppc,
 	spec->n_move = 0;
 	spec->np = 0;
 	const int range[2] = { 0, nx - 1 };
-	if (zb_opt_device_init() && spec->density.type == UNIFORM) {
+	int *lat_lo = NULL, *lat_hi = NULL;
+	long long total2 = -1;
+	if (zb_opt_device_init() == 2) total2 = lattice_cells(spec, &lat_lo, &lat_hi);
+	if (total2 >= 0) {
+		/* device_init = 2: the reference's own initial population on the reference's random stream, generated on the
+		   device at the first step; the host stream is moved past its 3 deviates per particle now (see the em2d twin) */
+		zb_spec* e = zb_spec_of(spec, 1);
+		zb_rand_get_state(&e->rs_z, &e->rs_w, &e->rs_have, &e->rs_spare);
+		uint32_t z = e->rs_z, w = e->rs_w; int have = e->rs_have; double spare = e->rs_spare;
+		if (zdev_ref_normals(&z, &w, &have, &spare, 3 * total2, spec->uth, NULL) == 0) {
+			zb_rand_set_state(z, w, have, spare);
+			e->device_init = 2;
+			e->lat_lo = lat_lo; e->lat_hi = lat_hi;
+			spec->np = (total2 > 0x7fffffffLL) ? 0x7fffffff : (int) total2;
+			spec->density.total_np_inj += total2;
+		} else {
+			free(lat_lo); free(lat_hi);
+			total2 = -1;
+		}
+	}
+	if (total2 >= 0) {
+		/* done above */
+	} else if (zb_opt_device_init() == 1 && spec->density.type == UNIFORM) {
 		zb_spec* e = zb_spec_of(spec, 1);
 		e->device_init = 1;
 		e->device_seed = ((uint64_t) rand_uint32() << 32) | rand_uint32();

@@ -16,7 +16,10 @@ static int env_flag( const char* name ) { const char* e = getenv(name); return e
 int zb_opt_lazy( void ) { if (opt_lazy < 0) opt_lazy = env_flag("ZPIC_LAZY"); return opt_lazy; }
 int zb_opt_track_ids( void ) { if (opt_ids < 0) opt_ids = env_flag("ZPIC_TRACK_IDS"); return opt_ids; }
 int zb_opt_coherent( void ) { if (opt_coherent < 0) opt_coherent = env_flag("ZPIC_COHERENT"); return opt_coherent; }
-int zb_opt_device_init( void ) { if (opt_devinit < 0) opt_devinit = env_flag("ZPIC_DEVICE_INIT"); return opt_devinit; }
+int zb_opt_device_init( void ) {
+	if (opt_devinit < 0) { const char* e = getenv("ZPIC_DEVICE_INIT"); opt_devinit = e ? atoi(e) : 0; }
+	return opt_devinit;
+}
 
 void zpic_b200_set_option( const char* name, int value ) {
 	if (!strcmp(name, "lazy")) opt_lazy = value;
@@ -87,6 +90,7 @@ void zb_spec_drop( const t_species* spec ) {
 	zb_spec* e = zb_spec_of(spec, 0);
 	if (!e) return;
 	if (e->d) zdev_spec1d_destroy(e->d);
+	free(e->lat_lo); free(e->lat_hi);
 	*e = specs[--n_specs];
 }
 
@@ -137,6 +141,17 @@ void zb_cur_to_host( const t_current* cur ) {
 }
 void zb_spec_to_device( t_species* spec ) {
 	zb_spec* e = zb_spec_of(spec, 1);
+	if (e->device_init == 2) {
+		/* the reference's population, generated on the device from the state the stream had at spec_new */
+		uint32_t z = e->rs_z, w = e->rs_w; int have = e->rs_have; double spare = e->rs_spare;
+		if (zdev_spec1d_inject_lattice(zb_spec_dev(e), spec->ppc, spec->ufl, spec->uth, e->lat_lo, e->lat_hi, &z, &w, &have, &spare)) {
+			fprintf(stderr, "(*error*) zpic-b200: device-side injection lost the random stream\n");
+			exit(-1);
+		}
+		free(e->lat_lo); free(e->lat_hi); e->lat_lo = e->lat_hi = NULL;
+		e->device_init = 0; e->dev_stale = 0; e->host_stale = 1;
+		return;
+	}
 	if (e->device_init) {
 		zdev_spec1d_inject_uniform(zb_spec_dev(e), spec->ppc, spec->ufl, spec->uth, e->device_seed);
 		e->device_init = 0; e->dev_stale = 0; e->host_stale = 1;

@@ -19,8 +19,10 @@ typedef struct zb_grid {
 typedef struct zb_spec {
 	const t_species* spec;
 	zdev_spec1d* d;
-	int device_init;
+	int device_init;           /* generated on the device at first use: 1 counter-based, 2 the reference random stream */
 	uint64_t device_seed;
+	int* lat_lo; int* lat_hi;  /* 2: in-cell positions [lo, hi) of every cell that carry plasma */
+	uint32_t rs_z, rs_w; int rs_have; double rs_spare;   /* 2: the stream's state where this species' draws begin */
 	int dev_stale, host_stale;
 	const t_part* part_seen;
 	int np_seen;
