@@ -41,7 +41,7 @@ __host__ __device__ __forceinline__ unsigned short key1_of(int cell, float x) {
 	b = b < 0 ? 0 : (b > SUB1 - 1 ? SUB1 - 1 : b);
 	return (unsigned short) (cell * SUB1 + b);
 }
-#define REC1_CHUNK_WORDS 160          // 5 rows x 32 slots
+#define REC1_CHUNK_WORDS 128          // 4 rows x 32 slots: x, ux, uy, uz (the cell is in the key)
 
 struct buf1d {
 	float* rec;              // chunked records
@@ -53,14 +53,16 @@ struct buf1d {
 struct mig1d { part1_aos* rec; int* tag; int* np; int div; };
 
 __device__ __forceinline__ size_t rec1_word(int64_t slot) { return (size_t) (slot >> 5) * REC1_CHUNK_WORDS + (size_t) (slot & 31); }
-__device__ __forceinline__ rec20 rec1_load(const float* __restrict__ rec, int64_t slot) {
+// the record of a LIVE slot; its cell is carried by its sort key (key1_of)
+__device__ __forceinline__ rec20 rec1_load(const float* __restrict__ rec, int64_t slot, unsigned short key) {
 	const float* q = rec + rec1_word(slot);
-	rec20 r; r.x = q[0]; r.ux = q[32]; r.uy = q[64]; r.uz = q[96]; r.cell = __float_as_int(q[128]);
+	rec20 r; r.x = q[0]; r.ux = q[32]; r.uy = q[64]; r.uz = q[96]; r.cell = (int) key / SUB1;
 	return r;
 }
+// (the caller stores the key: key1_of(r.cell, r.x))
 __device__ __forceinline__ void rec1_store(float* __restrict__ rec, int64_t slot, const rec20& r) {
 	float* q = rec + rec1_word(slot);
-	q[0] = r.x; q[32] = r.ux; q[64] = r.uy; q[96] = r.uz; q[128] = __int_as_float(r.cell);
+	q[0] = r.x; q[32] = r.ux; q[64] = r.uy; q[96] = r.uz;
 }
 
 struct ctl1d {
@@ -87,9 +89,6 @@ struct zdev_spec1d {
 	int ids_valid;
 	std::vector<int64_t>* h_off;
 	std::vector<cudaEvent_t>* ev; int ev_next, ev_pending; double push_ms; int64_t push_launches;
-	// PUSH1_PRESORTED build variant: perm[] and the live counts come from k_sort1d (see there)
-	unsigned short* gperm; int64_t gperm_cap;
-	int* tile_nlive;
 };
 
 static const int P1_THREADS = 256;
@@ -101,7 +100,7 @@ static void buf_alloc(buf1d& b, int64_t n, int with_tag) {
 	size_t nn = (size_t) (n > 0 ? n : 1);
 	memset(&b, 0, sizeof b);
 	if (nn & 31) nn = (nn + 31) & ~(size_t) 31;      // whole chunks
-	ZDEV_CHECK(cudaMalloc(&b.rec, nn * 20));
+	ZDEV_CHECK(cudaMalloc(&b.rec, nn * 16));
 	ZDEV_CHECK(cudaMalloc(&b.key, nn * 2));
 	if (with_tag) ZDEV_CHECK(cudaMalloc(&b.tag, nn * 4));
 }
@@ -151,7 +150,6 @@ extern "C" void zdev_spec1d_destroy(zdev_spec1d* s) {
 	ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 	free_particles(s);
 	cudaFree(s->tile_off); cudaFree(s->tile_np); cudaFree(s->tile_np_q); cudaFree(s->ctl);
-	cudaFree(s->gperm); cudaFree(s->tile_nlive);
 	if (s->ev) { for (auto& e : *s->ev) cudaEventDestroy(e); delete s->ev; }
 	delete s->h_off;
 	delete s;
@@ -311,7 +309,7 @@ __global__ void k1_gather(buf1d p, const int64_t* __restrict__ off, const int* _
 		if ((threadIdx.x & 31) == 0 && m) wbase = atomicAdd(&s_run, __popc(m));
 		wbase = __shfl_sync(0xffffffffu, wbase, 0);
 		if (live) {
-			rec20 v = rec1_load(p.rec, b + k);
+			rec20 v = rec1_load(p.rec, b + k, p.key[b + k]);
 			part1_aos r = { t * TX + v.cell, v.x, v.ux, v.uy, v.uz };
 			int64_t d = by_tag ? (int64_t) p.tag[b + k] : o + wbase + __popc(m & ((1u << (threadIdx.x & 31)) - 1));
 			out[d] = r;
@@ -371,7 +369,7 @@ __global__ void k1_relayout(buf1d src, const int64_t* __restrict__ off_src, buf1
 		const unsigned short key = src.key[a + k];
 		dst.key[b + k] = key;
 		if (key != KEY1_EMPTY) {
-			rec1_store(dst.rec, b + k, rec1_load(src.rec, a + k));
+			rec1_store(dst.rec, b + k, rec1_load(src.rec, a + k, key));
 			if (src.tag) dst.tag[b + k] = src.tag[a + k];
 		}
 	}
@@ -671,95 +669,18 @@ __device__ __forceinline__ void flush_cell1(const float acc[5], int cell, int la
 
 struct pair1_rec { f2 x, ux, uy, uz; int ca, cb, ta, tb; };
 
-#ifdef PUSH1_PRESORTED
-// ---- PUSH1_PRESORTED build variant (unmeasured; the em1d twin of PUSH_PRESORTED in zdev_spec2d.cu): phase A of
-// k_push1d as a kernel of its own - its 16 KB of counters and its barriers leave the push kernel, more CTAs of
-// the light sort kernel share an SM - handing perm[] (16-bit slot indices in key order) and the live count of
-// every tile to the push kernel through global memory.
-__global__ void __launch_bounds__(P1_THREADS)
-k_sort1d(buf1d A, const int64_t* __restrict__ tile_off, const int* __restrict__ tile_np,
-         unsigned short* __restrict__ gperm, int* __restrict__ tile_nlive, int TX, unsigned smem_keys) {
-	extern __shared__ __align__(16) unsigned char s_dyn[];
-	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
-	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_keys);
-	__shared__ int s_cnt[512 * SUB1], s_cur[512 * SUB1];
-	__shared__ int s_wsum[P1_WARPS];
-	__shared__ __align__(8) unsigned long long s_bar;
-	const int NK = TX * SUB1;
-	const int t = blockIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int n = tile_np[t];
-	const int64_t base = tile_off[t];
-	if (threadIdx.x == 0) {
-		mbar_init(&s_bar, 1);
-		if (n > 0) bulk_load(s_dyn, A.key + base, (unsigned) ((n * 2 + 15) & ~15), &s_bar);
-	}
-	for (int k = threadIdx.x; k < NK; k += P1_THREADS) s_cnt[k] = 0;
-	__syncthreads();
-	if (n > 0) mbar_wait(&s_bar, 0);
-	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
-	const int ws = (S + P1_WARPS - 1) / P1_WARPS;
-	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
-	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
-	#pragma unroll 4
-	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
-			if (c0 != KEY1_EMPTY) atomicAdd(&s_cnt[c0], 1);
-			if (c1 != KEY1_EMPTY) atomicAdd(&s_cnt[c1], 1);
-		}
-	}
-	__syncthreads();
-	int nlive;
-	{
-		constexpr int PER = 2 * SUB1;
-		const int i0 = PER * threadIdx.x;
-		int c[PER], v = 0;
-		#pragma unroll
-		for (int k = 0; k < PER; k++) { c[k] = (i0 + k < NK) ? s_cnt[i0 + k] : 0; v += c[k]; }
-		int incl = v;
-		for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += u; }
-		if (lane == 31) s_wsum[warp] = incl;
-		__syncthreads();
-		int woff = 0, tot = 0;
-		#pragma unroll
-		for (int w = 0; w < P1_WARPS; w++) { int cw = s_wsum[w]; woff += (w < warp) ? cw : 0; tot += cw; }
-		int run = woff + incl - v;
-		#pragma unroll
-		for (int k = 0; k < PER; k++) { if (i0 + k < NK) s_cur[i0 + k] = run; run += c[k]; }
-		nlive = tot;
-		__syncthreads();
-	}
-	#pragma unroll 4
-	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
-			if (c0 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
-			if (c1 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
-		}
-	}
-	__syncthreads();
-	{
-		const unsigned* src = reinterpret_cast<const unsigned*>(s_perm);
-		unsigned* dst = reinterpret_cast<unsigned*>(gperm + base);
-		for (int k = threadIdx.x; k < (nlive + 1) / 2; k += P1_THREADS) dst[k] = src[k];
-	}
-	if (threadIdx.x == 0) tile_nlive[t] = nlive;
-}
-#endif
 
 // dynamic shared memory of k_push1d: [keys during the sort | field pairs + queues afterwards][perm][raw planes]
 static size_t push1_smem_front(int TX, int max_cap) {
-	size_t late = (size_t) 6 * (TX + 2) * 8 + (size_t) P1_WARPS * XQ1_CAP * sizeof(xq1_entry), keys = ((size_t) max_cap * 2 + 15) & ~(size_t) 15;
+	// + 128 keys: the sort walks 64 * S >= n keys and the ones past n are padded with KEY1_EMPTY in place
+	size_t late = (size_t) 6 * (TX + 2) * 8 + (size_t) P1_WARPS * XQ1_CAP * sizeof(xq1_entry), keys = ((size_t) (max_cap + 128) * 2 + 15) & ~(size_t) 15;
 	late = (late + 15) & ~(size_t) 15;
 	return late > keys ? late : keys;
 }
+// perm[] = 32-bit (key << 16 | slot) entries; the holes are sorted too (behind the live entries)
+static size_t push1_smem_perm(int max_cap) { return (((size_t) (max_cap + 128) * 4 + 15) & ~(size_t) 15); }
 static size_t push1_smem_bytes(int TX, int max_cap) {
-	return push1_smem_front(TX, max_cap) + (((size_t) max_cap * 2 + 15) & ~(size_t) 15) + (size_t) 6 * (TX + 2) * 4;
+	return push1_smem_front(TX, max_cap) + push1_smem_perm(max_cap) + (size_t) 6 * (TX + 2) * 4;
 }
 
 template <bool TAGS>
@@ -768,22 +689,17 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
          mig1d mig, ctl1d* __restrict__ ctl,
          const f3* __restrict__ E, const f3* __restrict__ B, f3* __restrict__ J, int nx, int TX,
          zdev_push1d_params prm, unsigned smem_front, unsigned smem_perm
-#ifdef PUSH1_PRESORTED
-         , const unsigned short* __restrict__ gperm, const int* __restrict__ tile_nlive
-#endif
          ) {
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	const int PL = TX + 2;
 	f2* const s_f2 = reinterpret_cast<f2*>(s_dyn);                     // 6 planes of (F[k], F[k+1])
 	xq1_entry* const s_xq = reinterpret_cast<xq1_entry*>(s_dyn + 6 * PL * 8);
 	const unsigned short* const s_key = reinterpret_cast<const unsigned short*>(s_dyn);
-	unsigned short* const s_perm = reinterpret_cast<unsigned short*>(s_dyn + smem_front);
+	unsigned* const s_perm = reinterpret_cast<unsigned*>(s_dyn + smem_front);
 	float* const s_raw = reinterpret_cast<float*>(s_dyn + smem_front + smem_perm);
-#ifndef PUSH1_PRESORTED
-	__shared__ int s_cnt[512 * SUB1], s_cur[512 * SUB1];
+	__shared__ int s_cnt[512 * SUB1 + 1], s_cur[512 * SUB1 + 1];       // bin NK: the holes
 	const int NK = TX * SUB1;                            // sort keys of the tile
 	__shared__ int s_wsum[P1_WARPS];
-#endif
 	__shared__ int s_nmig, s_done;
 	__shared__ __align__(8) unsigned long long s_bar;
 
@@ -792,22 +708,6 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int n = tile_np[t];
 	const int64_t base = tile_off[t];
 
-#ifdef PUSH1_PRESORTED
-	// ---- perm[] was built by k_sort1d: one bulk copy into its place, in flight while the fields are staged
-	const int nlive = tile_nlive[t];
-	if (threadIdx.x == 0) {
-		s_nmig = 0; s_done = 0;
-		mbar_init(&s_bar, 1);
-		if (nlive > 0) bulk_load(s_perm, gperm + base, (unsigned) ((nlive * 2 + 15) & ~15), &s_bar);
-	}
-	for (int k = threadIdx.x; k < cx + 2; k += P1_THREADS) {        // cells x0-1 .. x0+cx
-		f3 e = E[x0 + k], b = B[x0 + k];
-		s_raw[k] = e.x; s_raw[k + PL] = e.y; s_raw[k + 2 * PL] = e.z;
-		s_raw[k + 3 * PL] = b.x; s_raw[k + 4 * PL] = b.y; s_raw[k + 5 * PL] = b.z;
-	}
-	__syncthreads();
-	(void) s_key; (void) n; (void) warp;
-#else
 	if (threadIdx.x == 0) {
 		s_nmig = 0; s_done = 0;
 		mbar_init(&s_bar, 1);
@@ -818,7 +718,7 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_raw[k] = e.x; s_raw[k + PL] = e.y; s_raw[k + 2 * PL] = e.z;
 		s_raw[k + 3 * PL] = b.x; s_raw[k + 4 * PL] = b.y; s_raw[k + 5 * PL] = b.z;
 	}
-	for (int k = threadIdx.x; k < NK; k += P1_THREADS) s_cnt[k] = 0;
+	for (int k = threadIdx.x; k <= NK; k += P1_THREADS) s_cnt[k] = 0;
 	__syncthreads();
 	if (n > 0) mbar_wait(&s_bar, 0);
 
@@ -828,19 +728,22 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	// Lane l owns the words [l*S, (l+1)*S) of the key array (S odd: the lanes of a warp read distinct banks
 	// and sit S*2 keys apart, i.e. in different cells as long as a cell holds fewer particles than that);
 	// the warps split every lane's stretch into WARPS consecutive pieces.
+	// Branch-free (as in zdev_spec2d.cu): the keys past n (up to the 64 * S the lanes cover) are padded with
+	// KEY1_EMPTY, and a hole counts as key NK - it gets a counter and a stretch of perm[] behind the live entries.
 	const int S = ((((n + 1) >> 1) + 31) >> 5) | 1;
+	{
+		unsigned short* const kw = const_cast<unsigned short*>(s_key);
+		for (int k = n + threadIdx.x; k < 64 * S; k += P1_THREADS) kw[k] = (unsigned short) KEY1_EMPTY;
+		__syncthreads();
+	}
 	const int ws = (S + P1_WARPS - 1) / P1_WARPS;
 	const int w0 = lane * S + warp * ws, wn = min(ws, S - warp * ws);
 	const unsigned* const s_key2 = reinterpret_cast<const unsigned*>(s_key) + w0;
 	#pragma unroll 4
 	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
-			if (c0 != KEY1_EMPTY) atomicAdd(&s_cnt[c0], 1);
-			if (c1 != KEY1_EMPTY) atomicAdd(&s_cnt[c1], 1);
-		}
+		const unsigned two = s_key2[j];
+		atomicAdd(&s_cnt[min(two & 0xffffu, (unsigned) NK)], 1);
+		atomicAdd(&s_cnt[min(two >> 16, (unsigned) NK)], 1);
 	}
 	__syncthreads();
 	int nlive;
@@ -860,21 +763,19 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		int run = woff + incl - v;
 		#pragma unroll
 		for (int k = 0; k < PER; k++) { if (i0 + k < NK) s_cur[i0 + k] = run; run += c[k]; }
+		if (threadIdx.x == 0) s_cur[NK] = tot;               // the holes start behind the live entries
 		nlive = tot;
 		__syncthreads();
 	}
 	#pragma unroll 4
 	for (int j = 0; j < wn; j++) {
-		const int i = 2 * (w0 + j);
-		if (i < n) {
-			const unsigned two = s_key2[j];
-			const unsigned c0 = two & 0xffffu, c1 = (i + 1 < n) ? (two >> 16) : KEY1_EMPTY;
-			if (c0 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c0], 1)] = (unsigned short) i;
-			if (c1 != KEY1_EMPTY) s_perm[atomicAdd(&s_cur[c1], 1)] = (unsigned short) (i + 1);
-		}
+		const unsigned two = s_key2[j];
+		const unsigned c0 = min(two & 0xffffu, (unsigned) NK), c1 = min(two >> 16, (unsigned) NK);
+		const unsigned i = 2u * (unsigned) (w0 + j);
+		s_perm[atomicAdd(&s_cur[c0], 1)] = (c0 << 16) | i;
+		s_perm[atomicAdd(&s_cur[c1], 1)] = (c1 << 16) | (i + 1u);
 	}
 	__syncthreads();                                    // the keys are dead: their bytes become field pairs + queues
-#endif
 	// ---- the fields as (F[k], F[k+1]) pairs: one LDS.64 per component and particle
 	for (int k = threadIdx.x; k < 6 * PL; k += P1_THREADS) {
 		const int pl = k / PL, o = k - pl * PL;
@@ -882,9 +783,6 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		s_f2[k] = mk2(s_raw[k], s_raw[o1]);
 	}
 	__syncthreads();
-#ifdef PUSH1_PRESORTED
-	if (nlive > 0) mbar_wait(&s_bar, 0);
-#endif
 
 	// ---- phase B: every warp streams a contiguous range of the sorted particles, 64 per iteration (lane l
 	//      owns the particles l and l+32 of the block); no block barriers from here on
@@ -948,11 +846,12 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	};
 
 	auto load_pair = [&](int pa, pair1_rec& r) {
-		const int ia = s_perm[pa < pend ? pa : pbeg], ib = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const unsigned va = s_perm[pa < pend ? pa : pbeg], vb = s_perm[pa + 32 < pend ? pa + 32 : pbeg];
+		const int ia = va & 0xffffu, ib = vb & 0xffffu;
 		const float* qa = Arec + (ia >> 5) * REC1_CHUNK_WORDS + (ia & 31);
 		const float* qb = Arec + (ib >> 5) * REC1_CHUNK_WORDS + (ib & 31);
 		r.x = mk2(qa[0], qb[0]); r.ux = mk2(qa[32], qb[32]); r.uy = mk2(qa[64], qb[64]); r.uz = mk2(qa[96], qb[96]);
-		r.ca = __float_as_int(qa[128]); r.cb = __float_as_int(qb[128]);
+		r.ca = (int) (va >> 16) / SUB1; r.cb = (int) (vb >> 16) / SUB1;             // the sort key carries the cell
 		r.ta = r.tb = 0;
 		if (TAGS) { r.ta = A.tag[base + ia]; r.tb = A.tag[base + ib]; }
 	};
@@ -1057,13 +956,13 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 		const bool sta = actA && (unsigned) nlxa < (unsigned) cx, stb = actB && (unsigned) nlxb < (unsigned) cx;
 		if (actA) {
 			float* qd = Brec + (pa >> 5) * REC1_CHUNK_WORDS + (pa & 31);
-			qd[0] = xn.x; qd[32] = ux.x; qd[64] = uy.x; qd[96] = uz.x; qd[128] = __int_as_float(nlxa);
+			qd[0] = xn.x; qd[32] = ux.x; qd[64] = uy.x; qd[96] = uz.x;
 			Bo.key[base + pa] = sta ? key1_of(nlxa, xn.x) : (unsigned short) KEY1_EMPTY;
 			if (TAGS) Bo.tag[base + pa] = v.ta;
 		}
 		if (actB) {
 			float* qd = Brec + (pb >> 5) * REC1_CHUNK_WORDS + (pb & 31);
-			qd[0] = xn.y; qd[32] = ux.y; qd[64] = uy.y; qd[96] = uz.y; qd[128] = __int_as_float(nlxb);
+			qd[0] = xn.y; qd[32] = ux.y; qd[64] = uy.y; qd[96] = uz.y;
 			Bo.key[base + pb] = stb ? key1_of(nlxb, xn.y) : (unsigned short) KEY1_EMPTY;
 			if (TAGS) Bo.tag[base + pb] = v.tb;
 		}
@@ -1192,37 +1091,13 @@ extern "C" void zdev_spec1d_advance(zdev_spec1d* s, zdev_grid1d* grid, zdev_grid
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV1_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
-	const unsigned front = (unsigned) push1_smem_front(s->TX, s->max_cap), permb = (unsigned) (((size_t) s->max_cap * 2 + 15) & ~(size_t) 15);
-#ifdef PUSH1_PRESORTED
-	if (s->gperm_cap < s->cap_total) {
-		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(s->gperm);
-		ZDEV_CHECK(cudaMalloc(&s->gperm, (size_t) s->cap_total * 2 + 64));
-		s->gperm_cap = s->cap_total;
-	}
-	if (!s->tile_nlive) ZDEV_CHECK(cudaMalloc(&s->tile_nlive, (size_t) s->ntiles * sizeof(int)));
-	{
-		static size_t sort_configured = 0;
-		if (2 * (size_t) permb > sort_configured) {
-			ZDEV_CHECK(cudaFuncSetAttribute(k_sort1d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (2 * (size_t) permb)));
-			sort_configured = 2 * (size_t) permb;
-		}
-	}
-	ZDEV_LAUNCH(k_sort1d, s->ntiles, P1_THREADS, 2 * (size_t) permb, s->p, s->tile_off, s->tile_np, s->gperm, s->tile_nlive, s->TX, permb);
-	if (s->track_ids)
-		ZDEV_LAUNCH(k_push1d<true>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
-		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb, s->gperm, s->tile_nlive);
-	else
-		ZDEV_LAUNCH(k_push1d<false>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
-		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb, s->gperm, s->tile_nlive);
-#else
+	const unsigned front = (unsigned) push1_smem_front(s->TX, s->max_cap), permb = (unsigned) push1_smem_perm(s->max_cap);
 	if (s->track_ids)
 		ZDEV_LAUNCH(k_push1d<true>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
 		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
 	else
 		ZDEV_LAUNCH(k_push1d<false>, s->ntiles, P1_THREADS, smem, s->p, s->q, s->tile_off, s->tile_np, s->tile_np_q, s->mig, s->ctl,
 		            zdev_grid1d_Epart(grid), zdev_grid1d_Bpart(grid), zdev_grid1d_J(gcur), s->nx, s->TX, *prm, front, permb);
-#endif
 	if (slot >= 0) ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot + 1], zdev_strm));
 	{ buf1d t = s->p; s->p = s->q; s->q = t; }
 	{ int* t = s->tile_np; s->tile_np = s->tile_np_q; s->tile_np_q = t; }
@@ -1253,7 +1128,7 @@ __global__ void k1_deposit_charge(buf1d p, const int64_t* __restrict__ off, cons
 	int64_t b = off[t];
 	for (int k = threadIdx.x; k < n; k += blockDim.x) {
 		if (p.key[b + k] == KEY1_EMPTY) continue;
-		rec20 v = rec1_load(p.rec, b + k);
+		rec20 v = rec1_load(p.rec, b + k, p.key[b + k]);
 		int idx = t * TX + v.cell;
 		atomicAdd(&rho[idx], (1.0f - v.x) * q);
 		atomicAdd(&rho[idx + 1], (v.x) * q);
