@@ -15,6 +15,7 @@
 // dep_current_zamb :707-779, periodic / open / moving-window boundaries) and :791-850 (spec_sort).
 // Arithmetic order follows the reference exactly (no contraction): one step is bit-identical.
 #include "zdev_common.cuh"
+#include <type_traits>
 #include "pic2d_core.cuh"      // ltrim
 #include "pic2d_packed.cuh"    // packed fp32 arithmetic, boris2
 #include "zdev_tma.cuh"
@@ -859,9 +860,12 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	pair1_rec nv;
 	if (pbeg < pend) load_pair(pbeg + lane, nv);
 
-	for (int p0 = pbeg; p0 < pend; p0 += 64) {
+	// one iteration = 64 particles; FULL: all 64 exist (every iteration but the last of a warp's range), so the
+	// activity masks are compile-time true and the predicates, selects and store guards they feed disappear
+	auto advance64 = [&](const int p0, auto full_tag) {
+		constexpr bool FULL = decltype(full_tag)::value;
 		const int pa = p0 + lane, pb = pa + 32;
-		const bool actA = pa < pend, actB = pb < pend;
+		const bool actA = FULL || pa < pend, actB = FULL || pb < pend;
 		const pair1_rec v = nv;
 		if (p0 + 64 < pend) load_pair(pa + 64, nv);        // software pipeline: next iteration's records
 
@@ -991,6 +995,11 @@ k_push1d(buf1d A, buf1d Bo, const int64_t* __restrict__ tile_off, const int* __r
 				}
 			}
 		}
+	};
+	{
+		int p0 = pbeg;
+		for (; p0 + 64 <= pend; p0 += 64) advance64(p0, std::true_type());
+		if (p0 < pend) advance64(p0, std::false_type());
 	}
 	if (cur >= 0) flush_cell1(acc, cur, lane, J0);
 	if (nxq) drain1(xq, nxq, lane, J0, prm.qnx);
