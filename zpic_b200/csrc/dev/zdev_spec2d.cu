@@ -1510,46 +1510,94 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 // Boundary conditions for the particles that left their tile (reference particles.c:1237-1259: periodic y
 // always; x periodic, absorbing under a moving window, or handed to the neighbour slab), then append them
 // to their destination tiles.  One warp per tile segment.
-__global__ void k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig2d mig,
+__global__ void __launch_bounds__(256, 3) k_migrate2d(soa2d p, const int64_t* __restrict__ tile_off, int* __restrict__ tile_np, mig2d mig,
                             ctl2d* __restrict__ ctl, int TX, int TY, int ntx, int ntiles, int nx, int ny,
                             int moving_window, int slab_left, int slab_right,
                             part_aos* __restrict__ exp_l, part_aos* __restrict__ exp_r, unsigned int exp_cap,
                             part_aos* __restrict__ ovf, int* __restrict__ ovf_tag, unsigned int ovf_cap, slab_pub pub) {
+	// The work per record is a chain of dependent memory operations (record -> slot reservation -> tile bounds ->
+	// stores), so a warp keeps MIG_U records per lane in flight and runs the chain phase by phase; reservations of
+	// lanes that target the same tile (most leavers of a tile go to the same neighbour) or the same export list are
+	// combined into one atomic per warp instruction.
+	constexpr int MIG_U = 4;
 	const int lane = threadIdx.x & 31;
+	const unsigned lt = (1u << lane) - 1u;
 	const int nwarp = (gridDim.x * blockDim.x) >> 5;
+	const int lgx = 31 - __clz(TX), lgy = 31 - __clz(TY);             // tile shapes are powers of two
 	for (int ts = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ts < ntiles; ts += nwarp) {
 		const int n = mig.np[ts];
 		const int64_t mb = tile_off[ts] / mig.div;
-		for (int k = lane; k < n; k += 32) {
-			part_aos r = mig.rec[mb + k];
-			int ix = r.ix, iy = r.iy;
-			iy += ((iy < 0) ? ny : 0) - ((iy >= ny) ? ny : 0);
-			if (ix < 0 || ix >= nx) {
-				const int side = ix >= nx;
-				if (side ? slab_right : slab_left) {
-					// leaves the slab: export in the neighbour's frame (all slabs have the same width)
-					unsigned int slot = atomicAdd(&ctl->n_exp[side], 1u);
-					if (slot >= exp_cap) { atomicOr(&ctl->flags, 4u); continue; }
-					r.ix = side ? ix - nx : ix + nx; r.iy = iy;
-					(side ? exp_r : exp_l)[slot] = r;
+		for (int k0 = 0; k0 < n; k0 += 32 * MIG_U) {                  // (warp-uniform trip count: the lanes vote below)
+			part_aos r[MIG_U];
+			int t[MIG_U], ex[MIG_U], tag[MIG_U];
+			#pragma unroll
+			for (int u = 0; u < MIG_U; u++) {
+				const int k = k0 + 32 * u + lane;
+				t[u] = -1; ex[u] = -1; tag[u] = 0;
+				if (k < n) { r[u] = mig.rec[mb + k]; if (p.tag) tag[u] = mig.tag[mb + k]; t[u] = 0; }
+			}
+			// boundary conditions: periodic y always; x periodic, absorbing under a moving window, or export
+			#pragma unroll
+			for (int u = 0; u < MIG_U; u++) {
+				if (t[u] < 0) continue;
+				int ix = r[u].ix, iy = r[u].iy;
+				iy += ((iy < 0) ? ny : 0) - ((iy >= ny) ? ny : 0);
+				if (ix < 0 || ix >= nx) {
+					const int side = ix >= nx;
+					if (side ? slab_right : slab_left) { ex[u] = side; ix += side ? -nx : nx; t[u] = -1; }   // the neighbour's frame
+					else if (moving_window) t[u] = -1;                                                  // absorbed
+					else ix += side ? -nx : nx;
+				}
+				r[u].ix = ix; r[u].iy = iy;
+				if (t[u] >= 0) t[u] = (ix >> lgx) + (iy >> lgy) * ntx;
+			}
+			// leaves the slab: export (all slabs have the same width); one reservation per side and instruction
+			if (slab_left | slab_right) {
+				#pragma unroll
+				for (int u = 0; u < MIG_U; u++) {
+					#pragma unroll
+					for (int side = 0; side < 2; side++) {
+						const unsigned m = __ballot_sync(0xffffffffu, ex[u] == side);
+						if (m == 0u) continue;
+						const int leader = __ffs(m) - 1;
+						unsigned int base = 0;
+						if (lane == leader) base = atomicAdd(&ctl->n_exp[side], (unsigned) __popc(m));
+						base = __shfl_sync(0xffffffffu, base, leader);
+						if (ex[u] == side) {
+							const unsigned int slot = base + __popc(m & lt);
+							if (slot >= exp_cap) atomicOr(&ctl->flags, 4u);
+							else (side ? exp_r : exp_l)[slot] = r[u];
+						}
+					}
+				}
+			}
+			// reserve a slot in the destination tile
+			int slot[MIG_U];
+			#pragma unroll
+			for (int u = 0; u < MIG_U; u++) {
+				const unsigned grp = __match_any_sync(0xffffffffu, t[u]);
+				const int leader = __ffs(grp) - 1;
+				int base = 0;
+				if (lane == leader && t[u] >= 0) base = atomicAdd(&tile_np[t[u]], __popc(grp));
+				slot[u] = __shfl_sync(0xffffffffu, base, leader) + __popc(grp & lt);
+			}
+			int64_t lo[MIG_U], hi[MIG_U];
+			#pragma unroll
+			for (int u = 0; u < MIG_U; u++) if (t[u] >= 0) { lo[u] = tile_off[t[u]]; hi[u] = tile_off[t[u] + 1]; }
+			#pragma unroll
+			for (int u = 0; u < MIG_U; u++) {
+				if (t[u] < 0) continue;
+				const int64_t d = lo[u] + slot[u];
+				if (d >= hi[u]) {
+					atomicSub(&tile_np[t[u]], 1);
+					ovf_push(ctl, ovf, ovf_tag, ovf_cap, r[u], tag[u]);
 					continue;
 				}
-				if (moving_window) continue;                 // absorbed
-				ix += side ? -nx : nx;
+				const int lx = r[u].ix & (TX - 1), ly = r[u].iy & (TY - 1);
+				rec_store(p.rec, d, r[u].x, r[u].y, r[u].ux, r[u].uy, r[u].uz);
+				p.key[d] = (unsigned short) (lx + ly * TX);
+				if (p.tag) p.tag[d] = tag[u];
 			}
-			int tx = ix / TX, ty = iy / TY, t = tx + ty * ntx;
-			int slot = atomicAdd(&tile_np[t], 1);
-			int64_t d = tile_off[t] + slot;
-			if (d >= tile_off[t + 1]) {
-				atomicSub(&tile_np[t], 1);
-				r.ix = ix; r.iy = iy;
-				ovf_push(ctl, ovf, ovf_tag, ovf_cap, r, p.tag ? mig.tag[mb + k] : 0);
-				continue;
-			}
-			const int lx = ix - tx * TX, ly = iy - ty * TY;
-			rec_store(p.rec, d, r.x, r.y, r.ux, r.uy, r.uz);
-			p.key[d] = (unsigned short) (lx + ly * TX);
-			if (p.tag) p.tag[d] = mig.tag[mb + k];
 		}
 	}
 	// linked slabs: the export lists ARE the neighbours' mailboxes; tell them how many records arrived
