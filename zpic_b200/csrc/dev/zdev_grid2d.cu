@@ -107,10 +107,13 @@ extern "C" void zdev_grid2d_download_window(zdev_grid2d* g, int which, float* ho
 
 // ------------------------------------------------------------------ slab links (zdev_slab.cuh)
 
+static const int SMOOTH_HALO_MAX = 16;        // the wide halo of the fused smoothing passes: passes + 2 columns at most
+
 extern "C" void zdev_grid2d_set_slab(zdev_grid2d* g, int left, int right, int wrap_left, int wrap_right) {
 	if (g->slab) return;
-	// the largest message: three columns of two grids, every row
-	zdev_link_open(&g->link, (size_t) 2 * 3 * g->nrows * sizeof(f3), left, right);
+	// the largest messages: three columns of two grids, or the wide halo of the fused smoothing passes
+	// (SMOOTH_HALO_MAX columns of one grid), every row
+	zdev_link_open(&g->link, (size_t) SMOOTH_HALO_MAX * g->nrows * sizeof(f3), left, right);
 	g->slab = 1; g->wrap_left = wrap_left; g->wrap_right = wrap_right;
 }
 
@@ -484,6 +487,77 @@ __global__ void k_smooth_y(f3* __restrict__ dst, const f3* __restrict__ src, int
 	dst[c] = stencil3(src[cw - nrow], src[cw], src[cw + nrow], sa, sb);
 }
 
+// ALL the [sa,sb,sa] passes along x in one kernel (reference current_smooth's x loop, current.c:427-447, each pass =
+// kernel_x, :316-354).  A WARP owns 32 consecutive cells of one row, one per lane, and runs the passes in registers:
+// the neighbours come from the lanes next door (two shuffles per component and pass), so every pass the valid
+// stretch shrinks by one lane per side and V = 32 - 2 passes cells in the middle come out; consecutive warps
+// overlap by 2 passes cells.  Every cell goes through exactly the stencils, on exactly the values, of the
+// pass-by-pass form (the overlap recomputes what the neighbouring warp computes), so the result is bit-identical;
+// the grid is read and written once instead of once per pass and nothing waits at a barrier.  The first warp of a
+// row starts so that guard -1 is its first valid lane; the guards nx, nx+1 fall to the last one.  What lies beyond
+// the row's ends:
+//   periodic box        the cells of the other end (the reference refreshes its x guards from there after every
+//                       pass, so guards and their images evolve alike);
+//   moving window       nothing - the guards keep their raw values through all passes (current.c:346: no refresh)
+//                       and the cells next to them see those (`frozen` cells);
+//   neighbour slab      the neighbour's cells, H = passes + 2 columns sent ONCE before the kernel (zdev_slab.cuh)
+//                       instead of a guard refresh after every pass; the warps at the row's ends wait for the
+//                       message and read the payload.
+// Rows outside 0..ny-1 are not filtered (kernel_x only walks the interior rows): copied through.
+#define SMX_MAXP 12
+#define SMX_WARPS 8
+struct smx_coef { float sa[SMX_MAXP], sb[SMX_MAXP]; };
+__global__ void __launch_bounds__(SMX_WARPS * 32)
+k_smooth_x_multi(f3* __restrict__ dst, const f3* __restrict__ src, int nx, int ny, int nrow, int npass, smx_coef cf,
+                 int frozen_lo, int frozen_hi, slab_msg L, slab_msg R, unsigned seq_l, unsigned seq_r) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int j = (int) blockIdx.y - 1;
+	const int V = 32 - 2 * npass;                                    // valid cells per warp
+	const int kw = blockIdx.x * SMX_WARPS + warp;                    // which stretch of the row
+	const int i = -1 - npass + kw * V + lane;                        // this lane's cell (extended index)
+	if (-1 + kw * V > nx + 1) return;                                // past the row's end
+	const bool mine = lane >= npass && lane < 32 - npass && i <= nx + 1;
+	if (j < 0 || j >= ny) {                                          // pass-through rows
+		if (mine) { const int c = cidx(i, j, nrow); dst[c] = src[c]; }
+		return;
+	}
+	const int H = npass + 2;
+	f3 v;
+	if (L.buf && -1 - npass + kw * V < 0) {                          // (warp-uniform) some lanes read the left halo
+		if (lane == 0) slab_wait_lane(L.flag, seq_l);
+		__syncwarp();
+	}
+	if (R.buf && -1 - npass + kw * V + 31 >= nx) {
+		if (lane == 0) slab_wait_lane(R.flag, seq_r);
+		__syncwarp();
+	}
+	if (i < 0 && L.buf) {
+		const float* q = reinterpret_cast<const float*>(L.buf + (size_t) j * H + (i + H));      // column i of the left halo
+		v.x = __ldcg(q); v.y = __ldcg(q + 1); v.z = __ldcg(q + 2);
+	} else if (i >= nx && R.buf) {
+		const float* q = reinterpret_cast<const float*>(R.buf + (size_t) j * H + min(i - nx, H - 1));
+		v.x = __ldcg(q); v.y = __ldcg(q + 1); v.z = __ldcg(q + 2);
+	} else {
+		int iw = i;
+		if (i < 0) iw = frozen_lo ? max(i, -1) : ((i % nx) + nx) % nx;
+		else if (i >= nx) iw = frozen_hi ? min(i, nx + 1) : i % nx;
+		v = src[cidx(iw, j, nrow)];
+	}
+	const bool keep = (frozen_lo && i < 0) || (frozen_hi && i >= nx);
+	#pragma unroll
+	for (int p = 0; p < SMX_MAXP; p++) {                             // (unrolled: the coefficients stay kernel parameters)
+		if (p >= npass) break;
+		const float sa = cf.sa[p], sb = cf.sb[p];
+		f3 lo, hi;
+		lo.x = __shfl_up_sync(0xffffffffu, v.x, 1); hi.x = __shfl_down_sync(0xffffffffu, v.x, 1);
+		lo.y = __shfl_up_sync(0xffffffffu, v.y, 1); hi.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+		lo.z = __shfl_up_sync(0xffffffffu, v.z, 1); hi.z = __shfl_down_sync(0xffffffffu, v.z, 1);
+		const f3 fs = stencil3(lo, v, hi, sa, sb);                   // current.c:334-336, left to right
+		if (!keep) v = fs;                                           // (lanes 0 and 31 see themselves: outside the valid stretch)
+	}
+	if (mine) dst[cidx(i, j, nrow)] = v;
+}
+
 // reference get_smooth_comp, em2d/current.c:297-304 (double -> float on b)
 static void smooth_comp(int n, float* sa, float* sb) {
 	float a = -1;
@@ -500,11 +574,37 @@ static void smooth_pass(zdev_grid2d* g, int dir, float sa, float sb, int moving_
 	f3* t = g->J; g->J = g->tmp; g->tmp = t;
 }
 
+static int smooth_fused = -1;             // ZPIC_FUSED_SMOOTH=0: one kernel per pass (same results bit for bit)
+static bool use_fused_smooth(int npass) {
+	if (smooth_fused < 0) { const char* e = getenv("ZPIC_FUSED_SMOOTH"); smooth_fused = e ? atoi(e) != 0 : 1; }
+	return smooth_fused && npass >= 2 && npass <= SMX_MAXP;
+}
+// all x passes of the plan [first, first + npass) in one kernel; L / R: wide halos of neighbour slabs (or none)
+static void smooth_x_fused(zdev_grid2d* g, const float* sa, const float* sb, int npass, int frozen_lo, int frozen_hi,
+                           slab_msg L, slab_msg R, unsigned seq_l, unsigned seq_r) {
+	need_J(g); need_tmp(g);
+	smx_coef cf;
+	for (int p = 0; p < npass; p++) { cf.sa[p] = sa[p]; cf.sb[p] = sb[p]; }
+	const int V = 32 - 2 * npass;                                   // cells a warp delivers
+	dim3 grd(zdev_div_up(zdev_div_up(g->nx + 3, V), SMX_WARPS), g->ny + 3);
+	ZDEV_LAUNCH(k_smooth_x_multi, grd, SMX_WARPS * 32, 0, g->tmp, g->J, g->nx, g->ny, g->nrow, npass, cf, frozen_lo, frozen_hi, L, R, seq_l, seq_r);
+	f3* t = g->J; g->J = g->tmp; g->tmp = t;
+}
+
 extern "C" void zdev_current_smooth(zdev_grid2d* g, int moving_window, int xtype, int ytype, int xlevel, int ylevel) {
 	float sa, sb;
 	if (xtype != 0) {
-		for (int i = 0; i < xlevel; i++) smooth_pass(g, 0, 0.25f, 0.5f, moving_window);
-		if (xtype == 2) { smooth_comp(xlevel, &sa, &sb); smooth_pass(g, 0, sa, sb, moving_window); }
+		const int npx = xlevel + (xtype == 2 ? 1 : 0);
+		if (use_fused_smooth(npx)) {
+			float ca[SMX_MAXP], cb[SMX_MAXP];
+			for (int i = 0; i < xlevel; i++) { ca[i] = 0.25f; cb[i] = 0.5f; }
+			if (xtype == 2) smooth_comp(xlevel, &ca[xlevel], &cb[xlevel]);
+			const slab_msg none = { nullptr, nullptr, 0, 0 };
+			smooth_x_fused(g, ca, cb, npx, moving_window, moving_window, none, none, 0, 0);
+		} else {
+			for (int i = 0; i < xlevel; i++) smooth_pass(g, 0, 0.25f, 0.5f, moving_window);
+			if (xtype == 2) { smooth_comp(xlevel, &sa, &sb); smooth_pass(g, 0, sa, sb, moving_window); }
+		}
 	}
 	if (ytype != 0) {
 		// sic: the reference counts the y passes with xlevel (em2d/current.c:449)
@@ -576,7 +676,36 @@ extern "C" void zdev_current_update(zdev_grid2d* g, int moving_window, int xtype
 	int dirs[64]; float sa[64], sb[64];
 	const int np = zdev_smooth_plan(xtype, ytype, xlevel, ylevel, dirs, sa, sb);
 	bool y_passes = false;
-	for (int k = 0; k < np; k++) {
+	int k0 = 0;
+	int npx = 0;
+	while (npx < np && dirs[npx] == 0) npx++;                // the x passes come first in the plan
+	if (use_fused_smooth(npx) && npx + 2 <= SMOOTH_HALO_MAX && g->nx >= npx + 2) {
+		// ONE exchange of H = passes + 2 columns per side (my lowest H columns to the left neighbour, my highest H
+		// to the right one), then all x passes in one kernel whose edge blocks read the neighbours' columns from
+		// the mailbox; a side without a neighbour (the open ends of a moving-window chain) keeps its guards frozen
+		zdev_link& K = g->link;
+		const int H = npx + 2;
+		const bool do_l = K.left >= 0, do_r = K.right >= 0;
+		slab_msg SL = { nullptr, nullptr, 0, 0 }, SR = SL, RL = SL, RR = SL;
+		unsigned seq_l = 0, seq_r = 0;
+		if (do_l) {
+			seq_l = ++K.seq[0];
+			SL = { (f3*) zdev_link_out(K, 0, seq_l), &zdev_link_out_hdr(K, 0)->flag[1], 0, H };
+			RL = { (f3*) zdev_link_in(K, 0, seq_l), &zdev_link_in_hdr(K)->flag[0], -H, H };
+		}
+		if (do_r) {
+			seq_r = ++K.seq[1];
+			SR = { (f3*) zdev_link_out(K, 1, seq_r), &zdev_link_out_hdr(K, 1)->flag[0], g->nx - H, H };
+			RR = { (f3*) zdev_link_in(K, 1, seq_r), &zdev_link_in_hdr(K)->flag[1], g->nx, H };
+		}
+		if (do_l || do_r) {
+			dim3 grd(std::max(1, std::min(zdev_div_up(H * g->ny, 256), 32)), 2);
+			ZDEV_LAUNCH(k_slab_send, grd, 256, 0, g->J, (const f3*) nullptr, 1, g->nrow, 0, g->ny, SL, SR, seq_l, seq_r, K.ticket);
+		}
+		smooth_x_fused(g, sa, sb, npx, !do_l, !do_r, RL, RR, seq_l, seq_r);
+		k0 = npx;
+	}
+	for (int k = k0; k < np; k++) {
 		smooth_pass(g, dirs[k], sa[k], sb[k], 1);
 		if (dirs[k] == 0) slab_halo_refresh(g, g->J, nullptr, 0, g->ny, false);
 		else y_passes = true;

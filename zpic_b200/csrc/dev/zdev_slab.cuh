@@ -116,7 +116,13 @@ __device__ __forceinline__ void slab_publish(unsigned* ticket, unsigned nblocks,
 	}
 }
 
+// the same for ONE lane of a warp that is about to read the payload (the caller follows with __syncwarp())
+__device__ __forceinline__ void slab_wait_lane(const unsigned* my_flag, unsigned seq);
+
 // Called by every thread of a receiving kernel before it reads the payload
+__device__ __forceinline__ void slab_wait_lane(const unsigned* my_flag, unsigned seq) {
+	while ((int) (ld_flag(my_flag) - seq) < 0) __nanosleep(200);
+}
 __device__ __forceinline__ void slab_wait(const unsigned* my_flag, unsigned seq) {
 	if (threadIdx.x == 0) {
 		while ((int) (ld_flag(my_flag) - seq) < 0) __nanosleep(200);
