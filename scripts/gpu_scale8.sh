@@ -5,4 +5,3 @@ nvidia-smi -L | wc -l
 timeout 400 $T --nproc-per-node 8 --master-port 29601 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; tail -2 gpurun_out/r02_bench_n8.err | cut -c1-300; cut -c1-330 gpurun_out/r02_bench_n8.json
 timeout 400 $T --nproc-per-node 8 --master-port 29602 bench.py --workload lwfa --gpus 8 --steps 200 --warmup 5 > gpurun_out/r02_lwfa_n8.json 2> gpurun_out/r02_lwfa_n8.err; tail -2 gpurun_out/r02_lwfa_n8.err | cut -c1-300; cut -c1-330 gpurun_out/r02_lwfa_n8.json
 timeout 400 $T --nproc-per-node 8 --master-port 29603 bench.py --workload kh --gpus 8 --steps 20 --warmup 3 > gpurun_out/r02_kh_n8.json 2> gpurun_out/r02_kh_n8.err; tail -2 gpurun_out/r02_kh_n8.err | cut -c1-300; cut -c1-330 gpurun_out/r02_kh_n8.json
-timeout 400 $T --nproc-per-node 4 --master-port 29604 bench.py --workload kh --gpus 4 --steps 20 --warmup 3 > gpurun_out/r02_kh_n4.json 2> gpurun_out/r02_kh_n4.err; tail -2 gpurun_out/r02_kh_n4.err | cut -c1-300; cut -c1-330 gpurun_out/r02_kh_n4.json
