@@ -4,8 +4,9 @@ sys.path.insert(0, os.getcwd())
 import bench
 from zpic_b200 import abi_em2d as A, load
 lib = load("em2d"); assert lib.zdev_init(0) == 0
-n = 1024
-lib.zpic_b200_set_option(b"device_init", 0); lib.zpic_b200_set_option(b"lazy", 0); lib.zpic_b200_set_option(b"coherent", 0)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+os.environ.setdefault("ZPIC_TILE_SLACK", "1.25")
+lib.zpic_b200_set_option(b"device_init", 2 if n > 1024 else 0); lib.zpic_b200_set_option(b"lazy", 0); lib.zpic_b200_set_option(b"coherent", 0)
 t0 = time.perf_counter()
 sim, species, _ = bench.build_weibel(lib, A, n, n, (8, 8))
 print("host init %.1f s" % (time.perf_counter() - t0))

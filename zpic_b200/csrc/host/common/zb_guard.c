@@ -112,9 +112,26 @@ void* zb_guard_alloc( size_t bytes )
 {
 	if (!zb_guard_enabled()) return calloc(bytes ? bytes : 1, 1);
 	if (n_regions == ZB_G_MAX) { fprintf(stderr, "(*error*) zpic-b200: too many host mirrors\n"); exit(-1); }
-	const size_t len = round_pages(bytes);
-	void* p = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-	if (p == MAP_FAILED) { fprintf(stderr, "(*error*) zpic-b200: host mirror of %zu bytes: out of memory\n", bytes); exit(-1); }
+	size_t len = round_pages(bytes);
+	void* p;
+	const size_t huge = (size_t) 2 << 20;
+	if (len >= 2 * huge) {
+		/* a large mirror (the E, B, J grids of a big box, a particle buffer): 2 MB-aligned and advised as huge pages -
+		   changing the protection of 200 MB walks 50 000 page-table entries per call with 4 KB pages, 100 with 2 MB */
+		len = (len + huge - 1) / huge * huge;
+		char* raw = mmap(NULL, len + huge, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		if (raw == MAP_FAILED) { fprintf(stderr, "(*error*) zpic-b200: host mirror of %zu bytes: out of memory\n", bytes); exit(-1); }
+		char* al = (char*) (((uintptr_t) raw + huge - 1) / huge * huge);
+		if (al > raw) munmap(raw, (size_t) (al - raw));
+		if (al + len < raw + len + huge) munmap(al + len, (size_t) (raw + len + huge - (al + len)));
+		p = al;
+#ifdef MADV_HUGEPAGE
+		madvise(p, len, MADV_HUGEPAGE);
+#endif
+	} else {
+		p = mmap(NULL, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		if (p == MAP_FAILED) { fprintf(stderr, "(*error*) zpic-b200: host mirror of %zu bytes: out of memory\n", bytes); exit(-1); }
+	}
 	install();
 	region* r = &regions[n_regions++];
 	memset(r, 0, sizeof *r);
