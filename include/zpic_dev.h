@@ -118,7 +118,8 @@ void zdev_emf_set_ext_grid( zdev_grid2d* g, const float* host_ext_e, const float
 void zdev_emf_advance( zdev_grid2d* g, zdev_grid2d* g_cur, float dt, float dx, float dy,
                        int moving_window, int shift_window );
 /* The three stencils of emf_advance run as ONE kernel by default (60 B instead of 132 B of traffic per cell,
- * bit-identical results); 0 selects the three separate kernels below ($ZPIC_FUSED_YEE=0 does the same). */
+ * bit-identical results): 2 (default) marches the rows through registers, 1 works on shared-memory tiles, 0 selects
+ * the three separate kernels below ($ZPIC_FUSED_YEE=0 / 1 / 2 does the same). */
 void zdev_yee_set_fused( int on );
 /* pieces, for kernel-level parity tests */
 void zdev_yee_b( zdev_grid2d* g, float dt_dx, float dt_dy );            /* emf.c:500-522 */
@@ -231,6 +232,9 @@ void zdev_spec2d_fetch( zdev_spec2d* s, double* energy_sum, int64_t* np );
 /* spec_deposit_charge on the device (em2d/particles.c:1289-1324): charge is a host
  * (nx+1)*(ny+1) float array that is ADDED to, like the reference does */
 void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, float* charge );
+/* the multi-threaded host copy the charge deposit uses between the caller's pageable array and its pinned staging
+   buffer (host only, no device call: exercised on the CPU by tests/test_abi_symbols.py) */
+void zdev_spec2d_par_memcpy( void* dst, const void* src, size_t bytes );
 /* spec_deposit_pha on the device (em2d/particles.c:1569-1632): quant1/2 = the reference's
  * X1 (1), X2 (2), U1 (4), U2 (5), U3 (6), pha_buf is a host pha_nx[0]*pha_nx[1] float array that is ADDED to */
 void zdev_spec2d_deposit_pha( zdev_spec2d* s, int quant1, int quant2, const int pha_nx[2], const float pha_range[2][2],

@@ -19,7 +19,7 @@ def grid_half():
     lib.zdev_emf_advance(g, g, dt, dx, dx, 0, 0)
 
 
-for fused in (1, 0, 2, 1, 0, 2):      # 2: the interior / rim split of the one-pass kernel (unmeasured so far)
+for fused in (1, 0, 2, 1, 0, 2):      # 1: tile kernel (shared memory), 0: three stencils, 2: rows marched in registers
     lib.zdev_yee_set_fused(fused)
     for _ in range(5):
         grid_half()

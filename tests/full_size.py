@@ -89,10 +89,15 @@ def measure(code, lib, n, ppc, steps):
         "charge_sum_rel": [abs(s - qk * m) / abs(qk * m) for s, qk, m in zip(sums, q, npK)],
         "gauss_max": float(np.abs(res - res0).max()) / scale,
         "gauss_rms": float(np.sqrt(((res - res0) ** 2).mean())) / scale,
+        "gauss_at": [int(v) for v in np.unravel_index(int(np.abs(res - res0).argmax()), res.shape)],
         "energy_1": en1[0] + sum(en1[1]), "energy_K": enK[0] + sum(enK[1]),
         "field_energy_K": enK[0],
         "seconds": None,
     }
+    bad = np.argwhere(np.abs(res - res0) > 1e-5 * scale)
+    out["gauss_bad"] = int(len(bad))
+    out["gauss_bad_cells"] = [[int(j), int(i), float((res - res0)[j, i]) / scale] for j, i in bad[:24]] if code == "em2d" else []
+    out["charge_sum_err"] = [float(s - qk * m) for s, qk, m in zip(sums, q, npK)]
     out["energy_rel_drift"] = abs(out["energy_K"] - out["energy_1"]) / abs(out["energy_1"])
     deck.delete()
     out["seconds"] = round(time.time() - t0, 2)

@@ -80,3 +80,20 @@ def test_headers_declare_the_whole_reference_api(code):
         assert not missing, (os.path.basename(h), sorted(missing))
         checked += len(declared(ref_h))
     assert checked > 60
+
+
+def test_host_copy_of_the_charge_deposit_covers_every_byte():
+    """zdev_spec2d_par_memcpy splits a large copy over a few threads: every byte must arrive whatever the size
+    (67 141 636 bytes = the (4096+1)^2 charge grid, whose size is 4 more than 8 page-aligned chunks - the
+    original chunking dropped the last node)"""
+    import numpy as np
+    lib = C.CDLL(zbuild.lib_path("em2d"))
+    lib.zdev_spec2d_par_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.zdev_spec2d_par_memcpy.restype = None
+    rng = np.random.default_rng(5)
+    for nbytes in (0, 1, 4095, 4 << 20, (8 << 20) + 1, 4097 * 4097 * 4, 8 * 2049 * 4096 + 4, 33554432 + 4095, 50000001):
+        src = rng.integers(1, 255, nbytes, dtype=np.uint8)
+        dst = np.zeros(nbytes + 64, dtype=np.uint8)
+        lib.zdev_spec2d_par_memcpy(dst.ctypes.data, src.ctypes.data, nbytes)
+        assert np.array_equal(dst[:nbytes], src), nbytes
+        assert not dst[nbytes:].any(), nbytes

@@ -40,12 +40,14 @@ def _fill_random(deck, rng, amp=1.0):
     return vals
 
 
-@pytest.mark.parametrize("mw,fused,nx,ny", [(0, 1, 70, 45), (1, 1, 70, 45), (0, 0, 70, 45), (0, 1, 300, 90), (1, 1, 300, 90)])
+@pytest.mark.parametrize("mw,fused,nx,ny", [(0, 1, 70, 45), (1, 1, 70, 45), (0, 0, 70, 45), (0, 1, 300, 90), (1, 1, 300, 90),
+                                            (0, 2, 70, 45), (1, 2, 70, 45), (0, 2, 300, 90), (1, 2, 300, 90), (0, 2, 29, 200), (1, 2, 1000, 17)])
 def test_field_solver_bit_exact(ours, ref, mw, fused, nx, ny, monkeypatch):
     """yee_b/yee_e/yee_b + guard refresh on random E, B, J: every cell, guards included.  mw = 1: the x guards
     are NOT refreshed (moving window, em2d/emf.c:581), so the raw stencil results in the guard columns are
-    compared too (1 step: the window does not shift yet).  fused = 0: the three separate stencil kernels
-    (the one-pass kernel is the default; the switch is read once per process, hence the seam call below)."""
+    compared too (1 step: the window does not shift yet).  fused = 0: the three separate stencil kernels, 1: the
+    one-pass kernel on shared-memory tiles, 2: the one-pass kernel with the rows in registers (the default; the
+    switch is read once per process, hence the seam call below)."""
     rng = np.random.default_rng(1)
     a = H.Deck(ours, (nx, ny), (0.1 * nx, 0.2 * ny), 0.05)
     b = H.Deck(ref, (nx, ny), (0.1 * nx, 0.2 * ny), 0.05)
@@ -67,7 +69,7 @@ def test_field_solver_bit_exact(ours, ref, mw, fused, nx, ny, monkeypatch):
     for it in range(3 - 2 * mw):
         lib.zdev_emf_advance(g, g, 0.05, float(np.float32(0.1 * nx) / np.float32(nx)), float(np.float32(0.2 * ny) / np.float32(ny)), mw, 0)
         ref.emf_advance(C.byref(b.sim.emf), C.byref(b.sim.current))
-    lib.zdev_yee_set_fused(1)
+    lib.zdev_yee_set_fused(2)                           # back to the default (rows marched in registers)
     assert b.sim.emf.n_move == 0
     eo = np.empty_like(e)
     bo = np.empty_like(e)

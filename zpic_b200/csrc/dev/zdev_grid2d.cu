@@ -365,19 +365,104 @@ k_yee_fused(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__
 	}
 }
 
+// The same one-pass field advance with the rows in REGISTERS (mode 2).  A warp owns 32 consecutive buffer
+// columns, one per lane, and marches up a stripe of rows: per step it loads one row of E (the row above), B and J,
+// and has everything else in registers - the half-step B of this row and the one below, the new E of this row and
+// the one below.  Neighbours along x come from the lanes next door (six shuffles per cell and step), neighbours
+// along y from the previous / next step:
+//     Bh[j] = B[j]  + yee_b(E[j],  E[j](i+1),  E[j+1])           valid on lanes 0..30
+//     En[j] = E[j]  + yee_e(Bh[j], Bh[j](i-1), Bh[j-1], J[j])    valid on lanes 1..30
+//     Bn[j-1] = Bh[j-1] + yee_b(En[j-1], En[j-1](i+1), En[j])    valid on lanes 1..29  -> rows j-1 of E and B leave
+// so 29 columns per warp come out (consecutive warps overlap by three lanes) and a stripe of H rows costs three
+// extra row loads.  The tile kernel above needs ~16 warp-instructions per cell (asynchronous 4-byte copies into
+// shared memory, three passes over the tile with index arithmetic and masks); this one ~3.5 and no shared memory
+// or barrier at all, which leaves the DRAM traffic (60 B per cell) as the bound.  Every cell, guards included,
+// goes through the expressions of yee_b / yee_e (em2d/emf.c:509-520, 537-559) on the same operands: bit-identical.
+#define YM_COLS 29
+__device__ __forceinline__ f3 ym_load(const f3* __restrict__ G, int bi, int bj, int nrow, int nrows) {
+	f3 v = {0.0f, 0.0f, 0.0f};
+	if (bi >= 0 && bi < nrow && bj >= 0 && bj < nrows) v = G[(long) bj * nrow + bi];
+	return v;
+}
+__device__ __forceinline__ f3 ym_shfl_down(const f3 v) {
+	f3 r; r.x = __shfl_down_sync(0xffffffffu, v.x, 1); r.y = __shfl_down_sync(0xffffffffu, v.y, 1); r.z = __shfl_down_sync(0xffffffffu, v.z, 1);
+	return r;
+}
+__global__ void __launch_bounds__(256)
+k_yee_march(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__ E, const f3* __restrict__ B,
+            const f3* __restrict__ J, int nrow, int nrows, int H, float hdt_dx, float hdt_dy, float dt_dx, float dt_dy, float dt) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int cg = blockIdx.x * 8 + warp;                          // column group: buffer columns cg*29 .. cg*29+28
+	if (cg * YM_COLS >= nrow) return;
+	const int bi = cg * YM_COLS - 1 + lane;                        // lane 1 holds the group's first column
+	const int R = blockIdx.y * H;
+	const bool col_b = bi >= 0 && bi <= nrow - 2;                  // yee_b: i in [-1,nx] = buffer [0, nrow-2]
+	const bool col_e = bi >= 1 && bi <= nrow - 1;                  // yee_e: i in [0,nx+1] = buffer [1, nrow-1]
+	const bool mine = lane >= 1 && lane <= YM_COLS && bi < nrow;
+	f3 Ec = ym_load(E, bi, R - 1, nrow, nrows);                    // E of the current row
+	f3 Bh_prev = {0, 0, 0}, En_prev = {0, 0, 0};
+	const int r_end = min(R + H, nrows);                           // rows [R, r_end) leave this stripe
+	for (int r = R - 1; r <= r_end; r++) {
+		const f3 Eup = ym_load(E, bi, r + 1, nrow, nrows);
+		f3 Bh = ym_load(B, bi, r, nrow, nrows);
+		const f3 Jc = ym_load(J, bi, r, nrow, nrows);
+		// half-step B of row r (yee_b: j in [-1,ny] = buffer rows [0, nrows-2])
+		{
+			const f3 Ex = ym_shfl_down(Ec);
+			if (col_b && r >= 0 && r <= nrows - 2) yf_b(Bh, Ec, Ex, Eup, hdt_dx, hdt_dy);
+		}
+		// new E of row r (yee_e: j in [0,ny+1] = buffer rows [1, nrows-1]); rows below the stripe are not needed
+		f3 En = Ec;
+		{
+			f3 bx;
+			bx.y = __shfl_up_sync(0xffffffffu, Bh.y, 1); bx.z = __shfl_up_sync(0xffffffffu, Bh.z, 1);
+			if (col_e && r >= max(R, 1) && r <= nrows - 1) {
+				const f3 b = Bh, by = Bh_prev;
+				En.x += ( + dt_dy * ( b.z - by.z ) ) - dt * Jc.x;
+				En.y += ( - dt_dx * ( b.z - bx.z ) ) - dt * Jc.y;
+				En.z += ( + dt_dx * ( b.y - bx.y ) - dt_dy * ( b.x - by.x ) ) - dt * Jc.z;
+			}
+		}
+		// row r-1 is complete: second half step of B from the new E, and out
+		{
+			const f3 Ex = ym_shfl_down(En_prev);
+			if (r - 1 >= R) {
+				f3 Bn = Bh_prev;
+				if (col_b && r - 1 <= nrows - 2) yf_b(Bn, En_prev, Ex, En, hdt_dx, hdt_dy);
+				if (mine) {
+					const long o = (long) (r - 1) * nrow + bi;
+					Eout[o] = En_prev;
+					Bout[o] = Bn;
+				}
+			}
+		}
+		Ec = Eup; Bh_prev = Bh; En_prev = En;
+	}
+}
+
 static int fused_yee = -1;
 static int fused_yee_on() {
-	if (fused_yee < 0) { const char* e = getenv("ZPIC_FUSED_YEE"); fused_yee = !e ? 1 : (e[0] == '0' ? 0 : 1); }
+	if (fused_yee < 0) { const char* e = getenv("ZPIC_FUSED_YEE"); fused_yee = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2)); }
 	return fused_yee;
 }
-extern "C" void zdev_yee_set_fused(int on) { fused_yee = on ? 1 : 0; }
+extern "C" void zdev_yee_set_fused(int on) { fused_yee = (on == 2) ? 2 : (on ? 1 : 0); }
 static void yee_fused(zdev_grid2d* g, zdev_grid2d* gj, float dt, float dx, float dy) {
 	need_EB(g); need_J(gj); check_same_shape(g, gj); need_tmp(g); need_tmp2(g);
 	const float dtb = dt / 2.0f;
 	const int alias_e = (g->Epart == g->E), alias_b = (g->Bpart == g->B);
-	dim3 grd(zdev_div_up(g->nrow, YF_W), zdev_div_up(g->nrows, YF_H));
-	ZDEV_LAUNCH(k_yee_fused, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
+	if (fused_yee_on() == 2) {
+		// stripes of H rows: tall ones amortise the three extra row loads, short ones keep a small grid's SMs busy
+		const int ncg = zdev_div_up(g->nrow, YM_COLS);
+		int H = 64;
+		while (H > 16 && (long) ncg * zdev_div_up(g->nrows, H) < (long) 32 * zdev_num_sm) H >>= 1;
+		dim3 grd(zdev_div_up(ncg, 8), zdev_div_up(g->nrows, H));
+		ZDEV_LAUNCH(k_yee_march, grd, 256, 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows, H,
 		            dtb / dx, dtb / dy, dt / dx, dt / dy, dt);
+	} else {
+		dim3 grd(zdev_div_up(g->nrow, YF_W), zdev_div_up(g->nrows, YF_H));
+		ZDEV_LAUNCH(k_yee_fused, grd, dim3(YF_W, YF_TY), 0, g->tmp, g->tmp2, g->E, g->B, gj->J, g->nrow, g->nrows,
+		            dtb / dx, dtb / dy, dt / dx, dt / dy, dt);
+	}
 	{ f3* t = g->E; g->E = g->tmp; g->tmp = t; }
 	{ f3* t = g->B; g->B = g->tmp2; g->tmp2 = t; }
 	if (alias_e) g->Epart = g->E;

@@ -1834,9 +1834,10 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
 	const size_t min_chunk = (size_t) 4 << 20;
 	unsigned nt = std::thread::hardware_concurrency();
 	nt = std::max(1u, std::min(std::min(nt, 8u), (unsigned) (bytes / min_chunk)));
+	{ static int knob = -1; if (knob < 0) { const char* e = getenv("ZPIC_PAR_MEMCPY"); knob = !e || e[0] != '0'; } if (!knob) nt = 1; }
 	if (nt <= 1) { memcpy(dst, src, bytes); return; }
 	std::vector<std::thread> th;
-	const size_t chunk = ((bytes / nt) + 4095) & ~(size_t) 4095;
+	const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t) 4095;     // nt chunks cover every byte (rounded UP)
 	for (unsigned k = 0; k < nt; k++) {
 		const size_t o = (size_t) k * chunk;
 		if (o >= bytes) break;
@@ -1845,6 +1846,8 @@ static void par_memcpy(void* dst, const void* src, size_t bytes) {
 	}
 	for (auto& t : th) t.join();
 }
+
+extern "C" void zdev_spec2d_par_memcpy(void* dst, const void* src, size_t bytes) { par_memcpy(dst, src, bytes); }   // host only: tests/test_abi_symbols.py
 
 extern "C" void zdev_spec2d_deposit_charge(zdev_spec2d* s, float q, int moving_window, float* charge) {
 	spec_settle(s);
