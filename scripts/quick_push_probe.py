@@ -9,7 +9,8 @@ from zpic_b200 import load
 from zpic_b200._lib import PushParams2D
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-ppc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+ppc_arg = sys.argv[2] if len(sys.argv) > 2 else "8"               # "8" = 8x8 per cell, "4x8" = 4 along x, 8 along y
+ppcx, ppcy = (int(v) for v in ppc_arg.split("x")) if "x" in ppc_arg else (int(ppc_arg), int(ppc_arg))
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 lib = load("em2d")
 assert lib.zdev_init(-1) == 0
@@ -18,19 +19,19 @@ dx = np.float32(0.1)
 dt = np.float32(0.07)
 specs = []
 for k, sign in enumerate((-1.0, 1.0)):
-    s = lib.zdev_spec2d_create(n, n, ppc * ppc, 0)
+    s = lib.zdev_spec2d_create(n, n, ppcx * ppcy, 0)
     ufl = (C.c_float * 3)(0, 0, 0.6 * sign)
     uth = (C.c_float * 3)(0.1, 0.1, 0.1)
-    lib.zdev_spec2d_inject_uniform(s, ppc, ppc, ufl, uth, 1234 + k)
-    q = np.float32(sign) / np.float32(ppc * ppc)
+    lib.zdev_spec2d_inject_uniform(s, ppcx, ppcy, ufl, uth, 1234 + k)
+    q = np.float32(sign) / np.float32(ppcx * ppcy)
     prm = PushParams2D(float(np.float32(0.5 * float(dt) / sign)), float(dt / dx), float(dt / dx),
                        float(q * dx / dt), float(q * dx / dt), float(q), 0, 0)
     specs.append((s, prm))
 lib.zdev_sync()
 tx, ty, nt, cap = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
 lib.zdev_spec2d_tile_info(specs[0][0], C.byref(tx), C.byref(ty), C.byref(nt), C.byref(cap))
-npart = 2 * n * n * ppc * ppc
-print("grid %d^2 ppc %d: %d particles, tile %dx%d, %d tiles, capacity %d" % (n, ppc * ppc, npart, tx.value, ty.value, nt.value, cap.value))
+npart = 2 * n * n * ppcx * ppcy
+print("grid %d^2 ppc %d: %d particles, tile %dx%d, %d tiles, capacity %d" % (n, ppcx * ppcy, npart, tx.value, ty.value, nt.value, cap.value))
 
 
 def step():

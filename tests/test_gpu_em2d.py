@@ -189,6 +189,31 @@ def test_every_tile_shape_is_bit_exact_and_conserves_particles(ours, ref, tile, 
     b.delete()
 
 
+def test_fast_beam_through_small_tiles_loses_nothing(ours, ref, monkeypatch):
+    """a relativistic beam moving diagonally at dt/dx = 0.7 sends 23 % of every 4x4 tile to its neighbours each
+    step: the migrants segments are sized for the most a time step below the Courant limit can move
+    (1 - (1 - 1/TX)(1 - 1/TY) of a tile; 1/8 of the capacity, the old size, lost particles here and aborted)"""
+    monkeypatch.setenv("ZPIC_TILE_X", "4")
+    monkeypatch.setenv("ZPIC_TILE_Y", "4")
+    monkeypatch.setenv("ZPIC_TILE_SLACK", "1.25")
+    sp = [dict(name="beam", m_q=-1.0, ppc=(8, 8), ufl=(5.0, 5.0, 0.0), uth=(0.01, 0.01, 0.01), n_sort=0)]
+    a = H.Deck(ours, (32, 32), (3.2, 3.2), 0.07, sp)
+    b = H.Deck(ref, (32, 32), (3.2, 3.2), 0.07, sp)
+    a.iter(1)
+    b.iter(1)
+    sa, sb = a.snapshot(), b.snapshot()
+    assert np.array_equal(sa["parts"][0].view(np.uint8), sb["parts"][0].view(np.uint8))
+    a.iter(5)
+    b.iter(5)
+    sa, sb = a.snapshot(), b.snapshot()
+    assert sa["np"][0] == sb["np"][0] == 32 * 32 * 64
+    same = (sa["parts"][0]["ix"] == sb["parts"][0]["ix"]) & (sa["parts"][0]["iy"] == sb["parts"][0]["iy"])
+    assert (~same).sum() <= 3
+    assert H.rel_l2(sa["J"], sb["J"]) < TOL_FIELD
+    a.delete()
+    b.delete()
+
+
 def test_tiles_grow_when_the_plasma_piles_up(ours, ref, monkeypatch):
     """tiles start with 64 spare slots (ZPIC_TILE_SLACK=1): the first density fluctuation fills one; the
     particles that find it full are parked, the tile layout grows and they are re-appended before the next

@@ -402,6 +402,8 @@ k_yee_march(f3* __restrict__ Eout, f3* __restrict__ Bout, const f3* __restrict__
 	f3 Ec = ym_load(E, bi, R - 1, nrow, nrows);                    // E of the current row
 	f3 Bh_prev = {0, 0, 0}, En_prev = {0, 0, 0};
 	const int r_end = min(R + H, nrows);                           // rows [R, r_end) leave this stripe
+	// (issuing the three row loads of step r+1 before the arithmetic of step r was measured: 0.2467 against 0.2455 ms
+	//  per grid half at 4096^2, 40 instead of 32 registers - 64 resident warps per SM already cover the latency)
 	for (int r = R - 1; r <= r_end; r++) {
 		const f3 Eup = ym_load(E, bi, r + 1, nrow, nrows);
 		f3 Bh = ym_load(B, bi, r, nrow, nrows);

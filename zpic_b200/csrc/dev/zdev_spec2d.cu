@@ -194,7 +194,8 @@ static void soa_free(soa2d& a) {
 	cudaFree(a.rec); cudaFree(a.key); cudaFree(a.tag);
 	memset(&a, 0, sizeof(a));
 }
-// migrants segments: 1/div of every tile's capacity (8; ZPIC_MIG_DIV overrides).  Under a moving window a
+// migrants segments: 1/div of every tile's capacity (div from the tile shape, mig_div_for below; ZPIC_MIG_DIV
+// overrides).  Under a moving window a
 // shift empties a whole column of every tile on top of the ordinary leavers, and laser-driven plasma leaves a
 // tile at close to one cell per step along a whole edge: div = 2 there.
 static void mig_alloc(zdev_spec2d* s, int div);
@@ -259,9 +260,20 @@ static void mig_free(zdev_spec2d* s) {
 	cudaFree(s->mig.rec); cudaFree(s->mig.tag); cudaFree(s->mig.np);
 	memset(&s->mig, 0, sizeof(s->mig)); s->mig_cap = 0;
 }
+// A tile's migrants segment is 1/div of the tile's capacity.  No particle moves more than one cell per axis and step
+// (v < c and the Courant limit dt < dx, dt < dy), so at most 1 - (1 - 1/TX)(1 - 1/TY) of a tile's particles can
+// leave it in one step, whatever the plasma does: the largest div that covers this bound makes the segment
+// overflow (flag 2, particles lost) impossible for a stable deck - 8 for 16x16 tiles, 5 for 16x8, 4 for 8x8,
+// 2 for 8x4 and 4x4.  A window shift moves one more column of every tile: div 2 (zdev_spec2d_advance).
+// $ZPIC_MIG_DIV overrides the choice either way (8 saves 28 B x 7.5 % of the slots on a big 16x8 run).
+static int mig_div_for(int TX, int TY) {
+	const double leave = 1.0 - (1.0 - 1.0 / TX) * (1.0 - 1.0 / TY);
+	const int d = (int) (1.0 / leave);
+	return d < 2 ? 2 : (d > 8 ? 8 : d);
+}
 static void mig_alloc(zdev_spec2d* s, int div) {
 	mig_free(s);
-	if (const char* e = getenv("ZPIC_MIG_DIV")) { const int v = atoi(e); if (v >= 1 && v < div) div = v; }
+	if (const char* e = getenv("ZPIC_MIG_DIV")) { const int v = atoi(e); if (v >= 1 && (v < div || div > 2)) div = v; }
 	s->mig.div = div;
 	s->mig_cap = s->alloc_total / div + 32;
 	ZDEV_CHECK(cudaMalloc(&s->mig.rec, (size_t) s->mig_cap * sizeof(part_aos)));
@@ -356,7 +368,7 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	soa_alloc(s->q, s->alloc_total, s->track_ids);
 	s->cap_total = total;
 	s->max_cap = (int) max_cap;
-	mig_alloc(s, 8);
+	mig_alloc(s, mig_div_for(s->TX, s->TY));
 	s->ovf_cap = (unsigned int) (total / 32 > (1 << 20) ? total / 32 : (1 << 20));
 	ZDEV_CHECK(cudaMalloc(&s->ovf, (size_t) s->ovf_cap * sizeof(part_aos)));
 	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag, (size_t) s->ovf_cap * 4));
@@ -418,8 +430,9 @@ static void check_flags(zdev_spec2d* s, unsigned int flags) {
 		exit(-1);
 	}
 	if (flags & 2u) {
-		fprintf(stderr, "(*error*) zpic-b200: a tile's migrants segment overflowed (1/%d of the tile capacity); "
-		        "set ZPIC_MIG_DIV=1 (or raise ZPIC_TILE_SLACK, current %.2f) and rerun, aborting.\n", s->mig.div, s->slack);
+		fprintf(stderr, "(*error*) zpic-b200: a tile's migrants segment overflowed (1/%d of the tile capacity): more particles "
+		        "left a %dx%d tile in one step than a time step below the Courant limit allows (or ZPIC_MIG_DIV is set "
+		        "too high); set ZPIC_MIG_DIV=1 and rerun, aborting.\n", s->mig.div, s->TX, s->TY);
 		exit(-1);
 	}
 	if (flags & 4u) {
@@ -1263,6 +1276,10 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 	const int mig_cap = (int) ((tile_off[t + 1] - base) / mig.div);
 	const int64_t mig_base = base / mig.div;
 
+#ifndef PUSH_CARRY_PPC
+#define PUSH_CARRY_PPC 24
+#endif
+	const int carry_max = (nlive >= PUSH_CARRY_PPC * NC) ? 1 : -1;      // see deposit32 (the scan's last run)
 	// per-lane partial sums of the 8 contributions to cell `cur` (warp-uniform; -1: none)
 	float acc[8];
 	#pragma unroll
@@ -1280,22 +1297,42 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			return;
 		}
 		const int b = __ffs(heads) - 1;                // lanes below b continue cell `cur`
-		const bool lo = lane < b;
-		// masks as multipliers: the selects would all land on the (half-rate) ALU pipe
-		const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
-		if (cur >= 0) {
-			#pragma unroll
-			for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
-			flush_cell<TX>(acc, cur, lane, jt, JW3);
-		}
-		if ((heads & (heads - 1u)) == 0u) {
-			// one new cell starts at lane b and runs to the end of the warp: it becomes `cur`
-			#pragma unroll
-			for (int q = 0; q < 8; q++) acc[q] = w[q] * mhi;
-			cur = __shfl_sync(0xffffffffu, key, 31);
-			if (cur >= NC) cur = -1;                   // the range ended inside these 32
+#ifndef PUSH_RUN_LOOP_MAX
+#define PUSH_RUN_LOOP_MAX 1
+#endif
+		if (__popc(heads) <= PUSH_RUN_LOOP_MAX) {
+			// One cell starts here (PUSH_RUN_LOOP_MAX = 1; the loop takes any number, but two or three through it were
+			// no faster than the scan below at 32 particles per cell and 3 - 8 % slower at 16): run by run, the lanes of
+			// the run are added to acc (masks as multipliers: the selects would all land on the half-rate ALU pipe),
+			// every run but the last is reduced and flushed (9 shuffles for the 8 sums), the last one stays in acc and
+			// becomes `cur`.  The first run, lanes [0, b), continues the cell the warp was in.
+			unsigned h = heads;
+			int cell = cur;
+			float m = lane < b ? 1.0f : 0.0f;
+			for (;;) {
+				#pragma unroll
+				for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], m, acc[q]);
+				if (h == 0u) break;
+				if (cell >= 0 && cell < NC) flush_cell<TX>(acc, cell, lane, jt, JW3);
+				#pragma unroll
+				for (int q = 0; q < 8; q++) acc[q] = 0.0f;
+				const int s0 = __ffs(h) - 1;
+				h &= h - 1u;
+				const int e0 = h ? __ffs(h) - 1 : 32;
+				cell = __shfl_sync(0xffffffffu, key, s0);
+				m = (lane >= s0 && lane < e0) ? 1.0f : 0.0f;
+			}
+			cur = cell < NC ? cell : -1;               // (>= NC: the range ended inside these 32)
 		} else {
-			// several cells start here: segmented inclusive scan, the last lane of each run holds its totals
+			const bool lo = lane < b;
+			const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
+			if (cur >= 0) {
+				#pragma unroll
+				for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
+				flush_cell<TX>(acc, cur, lane, jt, JW3);
+			}
+			// many cells start here (a few particles per cell): segmented inclusive scan, the last lane of each run
+			// holds its totals
 			#pragma unroll
 			for (int q = 0; q < 8; q++) w[q] *= mhi;
 			const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
@@ -1308,11 +1345,21 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 					if (take) w[q] += u;
 				}
 			}
-			const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);
+			// Every finished run is added to J by its last lane (8 reductions from one lane: ~10 instructions, against
+			// ~50 for the butterfly).  The last run is not finished.  In a tile with >= PUSH_CARRY_PPC particles per cell,
+			// when at most one cell starts after lane 0, its totals stay in acc and its cell becomes `cur`: the next 32
+			// lanes then continue it and are likely to see one boundary only (the cheaper path above).  With more
+			// cells per 32 lanes the next group takes this path whatever happens, and a carried run would only add a
+			// butterfly to it - the run is flushed here.  Measured, G push/s at 64 / 32 / 16 / 8 per cell and ms per
+			// LWFA step (16 per cell): never carry 56.4 / 46.1 / 39.9 / 32.2 / 1.78, carry in every tile 56.8 / 48.3 /
+			// 38.9 / 31.7 / 1.94 (profiles/r02_push_lowppc_ab.txt).
+			const bool carry = __popc(heads & ~1u) <= carry_max;
+			const bool tail = (lane == 31 ? !carry : (bool) ((heads >> (lane + 1)) & 1u));
 			if (tail && act && !lo) jt_weights(jt, (lx + 1) * 3 + (ly + 1) * JW3, JW3, w);
 			#pragma unroll
-			for (int q = 0; q < 8; q++) acc[q] = 0.0f;
-			cur = -1;
+			for (int q = 0; q < 8; q++) acc[q] = (carry && lane == 31) ? w[q] : 0.0f;
+			cur = carry ? __shfl_sync(0xffffffffu, key, 31) : -1;
+			if (cur >= NC) cur = -1;
 		}
 	};
 
