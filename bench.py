@@ -208,6 +208,86 @@ def slab_parity(lib, A, rank, world):
     return res if rank == 0 else None
 
 
+class Ranks:
+    """Barrier and max over the ranks of the job.  Launched by torchrun: torch.distributed over NCCL (the task contract).
+    The children the default run starts for the other configurations ($ZPIC_BENCH_CHILD) use the library's own job
+    segment instead (zb_par_barrier / zb_par_allgather, csrc/host/common/zb_par.h): a second NCCL job next to the
+    parent's would need a rendezvous store of its own."""
+
+    def __init__(self, lib, world, local):
+        self.lib, self.world, self.torch, self.dist = lib, world, None, None
+        if world > 1 and not os.environ.get("ZPIC_BENCH_CHILD"):
+            import torch
+            import torch.distributed as dist
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            os.environ.setdefault("ZPIC_JOB", "bench" + os.environ.get("MASTER_PORT", "0"))
+            self.torch, self.dist = torch, dist
+        elif world > 1:
+            lib.zb_par_allgather.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+            lib.zb_par_allgather.restype = None
+            lib.zb_par_init()
+
+    def barrier(self):
+        self.lib.zdev_sync()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+        elif self.world > 1:
+            self.lib.zb_par_barrier()
+
+    def max(self, x):
+        if self.dist is not None:
+            t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        if self.world > 1:
+            mine, every = C.c_double(x), (C.c_double * self.world)()
+            self.lib.zb_par_allgather(C.byref(mine), 8, every)
+            return max(every)
+        return x
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def other_configs(rank, world, args):
+    """The other BASELINE configurations, measured by the default run too (so that the driver's record holds them):
+    N = 1: configs[4] (em1d two-stream, 2^31 particles) and configs[2] (LWFA) on the one GPU; N > 1: configs[2] and
+    configs[3] (Kelvin-Helmholtz; its 2^31-particle box needs two GPUs) slab-decomposed over the N ranks.  Every rank
+    starts `bench.py --workload ...` as a child with its own rank environment - a child that fails or hangs costs
+    its timeout, not the line of the main configuration.  Returns {name: summary} on rank 0."""
+    if args.no_extras:
+        return None
+    jobs = [("em1d", ["--workload", "em1d", "--steps", "10", "--warmup", "3"], 240),
+            ("lwfa", ["--workload", "lwfa", "--steps", "200", "--warmup", "5"], 240)]
+    if world > 1:
+        jobs = [jobs[1], ("kh", ["--workload", "kh", "--steps", "20", "--warmup", "3"], 300)]
+    out = {}
+    for name, extra, limit in jobs:
+        env = dict(os.environ, ZPIC_BENCH_CHILD="1", ZPIC_JOB="bx%s%s" % (os.environ.get("MASTER_PORT", "0"), name))
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--gpus", str(world)] + extra, env=env,
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=limit)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if rank == 0:
+                if r.returncode == 0 and lines:
+                    d = json.loads(lines[-1])
+                    out[name] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"],
+                                 "n_gpus": d["n_gpus"], "scaling": d["scaling"], "workload": d["config"]["workload"],
+                                 "roofline_frac": d["roofline"]["frac"], "roofline_what": d["roofline"].get("kernel"),
+                                 "cell_updates_per_s": (d.get("cells") or {}).get("value"), "wall_s": round(time.time() - t0, 1)}
+                else:
+                    out[name] = {"error": "exit code %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+        except subprocess.TimeoutExpired:
+            if rank == 0:
+                out[name] = {"error": "no result within %d s" % limit}
+    return out if rank == 0 else None
+
+
 def run_ours(args):
     from zpic_b200 import abi_em2d as A
     from zpic_b200 import load
@@ -305,6 +385,9 @@ def run_ours(args):
         parity = slab_parity(lib, A, rank, world)
 
     out = None
+    others = None
+    if world > 1:
+        others = other_configs(rank, world, args)         # (N = 1: after the host-buffer legs below)
     if rank == 0:
         peak, peak_src = peaks()
         per_launch = np_total / 2.0                       # particles per k_push2d launch (one species)
@@ -347,12 +430,15 @@ def run_ours(args):
             out["cells"] = cells
             out["e2e"] = run_e2e(lib, A, args, n)
             out["cpu_baseline"] = cpu_baseline(seconds=args.cpu_seconds, threads=1)
+            others = other_configs(rank, world, args)
         else:
             out["slab_parity"] = parity
             out["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 2 * 32 * world, "d2h_bytes_per_step": 2 * 48 * world,
                           "mode": "the timed loop IS the public C API (sim_iter on every rank); per step only kernel parameters "
                                   "go in and the 48-byte control block of every species comes out (read one step late); the "
                                   "host-buffer legs (host-initialised species, per-step diagnostics, report set) are measured at N=1"}
+        if others is not None:
+            out["other_configs"] = others
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
@@ -419,16 +505,10 @@ def run_deck(args):
     from zpic_b200 import abi_em2d as A
     from zpic_b200 import load
     rank, world, local = (int(os.environ.get(k, "0" if k != "WORLD_SIZE" else "1")) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        os.environ.setdefault("ZPIC_JOB", "bench" + os.environ.get("MASTER_PORT", "0"))
     lib = load("em2d")
     if lib.zdev_init(local) != 0:
         raise SystemExit("bench.py: no CUDA device - the CUDA path is the only path")
+    ranks = Ranks(lib, world, local)
     lib.zpic_b200_set_option(b"device_init", 1)
     lib.zpic_b200_set_option(b"lazy", 1)
     K, W = args.steps, max(args.warmup, 3)
@@ -452,20 +532,14 @@ def run_deck(args):
         sampler.start()
     launches0 = lib.zdev_launch_count()
     e0, e1 = lib.zdev_event_create(), lib.zdev_event_create()
-    if dist is not None:
-        dist.barrier()
-        torch.cuda.synchronize()
+    ranks.barrier()
     lib.zdev_event_record(e0)
     for _ in range(K):
         lib.sim_iter(C.byref(sim))
     lib.zdev_event_record(e1)
     ms = lib.zdev_event_elapsed_ms(e0, e1)
-    lib.zdev_sync()
-    if dist is not None:
-        dist.barrier()
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ranks.barrier()
+    ms = ranks.max(ms)
     clocks = sampler.finish() if rank == 0 else None
     launches = lib.zdev_launch_count() - launches0
     # particles of the whole box after the run (collective: the count is summed over the slabs by the library)
@@ -491,9 +565,7 @@ def run_deck(args):
                          "note": "per GPU, algorithmic bytes of the whole step: 56 B per push + (72 + 24 per smoothing pass) B per cell"},
             "gpu_launches": int(launches), "clocks": clocks, "e2e": None, "cpu_baseline": None}))
     lib.sim_delete(C.byref(sim))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ranks.close()
 
 
 def run_em1d(args, lib=None):
@@ -782,6 +854,8 @@ def main():
     ap.add_argument("--lwfa-ny", type=int, default=1024, dest="lwfa_ny")
     ap.add_argument("--kh-n", type=int, default=8192, dest="kh_n")
     ap.add_argument("--no-check", action="store_true", dest="no_check", help="N > 1: skip the slab-parity check")
+    ap.add_argument("--no-extras", action="store_true", dest="no_extras",
+                    help="skip `other_configs` (the other BASELINE configurations, run as children after the main one)")
     ap.add_argument("--init", type=int, default=0, help="device-side initialisation: 2 = the reference random stream "
                     "(default at N = 1), 1 = counter-based generator (default at N > 1)")
     ap.add_argument("--log2-cells", type=int, default=22, dest="log2_cells", help="em1d: log2 of the cell count")

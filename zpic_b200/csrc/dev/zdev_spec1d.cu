@@ -401,7 +401,7 @@ static void spec1_resolve_overflow(zdev_spec1d* s) {
 		for (int t = 0; t < s->ntiles; t++) {
 			int64_t cap = off[t + 1] - off[t];
 			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			if (ovf_t[t] > 0 || need > cap - cap / 5) {
+			if (ovf_t[t] > 0 || need > cap - cap / 10) {          // (within 10 %: at the 1.25 slack of large runs every tile sits at 80 %)
 				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 64;
 				grown = (grown + 31) & ~(int64_t) 31;
 				if (grown > cap) cap = grown;

@@ -124,6 +124,10 @@ struct zdev_spec2d {
 	int64_t mig_cap;                 // total entries allocated in mig.rec
 	part_aos* ovf; int* ovf_tag;     // particles that found their destination tile full (global cell indices):
 	unsigned int ovf_cap;            //   the host grows the tiles and re-appends them before the next push
+	part_aos* ovf_alt; int* ovf_tag_alt;   // the second list: a regrow swaps the two (the parked particles wait in one while
+	                                 //   the re-append may park into the other) - no copy, no allocation per event
+	int* ev_cnt; int64_t* ev_off;    // device scratch of a regrow event (per-tile counts, the new offsets), kept
+	int* ev_host;                    // pinned: 2 x ntiles counts come back here
 	int appended;                    // appends since the last overflow check
 	int* tile_list;                  // device: ids of the ordinary tiles, then of the few that outgrew them
 	int n_small, cap_small;          // how many ordinary tiles, and their largest capacity
@@ -200,6 +204,7 @@ static void soa_free(soa2d& a) {
 // tile at close to one cell per step along a whole edge: div = 2 there.
 static void mig_alloc(zdev_spec2d* s, int div);
 static void mig_free(zdev_spec2d* s);
+static int64_t tile_cap_limit(int TX, int TY);
 
 // supported tile shapes (kernel template instantiations)
 static bool tile_supported(int tx, int ty) {
@@ -289,6 +294,8 @@ static void spec_free_particles(zdev_spec2d* s) {
 	if (s->cap_total) { soa_free(s->p); soa_free(s->q); }
 	mig_free(s);
 	cudaFree(s->ovf); cudaFree(s->ovf_tag); s->ovf = nullptr; s->ovf_tag = nullptr; s->ovf_cap = 0;
+	cudaFree(s->ovf_alt); cudaFree(s->ovf_tag_alt); s->ovf_alt = nullptr; s->ovf_tag_alt = nullptr;
+	cudaFree(s->ev_cnt); cudaFree(s->ev_off); cudaFreeHost(s->ev_host); s->ev_cnt = nullptr; s->ev_off = nullptr; s->ev_host = nullptr;
 	s->cap_total = 0; s->alloc_total = 0;
 }
 
@@ -344,6 +351,7 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	std::vector<int64_t>& off = *s->h_off;
 	off.assign(s->ntiles + 1, 0);
 	int64_t max_cap = 0;
+	const int64_t cap_limit = tile_cap_limit(s->TX, s->TY);
 	for (int ty = 0; ty < s->nty; ty++) for (int tx = 0; tx < s->ntx; tx++) {
 		int t = tx + ty * s->ntx;
 		int cx = (tx + 1) * s->TX <= s->nx ? s->TX : s->nx - tx * s->TX;
@@ -351,14 +359,14 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 		int64_t nominal = (int64_t) cx * cy * s->ppc_hint;
 		int64_t want = cnt[t] > nominal ? cnt[t] : nominal;
 		int64_t cap = (int64_t) (want * slack) + 64;
-		cap = (cap + 31) & ~(int64_t) 31;
+		cap = std::min((cap + 31) & ~(int64_t) 31, cap_limit);
+		if (want + 32 > cap) {
+			fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed what a push CTA can index and hold in "
+			        "shared memory (%lld); use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) want, s->TX, s->TY, (long long) cap_limit);
+			exit(-1);
+		}
 		off[t + 1] = off[t] + cap;
 		if (cap > max_cap) max_cap = cap;
-	}
-	if (max_cap > 0xfff0) {
-		fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed the shared-memory index "
-		        "buffer; use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) max_cap, s->TX, s->TY);
-		exit(-1);
 	}
 	int64_t total = off[s->ntiles];
 	spec_free_particles(s);
@@ -662,56 +670,82 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 	}
 	while (h.flags & 1u) {
 		const auto t_start = std::chrono::steady_clock::now();
+		double t_ph[5] = {0, 0, 0, 0, 0};
+		auto mark = [&](int k) { t_ph[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
 		check_flags(s, h.flags & (2u | 4u | 8u));
 		const int64_t n_ovf = h.n_ovf;
+		// scratch of the events, allocated at the first one (a cudaMalloc / cudaFree pair behind queued work costs
+		// 1 - 4 ms each: measured on the LWFA deck, where a tile outgrows its segment every ~10 steps)
+		if (!s->ev_cnt) {
+			ZDEV_CHECK(cudaMalloc(&s->ev_cnt, (size_t) s->ntiles * sizeof(int)));
+			ZDEV_CHECK(cudaMalloc(&s->ev_off, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
+			ZDEV_CHECK(cudaHostAlloc((void**) &s->ev_host, (size_t) 2 * s->ntiles * sizeof(int), cudaHostAllocPortable));
+		}
+		if (!s->ovf_alt) {
+			ZDEV_CHECK(cudaMalloc(&s->ovf_alt, (size_t) s->ovf_cap * sizeof(part_aos)));
+			if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag_alt, (size_t) s->ovf_cap * 4));
+		}
 		// what every tile holds and what is waiting for it
-		std::vector<int> np_t(s->ntiles), ovf_t(s->ntiles, 0);
-		int* d_cnt; ZDEV_CHECK(cudaMalloc(&d_cnt, (size_t) s->ntiles * sizeof(int)));
+		int* d_cnt = s->ev_cnt;
+		const int* ovf_t = s->ev_host; const int* np_t = s->ev_host + s->ntiles;
 		ZDEV_CHECK(cudaMemsetAsync(d_cnt, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
 		ZDEV_LAUNCH(k_count_tiles, zdev_div_up(n_ovf, 256), 256, 0, s->ovf, n_ovf, s->TX, s->TY, s->ntx, d_cnt);
-		ZDEV_CHECK(cudaMemcpyAsync(ovf_t.data(), d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
-		ZDEV_CHECK(cudaMemcpyAsync(np_t.data(), s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaMemcpyAsync(s->ev_host, d_cnt, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
+		ZDEV_CHECK(cudaMemcpyAsync(s->ev_host + s->ntiles, s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(d_cnt);
-		// new layout
+		mark(0);
+		// New layout.  A tile that was full gets twice what it needs now and so do the tiles up to two away from it (the
+		// spike that filled it is moving or widening: they are next - on the LWFA deck 37 events in 200 steps without the
+		// neighbours, 27 with one ring); every tile within 10 % of its capacity gets 1.5 x its need;
+		// nothing grows past what a push CTA can take (tile_cap_limit).  (The
+		// 10 % used to be 25 %: with the 1.25 slack of large runs EVERY tile sits at 80 %, so the first event grew them
+		// all - 340 M -> 444 M slots and a reallocation on the LWFA deck.)
 		std::vector<int64_t> off_new(s->ntiles + 1, 0);
 		const std::vector<int64_t>& off = *s->h_off;
+		const int64_t cap_limit = tile_cap_limit(s->TX, s->TY);
+		std::vector<int64_t> want(s->ntiles);
+		for (int t = 0; t < s->ntiles; t++) {
+			const int64_t cap = off[t + 1] - off[t], need = (int64_t) np_t[t] + ovf_t[t];
+			want[t] = (need > cap - cap / 10) ? std::max(cap, need + need / 2 + 256) : cap;
+		}
+		for (int t = 0; t < s->ntiles; t++) {
+			if (ovf_t[t] <= 0) continue;
+			const int64_t grown = 2 * ((int64_t) np_t[t] + ovf_t[t]) + 256;
+			const int tx = t % s->ntx, ty = t / s->ntx;
+			for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
+				const int ux = tx + dx, uy = (ty + dy + 2 * s->nty) % s->nty;
+				if (ux < 0 || ux >= s->ntx) continue;
+				int64_t& w = want[ux + uy * s->ntx];
+				if (grown > w) w = grown;
+			}
+		}
 		int64_t max_cap = 0;
 		for (int t = 0; t < s->ntiles; t++) {
-			int64_t cap = off[t + 1] - off[t];
 			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			if (ovf_t[t] > 0 || need > cap - cap / 4) {          // full (double it), or above 75 %: it will be next
-				int64_t grown = (ovf_t[t] > 0 ? 2 * need : need + need / 2) + 256;
-				grown = (grown + 31) & ~(int64_t) 31;
-				if (grown > cap) cap = grown;
+			int64_t cap = std::min((want[t] + 31) & ~(int64_t) 31, cap_limit);
+			if (need + 32 > cap) {
+				fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed what a push CTA can index and hold in "
+				        "shared memory (%lld); use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) need, s->TX, s->TY, (long long) cap_limit);
+				exit(-1);
 			}
 			off_new[t + 1] = off_new[t] + cap;
 			if (cap > max_cap) max_cap = cap;
 		}
-		if (max_cap > 0xfff0) {
-			fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed the shared-memory index "
-			        "buffer; use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) max_cap, s->TX, s->TY);
-			exit(-1);
-		}
 		const int64_t total = off_new[s->ntiles];
 		const int64_t slots_before = s->cap_total;
-		// the parked particles move out of the way first (appending them may park others again)
-		part_aos* d_wait; int* d_wait_tag = nullptr;
-		ZDEV_CHECK(cudaMalloc(&d_wait, (size_t) n_ovf * sizeof(part_aos)));
-		ZDEV_CHECK(cudaMemcpyAsync(d_wait, s->ovf, (size_t) n_ovf * sizeof(part_aos), cudaMemcpyDeviceToDevice, zdev_strm));
-		if (s->ovf_tag) {
-			ZDEV_CHECK(cudaMalloc(&d_wait_tag, (size_t) n_ovf * 4));
-			ZDEV_CHECK(cudaMemcpyAsync(d_wait_tag, s->ovf_tag, (size_t) n_ovf * 4, cudaMemcpyDeviceToDevice, zdev_strm));
-		}
-		int64_t* d_off_new; ZDEV_CHECK(cudaMalloc(&d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
+		// the parked particles wait in their list while the other list takes over (appending them may park others again)
+		part_aos* d_wait = s->ovf; int* d_wait_tag = s->ovf_tag;
+		s->ovf = s->ovf_alt; s->ovf_tag = s->ovf_tag_alt;
+		s->ovf_alt = d_wait; s->ovf_tag_alt = d_wait_tag;
+		int64_t* d_off_new = s->ev_off;
 		ZDEV_CHECK(cudaMemcpyAsync(d_off_new, off_new.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, zdev_strm));
+		mark(1);
 		if (total <= s->alloc_total) {
 			// the new layout fits the allocation: population -> the other buffer (scratch between steps), swap
 			ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, s->q, d_off_new, s->tile_np);
 			ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
 			{ soa2d t = s->p; s->p = s->q; s->q = t; }
-			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-			cudaFree(d_off_new);
+			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));        // (off_new, a host vector, was the source of an async copy)
 		} else {
 			// population -> new, larger buffers (q is scratch between steps: release it first)
 			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
@@ -722,28 +756,29 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 			ZDEV_LAUNCH(k_relayout, s->ntiles, 256, 0, s->p, s->tile_off, pn, d_off_new, s->tile_np);
 			ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, d_off_new, (size_t) (s->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, zdev_strm));
 			ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-			cudaFree(d_off_new);
 			soa_free(s->p);
 			s->p = pn;
 			soa_alloc(s->q, s->alloc_total, s->track_ids);
 			mig_alloc(s, s->mig.div);
 		}
+		mark(2);
 		*s->h_off = off_new;
 		s->cap_total = total;
 		s->max_cap = (int) max_cap;
 		spec_build_tile_lists(s);
+		mark(3);
 		// clear the overflow state (energy, counts and export counters of the step stay) and append
 		ZDEV_CHECK(cudaMemsetAsync(&s->ctl->n_ovf, 0, 2 * sizeof(unsigned int), zdev_strm));    // n_ovf, flags
 		spec_append_dev(s, d_wait, n_ovf, 0, d_wait_tag);
 		s->appended = 0;
 		ZDEV_CHECK(cudaMemcpyAsync(&h, s->ctl, sizeof h, cudaMemcpyDeviceToHost, zdev_strm));
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
-		cudaFree(d_wait); cudaFree(d_wait_tag);
 		if (getenv("ZPIC_VERBOSE"))
 			fprintf(stderr, "zpic-b200: %lld particles found their %dx%d tile full: slots %lld -> %lld, largest tile %d, "
-			        "%d outgrown tiles, %.1f ms\n", (long long) n_ovf, s->TX, s->TY, (long long) slots_before, (long long) total,
-			        s->max_cap, s->ntiles - s->n_small,
-			        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+			        "%d outgrown tiles, %.1f ms (counts %.1f, scratch %.1f, relayout %.1f, lists %.1f)\n", (long long) n_ovf, s->TX, s->TY,
+			        (long long) slots_before, (long long) total, s->max_cap, s->ntiles - s->n_small,
+			        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(),
+			        t_ph[0], t_ph[1] - t_ph[0], t_ph[2] - t_ph[1], t_ph[3] - t_ph[2]);
 	}
 	s->last = h; s->last_valid = 1;
 }
@@ -1141,6 +1176,16 @@ static push_smem push_smem_layout(int TX, int TY, int max_cap) {
 	L.front = (L.front + 15) & ~(size_t) 15;
 	L.total = L.front + (size_t) (max_cap + 128) * 4;     // the holes are sorted too (behind the live entries)
 	return L;
+}
+// the largest tile capacity a push CTA can take: 16-bit slot numbers in perm[], and its shared memory (227 KB per CTA,
+// of which up to 3.1 KB are the kernel's static arrays)
+static int64_t tile_cap_limit(int TX, int TY) {
+	int64_t lo = 32, hi = 0xfff0 & ~31;
+	while (lo < hi) {
+		const int64_t mid = ((lo + hi) / 2 + 31) & ~(int64_t) 31;
+		if (push_smem_layout(TX, TY, (int) mid).total <= (size_t) 223 * 1024) lo = mid; else hi = mid - 32;
+	}
+	return lo;
 }
 
 // One CTA per tile.
