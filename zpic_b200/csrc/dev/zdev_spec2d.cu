@@ -1342,40 +1342,24 @@ k_push2d(soa2d A, soa2d Bo, const int64_t* __restrict__ tile_off, const int* __r
 			return;
 		}
 		const int b = __ffs(heads) - 1;                // lanes below b continue cell `cur`
-#ifndef PUSH_RUN_LOOP_MAX
-#define PUSH_RUN_LOOP_MAX 1
-#endif
-		if (__popc(heads) <= PUSH_RUN_LOOP_MAX) {
-			// One cell starts here (PUSH_RUN_LOOP_MAX = 1; the loop takes any number, but two or three through it were
-			// no faster than the scan below at 32 particles per cell and 3 - 8 % slower at 16): run by run, the lanes of
-			// the run are added to acc (masks as multipliers: the selects would all land on the half-rate ALU pipe),
-			// every run but the last is reduced and flushed (9 shuffles for the 8 sums), the last one stays in acc and
-			// becomes `cur`.  The first run, lanes [0, b), continues the cell the warp was in.
-			unsigned h = heads;
-			int cell = cur;
-			float m = lane < b ? 1.0f : 0.0f;
-			for (;;) {
-				#pragma unroll
-				for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], m, acc[q]);
-				if (h == 0u) break;
-				if (cell >= 0 && cell < NC) flush_cell<TX>(acc, cell, lane, jt, JW3);
-				#pragma unroll
-				for (int q = 0; q < 8; q++) acc[q] = 0.0f;
-				const int s0 = __ffs(h) - 1;
-				h &= h - 1u;
-				const int e0 = h ? __ffs(h) - 1 : 32;
-				cell = __shfl_sync(0xffffffffu, key, s0);
-				m = (lane >= s0 && lane < e0) ? 1.0f : 0.0f;
-			}
-			cur = cell < NC ? cell : -1;               // (>= NC: the range ended inside these 32)
+		const bool lo = lane < b;
+		// masks as multipliers: the selects would all land on the (half-rate) ALU pipe
+		const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
+		if (cur >= 0) {
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
+			flush_cell<TX>(acc, cur, lane, jt, JW3);
+		}
+		if ((heads & (heads - 1u)) == 0u) {
+			// one new cell starts at lane b and runs to the end of the warp: it becomes `cur`.  (Two or three new cells
+			// through a loop of such butterflies instead of the scan below: no faster at 32 particles per cell, 3 - 8 %
+			// slower at 16, and the loop form cost the one-cell case 11 instructions per 32 particles -
+			// profiles/r02_push_lowppc_ab.txt.)
+			#pragma unroll
+			for (int q = 0; q < 8; q++) acc[q] = w[q] * mhi;
+			cur = __shfl_sync(0xffffffffu, key, 31);
+			if (cur >= NC) cur = -1;                   // the range ended inside these 32
 		} else {
-			const bool lo = lane < b;
-			const float mlo = lo ? 1.0f : 0.0f, mhi = lo ? 0.0f : 1.0f;
-			if (cur >= 0) {
-				#pragma unroll
-				for (int q = 0; q < 8; q++) acc[q] = __fmaf_rn(w[q], mlo, acc[q]);
-				flush_cell<TX>(acc, cur, lane, jt, JW3);
-			}
 			// many cells start here (a few particles per cell): segmented inclusive scan, the last lane of each run
 			// holds its totals
 			#pragma unroll
@@ -1755,6 +1739,8 @@ static void launch_push(zdev_spec2d* s, const f3* E, const f3* B, f3* J, const p
 		slot = s->ev_next; s->ev_next = (s->ev_next + 1) % EV_RING; s->ev_pending++;
 		ZDEV_CHECK(cudaEventRecord((*s->ev)[2 * slot], zdev_strm));
 	}
+	// (the few outgrown tiles of a density spike - one long-running CTA each - started first on a side stream so that the
+	//  ordinary tiles fill the machine around them: measured on the LWFA probe, 1.874 against 1.860 ms/step; not kept)
 	for (int grp = 0; grp < 2; grp++) {
 		const int ntl = grp ? s->ntiles - s->n_small : s->n_small;
 		if (ntl <= 0) continue;
