@@ -380,6 +380,13 @@ static void spec_layout(zdev_spec2d* s, const std::vector<int>& cnt, int64_t np)
 	s->ovf_cap = (unsigned int) (total / 32 > (1 << 20) ? total / 32 : (1 << 20));
 	ZDEV_CHECK(cudaMalloc(&s->ovf, (size_t) s->ovf_cap * sizeof(part_aos)));
 	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag, (size_t) s->ovf_cap * 4));
+	// the second overflow list and the scratch of the regrow events, here and not at the first event: allocating
+	// behind queued work stalled the first event of a run for up to 36 ms (spec_resolve_overflow)
+	ZDEV_CHECK(cudaMalloc(&s->ovf_alt, (size_t) s->ovf_cap * sizeof(part_aos)));
+	if (s->track_ids) ZDEV_CHECK(cudaMalloc(&s->ovf_tag_alt, (size_t) s->ovf_cap * 4));
+	ZDEV_CHECK(cudaMalloc(&s->ev_cnt, (size_t) s->ntiles * sizeof(int)));
+	ZDEV_CHECK(cudaMalloc(&s->ev_off, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
+	ZDEV_CHECK(cudaHostAlloc((void**) &s->ev_host, (size_t) 2 * s->ntiles * sizeof(int), cudaHostAllocPortable));
 	ZDEV_CHECK(cudaMemcpyAsync(s->tile_off, off.data(), (size_t) (s->ntiles + 1) * sizeof(int64_t),
 	                           cudaMemcpyHostToDevice, zdev_strm));
 	ZDEV_CHECK(cudaMemsetAsync(s->tile_np, 0, (size_t) s->ntiles * sizeof(int), zdev_strm));
@@ -674,8 +681,8 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		auto mark = [&](int k) { t_ph[k] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
 		check_flags(s, h.flags & (2u | 4u | 8u));
 		const int64_t n_ovf = h.n_ovf;
-		// scratch of the events, allocated at the first one (a cudaMalloc / cudaFree pair behind queued work costs
-		// 1 - 4 ms each: measured on the LWFA deck, where a tile outgrows its segment every ~10 steps)
+		// the scratch of the events is kept (a cudaMalloc / cudaFree pair behind queued work costs 1 - 4 ms each: measured
+		// on the LWFA deck, where a tile outgrows its segment every ~10 steps); normally allocated with the layout
 		if (!s->ev_cnt) {
 			ZDEV_CHECK(cudaMalloc(&s->ev_cnt, (size_t) s->ntiles * sizeof(int)));
 			ZDEV_CHECK(cudaMalloc(&s->ev_off, (size_t) (s->ntiles + 1) * sizeof(int64_t)));
