@@ -235,6 +235,10 @@ void zdev_spec2d_deposit_charge( zdev_spec2d* s, float q, int moving_window, flo
 /* the multi-threaded host copy the charge deposit uses between the caller's pageable array and its pinned staging
    buffer (host only, no device call: exercised on the CPU by tests/test_abi_symbols.py) */
 void zdev_spec2d_par_memcpy( void* dst, const void* src, size_t bytes );
+/* the tile layout after a regrow event (a density spike filled a tile): host only, no device call - see
+   zdev_spec2d.cu; returns the largest tile capacity or -1 when tile *bad_tile needs more than a push CTA can take */
+int64_t zdev_spec2d_plan_regrow( int ntx, int nty, int TX, int TY, const int64_t* off, const int* np, const int* ovf,
+                                 int64_t* off_new, int* bad_tile );
 /* spec_deposit_pha on the device (em2d/particles.c:1569-1632): quant1/2 = the reference's
  * X1 (1), X2 (2), U1 (4), U2 (5), U3 (6), pha_buf is a host pha_nx[0]*pha_nx[1] float array that is ADDED to */
 void zdev_spec2d_deposit_pha( zdev_spec2d* s, int quant1, int quant2, const int pha_nx[2], const float pha_range[2][2],

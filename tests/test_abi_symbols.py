@@ -97,3 +97,47 @@ def test_host_copy_of_the_charge_deposit_covers_every_byte():
         lib.zdev_spec2d_par_memcpy(dst.ctypes.data, src.ctypes.data, nbytes)
         assert np.array_equal(dst[:nbytes], src), nbytes
         assert not dst[nbytes:].any(), nbytes
+
+
+def test_regrow_plan_of_the_particle_tiles():
+    """zdev_spec2d_plan_regrow (host only): the tile layout after a density spike filled a tile - the full tile and the
+    tiles up to two away get twice its need, tiles within 10 % of their capacity 1.5 x theirs, nothing shrinks, nothing
+    grows past what a push CTA can hold (then the run stops instead), y wraps and x does not"""
+    import numpy as np
+    lib = C.CDLL(zbuild.lib_path("em2d"))
+    f = lib.zdev_spec2d_plan_regrow
+    f.restype = C.c_int64
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    ntx, nty, cap0 = 8, 6, 5184                                    # 16x16 tiles at 16 per cell, slack 1.25
+    off = (np.arange(ntx * nty + 1) * cap0).astype(np.int64)
+
+    def plan(npt, ovf):
+        new = np.zeros(ntx * nty + 1, dtype=np.int64)
+        bad = C.c_int(-1)
+        m = f(ntx, nty, 16, 16, off.ctypes.data, npt.ctypes.data, ovf.ctypes.data, new.ctypes.data, C.byref(bad))
+        return m, np.diff(new).reshape(nty, ntx), bad.value
+
+    npt = np.full(ntx * nty, 4096, dtype=np.int32)                 # every tile at 79 % (the nominal fill): nothing to do
+    ovf = np.zeros(ntx * nty, dtype=np.int32)
+    m, cap, _ = plan(npt, ovf)
+    assert m == cap0 and (cap == cap0).all()
+    npt[3 + 0 * ntx] = 4800                                        # one tile within 10 % of its capacity: 1.5 x its need, alone
+    m, cap, _ = plan(npt, ovf)
+    assert cap[0, 3] == (4800 + 2400 + 256 + 31) // 32 * 32 and (cap.ravel() != cap0).sum() == 1
+    npt[3 + 0 * ntx] = 4096
+    npt[0 + 5 * ntx], ovf[0 + 5 * ntx] = 5184, 100                 # a full tile in the corner x = 0, y = last row
+    m, cap, _ = plan(npt, ovf)
+    grown = (2 * 5284 + 256 + 31) // 32 * 32
+    assert m == grown
+    want = np.full((nty, ntx), cap0)
+    for y in (3, 4, 5, 0, 1):                                      # two rows either side, wrapping in y
+        want[y, 0:3] = grown                                       # ... and two columns to the right only (x does not wrap)
+    assert (cap == want).all()
+    assert (cap % 32 == 0).all() and (cap >= cap0).all()
+    npt[10], ovf[10] = 30000, 50                                   # twice its need would pass the limit: clamped, not fatal
+    m, cap, bad = plan(npt, ovf)
+    limit = m
+    assert 30050 + 32 <= limit < 2 * 30050 and cap.ravel()[10] == limit and limit % 32 == 0
+    npt[10] = limit                                                # a tile that NEEDS more than a CTA can take stops the run
+    m, cap, bad = plan(npt, ovf)
+    assert m == -1 and bad == 10

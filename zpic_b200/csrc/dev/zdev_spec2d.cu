@@ -664,6 +664,47 @@ __global__ void k_relayout(soa2d src, const int64_t* __restrict__ off_src, soa2d
 // list by the append / migrate kernels; here the tiles that need it get 1.5x the room they need now, the
 // population is copied to the new layout and the parked particles are appended.  Called (with one small
 // device -> host copy) after every advance, so nothing ever misses a push.
+// The layout after a regrow event (host only, no device call: exercised on the CPU by tests/test_abi_symbols.py).
+// off[] = the ntx*nty+1 offsets of the current layout, np[] / ovf[] = what every tile holds / what is parked for it,
+// off_new[] = the new offsets.  A tile that was full gets twice what it needs now and so do the tiles up to two away
+// from it (the spike that filled it is moving or widening: they are next - on the LWFA deck 37 events in 200 steps
+// without the neighbours, 27 with one ring, 17 with two); every tile within 10 % of its capacity gets 1.5 x its need
+// (the 10 % used to be 25 %: with the 1.25 slack of large runs EVERY tile sits at 80 %, so the first event grew them
+// all - 340 M -> 444 M slots and a reallocation on the LWFA deck); nothing shrinks, and nothing grows past what a push
+// CTA can take (tile_cap_limit).  Returns the largest capacity, or -1 (*bad_tile = which) when a tile NEEDS more than
+// that.  x does not wrap (slab edges, moving windows), y is periodic like the box.
+extern "C" int64_t zdev_spec2d_plan_regrow(int ntx, int nty, int TX, int TY, const int64_t* off, const int* np, const int* ovf,
+                                           int64_t* off_new, int* bad_tile) {
+	const int ntiles = ntx * nty;
+	const int64_t cap_limit = tile_cap_limit(TX, TY);
+	std::vector<int64_t> want(ntiles);
+	for (int t = 0; t < ntiles; t++) {
+		const int64_t cap = off[t + 1] - off[t], need = (int64_t) np[t] + ovf[t];
+		want[t] = (need > cap - cap / 10) ? std::max(cap, need + need / 2 + 256) : cap;
+	}
+	for (int t = 0; t < ntiles; t++) {
+		if (ovf[t] <= 0) continue;
+		const int64_t grown = 2 * ((int64_t) np[t] + ovf[t]) + 256;
+		const int tx = t % ntx, ty = t / ntx;
+		for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
+			const int ux = tx + dx, uy = (ty + dy + 2 * nty) % nty;
+			if (ux < 0 || ux >= ntx) continue;
+			int64_t& w = want[ux + uy * ntx];
+			if (grown > w) w = grown;
+		}
+	}
+	int64_t max_cap = 0;
+	off_new[0] = 0;
+	for (int t = 0; t < ntiles; t++) {
+		const int64_t need = (int64_t) np[t] + ovf[t];
+		const int64_t cap = std::min((want[t] + 31) & ~(int64_t) 31, cap_limit);
+		if (need + 32 > cap) { if (bad_tile) *bad_tile = t; return -1; }
+		off_new[t + 1] = off_new[t] + cap;
+		if (cap > max_cap) max_cap = cap;
+	}
+	return max_cap;
+}
+
 static void spec_resolve_overflow(zdev_spec2d* s) {
 	s->appended = 0;
 	ctl2d h;
@@ -701,42 +742,14 @@ static void spec_resolve_overflow(zdev_spec2d* s) {
 		ZDEV_CHECK(cudaMemcpyAsync(s->ev_host + s->ntiles, s->tile_np, (size_t) s->ntiles * sizeof(int), cudaMemcpyDeviceToHost, zdev_strm));
 		ZDEV_CHECK(cudaStreamSynchronize(zdev_strm));
 		mark(0);
-		// New layout.  A tile that was full gets twice what it needs now and so do the tiles up to two away from it (the
-		// spike that filled it is moving or widening: they are next - on the LWFA deck 37 events in 200 steps without the
-		// neighbours, 27 with one ring); every tile within 10 % of its capacity gets 1.5 x its need;
-		// nothing grows past what a push CTA can take (tile_cap_limit).  (The
-		// 10 % used to be 25 %: with the 1.25 slack of large runs EVERY tile sits at 80 %, so the first event grew them
-		// all - 340 M -> 444 M slots and a reallocation on the LWFA deck.)
 		std::vector<int64_t> off_new(s->ntiles + 1, 0);
-		const std::vector<int64_t>& off = *s->h_off;
-		const int64_t cap_limit = tile_cap_limit(s->TX, s->TY);
-		std::vector<int64_t> want(s->ntiles);
-		for (int t = 0; t < s->ntiles; t++) {
-			const int64_t cap = off[t + 1] - off[t], need = (int64_t) np_t[t] + ovf_t[t];
-			want[t] = (need > cap - cap / 10) ? std::max(cap, need + need / 2 + 256) : cap;
-		}
-		for (int t = 0; t < s->ntiles; t++) {
-			if (ovf_t[t] <= 0) continue;
-			const int64_t grown = 2 * ((int64_t) np_t[t] + ovf_t[t]) + 256;
-			const int tx = t % s->ntx, ty = t / s->ntx;
-			for (int dy = -2; dy <= 2; dy++) for (int dx = -2; dx <= 2; dx++) {
-				const int ux = tx + dx, uy = (ty + dy + 2 * s->nty) % s->nty;
-				if (ux < 0 || ux >= s->ntx) continue;
-				int64_t& w = want[ux + uy * s->ntx];
-				if (grown > w) w = grown;
-			}
-		}
-		int64_t max_cap = 0;
-		for (int t = 0; t < s->ntiles; t++) {
-			const int64_t need = (int64_t) np_t[t] + ovf_t[t];
-			int64_t cap = std::min((want[t] + 31) & ~(int64_t) 31, cap_limit);
-			if (need + 32 > cap) {
-				fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed what a push CTA can index and hold in "
-				        "shared memory (%lld); use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) need, s->TX, s->TY, (long long) cap_limit);
-				exit(-1);
-			}
-			off_new[t + 1] = off_new[t] + cap;
-			if (cap > max_cap) max_cap = cap;
+		int bad_tile = -1;
+		const int64_t max_cap = zdev_spec2d_plan_regrow(s->ntx, s->nty, s->TX, s->TY, s->h_off->data(), np_t, ovf_t, off_new.data(), &bad_tile);
+		if (max_cap < 0) {
+			fprintf(stderr, "(*error*) zpic-b200: %lld particles in one %dx%d tile exceed what a push CTA can index and hold in "
+			        "shared memory (%lld); use smaller tiles (ZPIC_TILE_X/Y)\n", (long long) np_t[bad_tile] + ovf_t[bad_tile],
+			        s->TX, s->TY, (long long) tile_cap_limit(s->TX, s->TY));
+			exit(-1);
 		}
 		const int64_t total = off_new[s->ntiles];
 		const int64_t slots_before = s->cap_total;
