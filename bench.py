@@ -453,9 +453,10 @@ def _new_species(lib, A, n):
     return C.cast(libc.calloc(n, C.sizeof(A.Species)), C.POINTER(A.Species))
 
 
-def build_lwfa(lib, A, nx, ny):
+def build_lwfa(lib, A, nx, ny, a0=5.0):
     """BASELINE configs[2]: the reference's em2d/input/lwfa-large.c geometry (dx = 0.01, 0.05) scaled to nx x ny cells,
-    4x4 particles per cell, plasma from x = 0.5 on (STEP), gaussian laser a0 = 3 launched 3 c/wp from the right edge,
+    4x4 particles per cell, plasma from x = 0.5 on (STEP: the pulse is inside the plasma from the first step), the gaussian
+    laser of that deck (a0 = 5, omega0 10, W0 4, fwhm 2, input/lwfa-large.c:40-50) launched 3 c/wp from the right edge,
     moving window, compensated smoothing level 4 (input/lwfa.c:15-63 settings)"""
     lib.set_rand_seed(12345, 67890)
     cnx, box, dt = (C.c_int * 2)(nx, ny), (C.c_float * 2)(nx * 0.01, ny * 0.05), 0.009
@@ -466,7 +467,7 @@ def build_lwfa(lib, A, nx, ny):
     sim = A.Simulation()
     lib.sim_new(C.byref(sim), cnx, box, dt, 1.0e9, 0, species, 1)
     laser = A.Laser()
-    laser.type, laser.start, laser.fwhm, laser.a0, laser.omega0 = A.GAUSSIAN, box[0] - 3.0, 2.0, 3.0, 10.0
+    laser.type, laser.start, laser.fwhm, laser.a0, laser.omega0 = A.GAUSSIAN, box[0] - 3.0, 2.0, a0, 10.0
     laser.W0, laser.focus, laser.axis, laser.polarization = 4.0, box[0] - 10.0, box[1] / 2, np.pi / 2
     lib.sim_add_laser(C.byref(sim), C.byref(laser))
     lib.sim_set_moving_window(C.byref(sim))
@@ -515,9 +516,9 @@ def run_deck(args):
     t0 = time.time()
     if args.workload == "lwfa":
         nx, ny = args.lwfa_nx, args.lwfa_ny
-        sim, species, nsp, ppc_total, dt, keep = build_lwfa(lib, A, nx, ny)
-        what = ("em2d LWFA %dx%d cells, 16 ppc, laser a0 3, moving window with host injection of the new column, "
-                "compensated smoothing level 4 (BASELINE configs[2])" % (nx, ny))
+        sim, species, nsp, ppc_total, dt, keep = build_lwfa(lib, A, nx, ny, args.lwfa_a0)
+        what = ("em2d LWFA %dx%d cells, 16 ppc, laser a0 %g, moving window with host injection of the new column, "
+                "compensated smoothing level 4 (BASELINE configs[2])" % (nx, ny, args.lwfa_a0))
     else:
         nx = ny = args.kh_n
         sim, species, nsp, ppc_total, dt, keep = build_kh(lib, A, nx)
@@ -852,6 +853,8 @@ def main():
                          "(slab-decomposed over the ranks of the job), em1d = configs[4] (one GPU)")
     ap.add_argument("--lwfa-nx", type=int, default=16384, dest="lwfa_nx")
     ap.add_argument("--lwfa-ny", type=int, default=1024, dest="lwfa_ny")
+    ap.add_argument("--lwfa-a0", type=float, default=5.0, dest="lwfa_a0",
+                    help="lwfa: normalised vector potential of the laser (5 = em2d/input/lwfa-large.c:44; the round-2 runs before this option existed used 3)")
     ap.add_argument("--kh-n", type=int, default=8192, dest="kh_n")
     ap.add_argument("--no-check", action="store_true", dest="no_check", help="N > 1: skip the slab-parity check")
     ap.add_argument("--no-extras", action="store_true", dest="no_extras",
